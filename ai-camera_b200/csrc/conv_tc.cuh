@@ -1,0 +1,43 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+// See conv_tc.cu for the design notes.
+#pragma once
+#include "common.cuh"
+
+namespace aicam {
+
+// Packed weights: bf16 [q_pad][cout][8] where a "chunk" q holds 8 consecutive K elements
+// (16 bytes), K index = tap * cin_pad + c.  q_pad is even (one tcgen05.mma consumes K = 16).
+struct PackedConv {
+  __nv_bfloat16* w = nullptr;  // device
+  float* bias = nullptr;       // device, [cout]
+  int cin = 0;        // real input channels
+  int cin_pad = 0;    // 4 (stem: 3 -> 4) or a multiple of 8
+  int cout = 0, ksize = 1, stride = 1;
+  int q = 0, q_pad = 0;
+};
+
+struct ConvLaunch {
+  const __nv_bfloat16* in;
+  long long in_img_stride;  // elements between images
+  int in_cstride, in_coff;  // channels per pixel in the buffer, first channel used
+  int batch, h, w;          // input spatial size
+  int ho, wo;
+  void* out;
+  long long out_img_stride;
+  int out_cstride, out_coff;
+  int out_f32;
+  const __nv_bfloat16* res;
+  long long res_img_stride;
+  int res_cstride, res_coff;
+  int res_mode;  // 0 none, 1 act(conv)+res, 2 act(conv+res)
+  int act;       // 0 none, 1 SiLU, 2 ReLU
+  const int* batch_dev = nullptr;  // optional device-side image count (<= batch)
+};
+
+// host: pack OIHW fp32 weights (host) into the device layout above
+int pack_conv_weights(const float* w_oihw, const float* bias, int cout, int cin, int ksize, int stride,
+                      PackedConv* out);
+void free_packed_conv(PackedConv* p);
+int launch_conv(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream);
+
+}  // namespace aicam

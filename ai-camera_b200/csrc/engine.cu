@@ -1,0 +1,479 @@
+// Engine: loads a flat ".aicw" weight blob and runs YOLOv8 detect or the DeepSORT ReID net as
+// a static list of kernel launches over preallocated NHWC bf16 buffers.
+//
+// Replaces the TensorRT engine object of the reference
+// (/root/reference/src/trt_utils/trt_engine.py: _init_engine :45-60 -> engine_create,
+//  infer :151-203 -> yolo_forward / reid_forward).  Architectures are the named public ones
+// (SURVEY.md Appendix D); the reference itself holds no network definition.
+//
+// Data layout in HBM: every activation is NHWC bf16, [max_batch][H][W][C].  Concatenations
+// (C2f, SPPF, the FPN/PAN joins) are never materialised by a copy: producers write straight
+// into channel slices of the wider buffer (conv out_coff/out_cstride), and consumers read a
+// slice (in_coff/in_cstride).
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <vector>
+
+#include "conv_tc.cuh"
+#include "layers.cuh"
+
+namespace aicam {
+
+namespace {
+
+struct BlobTensor {
+  std::vector<int> dims;
+  const float* data;
+  size_t count;
+};
+
+struct Buffer {
+  __nv_bfloat16* ptr;
+  int h, w, c;
+};
+
+struct View {
+  int buf = -1;        // index into buffers; -1 = external input, -2 = external output
+  int coff = 0;        // first channel
+  long long eoff = 0;  // extra element offset (Detect levels inside the head tensor)
+};
+
+struct Op {
+  enum Type { CONV, MAXPOOL, UPSAMPLE, AVGL2 } type;
+  int conv = -1;
+  View in, out, res;
+  int h = 0, w = 0, c = 0;  // input spatial size / channels moved (pool, upsample)
+  int k = 0, stride = 1;
+  int act = 0, res_mode = 0, out_f32 = 0;
+};
+
+}  // namespace
+
+}  // namespace aicam
+
+struct aicam_engine {
+  int kind = 0, device = 0, max_batch = 0;
+  uint32_t params[8] = {0};
+  std::vector<aicam::PackedConv> convs;
+  std::map<std::string, int> conv_by_name;
+  std::vector<aicam::Buffer> buffers;
+  std::vector<aicam::Op> ops;
+  double macs_per_item = 0.0;
+  // external tensor geometry
+  int in_h = 0, in_w = 0;
+  int out_cstride = 0;         // yolov8: 64 + nc
+  long long out_img_stride = 0;
+  int num_anchors = 0;
+  int feat_buf = -1;           // reid: buffer feeding the average pool
+};
+
+namespace aicam {
+
+namespace {
+
+struct Builder {
+  aicam_engine* e;
+  std::map<std::string, BlobTensor>* tensors;
+  int err = AICAM_OK;
+
+  int buf(int h, int w, int c) {
+    Buffer b{nullptr, h, w, c};
+    const size_t bytes = static_cast<size_t>(e->max_batch) * h * w * c * sizeof(__nv_bfloat16);
+    if (cudaMalloc(&b.ptr, bytes) != cudaSuccess) {
+      err = fail(AICAM_ERR_CUDA, "engine: cudaMalloc of an activation buffer failed");
+      b.ptr = nullptr;
+    } else {
+      cudaMemset(b.ptr, 0, bytes);
+    }
+    e->buffers.push_back(b);
+    return static_cast<int>(e->buffers.size()) - 1;
+  }
+
+  int conv(const std::string& name, View in, int h, int w, View out, int cin, int cout, int k, int s, int act,
+           View res = View(), int res_mode = 0, int out_f32 = 0) {
+    if (err) return err;
+    auto wi = tensors->find(name + ".weight");
+    auto bi = tensors->find(name + ".bias");
+    if (wi == tensors->end() || bi == tensors->end())
+      return err = fail(AICAM_ERR_IO, "engine: blob has no tensor " + name + ".weight/.bias");
+    const BlobTensor& wt = wi->second;
+    if (wt.dims.size() != 4 || wt.dims[0] != cout || wt.dims[1] != cin || wt.dims[2] != k || wt.dims[3] != k ||
+        static_cast<int>(bi->second.count) != cout)
+      return err = fail(AICAM_ERR_IO, "engine: tensor " + name + " has an unexpected shape");
+    PackedConv pc;
+    if (int rc = pack_conv_weights(wt.data, bi->second.data, cout, cin, k, s, &pc)) return err = rc;
+    e->convs.push_back(pc);
+    e->conv_by_name[name] = static_cast<int>(e->convs.size()) - 1;
+    Op op;
+    op.type = Op::CONV;
+    op.conv = static_cast<int>(e->convs.size()) - 1;
+    op.in = in; op.out = out; op.res = res;
+    op.h = h; op.w = w; op.k = k; op.stride = s;
+    op.act = act; op.res_mode = res_mode; op.out_f32 = out_f32;
+    e->ops.push_back(op);
+    const int ho = (h + 2 * (k / 2) - k) / s + 1, wo = (w + 2 * (k / 2) - k) / s + 1;
+    e->macs_per_item += static_cast<double>(ho) * wo * cout * cin * k * k;
+    return AICAM_OK;
+  }
+
+  void pool(View in, View out, int h, int w, int c, int k, int s) {
+    Op op; op.type = Op::MAXPOOL; op.in = in; op.out = out; op.h = h; op.w = w; op.c = c; op.k = k; op.stride = s;
+    e->ops.push_back(op);
+  }
+  void upsample(View in, View out, int h, int w, int c) {
+    Op op; op.type = Op::UPSAMPLE; op.in = in; op.out = out; op.h = h; op.w = w; op.c = c;
+    e->ops.push_back(op);
+  }
+
+  static View V(int b, int coff = 0, long long eoff = 0) { View v; v.buf = b; v.coff = coff; v.eoff = eoff; return v; }
+
+  // Ultralytics C2f: cv1 -> split -> n chained Bottlenecks (3x3, 3x3, optional shortcut) -> cv2 on the concat
+  void c2f(const std::string& name, View in, int cin, View out, int cout, int n, bool shortcut, int h, int w) {
+    const int c = cout / 2;
+    const int cat = buf(h, w, (2 + n) * c);
+    const int tmp = buf(h, w, c);
+    conv(name + ".cv1.conv", in, h, w, V(cat, 0), cin, 2 * c, 1, 1, 1);
+    for (int j = 0; j < n; ++j) {
+      const std::string m = name + ".m." + std::to_string(j);
+      conv(m + ".cv1.conv", V(cat, (1 + j) * c), h, w, V(tmp, 0), c, c, 3, 1, 1);
+      conv(m + ".cv2.conv", V(tmp, 0), h, w, V(cat, (2 + j) * c), c, c, 3, 1, 1,
+           shortcut ? V(cat, (1 + j) * c) : View(), shortcut ? 1 : 0);
+    }
+    conv(name + ".cv2.conv", V(cat, 0), h, w, out, (2 + n) * c, cout, 1, 1, 1);
+  }
+
+  void build_yolov8() {
+    const int c1 = e->params[0], c2 = e->params[1], c3 = e->params[2], c4 = e->params[3], c5 = e->params[4];
+    const int ns = e->params[5], nl = e->params[6], nc = e->params[7];
+    const int cb = std::max(16, std::max(c3 / 4, 64));
+    const int cc = std::max(c3, std::min(nc, 100));
+    const int S = AICAM_YOLO_INPUT;
+    e->in_h = e->in_w = S;
+    const int h2 = S / 2, h4 = S / 4, h8 = S / 8, h16 = S / 16, h32 = S / 32;
+    e->num_anchors = h8 * h8 + h16 * h16 + h32 * h32;
+    e->out_cstride = AICAM_HEAD_DFL + nc;
+    e->out_img_stride = static_cast<long long>(e->num_anchors) * e->out_cstride;
+
+    const int a0 = buf(h2, h2, c1), a1 = buf(h4, h4, c2), a2 = buf(h4, h4, c2), a3 = buf(h8, h8, c3);
+    const int cat14 = buf(h8, h8, c4 + c3);    // [up(n12) | P3]
+    const int a5 = buf(h16, h16, c4);
+    const int cat11 = buf(h16, h16, c5 + c4);  // [up(P5) | P4]
+    const int a7 = buf(h32, h32, c5), a8 = buf(h32, h32, c5);
+    const int cats = buf(h32, h32, 2 * c5);    // SPPF concat: 4 x c5/2
+    const int cat20 = buf(h32, h32, c4 + c5);  // [conv19(o4) | P5]
+    const int cat17 = buf(h16, h16, c3 + c4);  // [conv16(o3) | n12]
+    const int o3 = buf(h8, h8, c3), o4 = buf(h16, h16, c4), o5 = buf(h32, h32, c5);
+
+    conv("model.0.conv", V(-1), S, S, V(a0), 3, c1, 3, 2, 1);
+    conv("model.1.conv", V(a0), h2, h2, V(a1), c1, c2, 3, 2, 1);
+    c2f("model.2", V(a1), c2, V(a2), c2, ns, true, h4, h4);
+    conv("model.3.conv", V(a2), h4, h4, V(a3), c2, c3, 3, 2, 1);
+    c2f("model.4", V(a3), c3, V(cat14, c4), c3, nl, true, h8, h8);
+    conv("model.5.conv", V(cat14, c4), h8, h8, V(a5), c3, c4, 3, 2, 1);
+    c2f("model.6", V(a5), c4, V(cat11, c5), c4, nl, true, h16, h16);
+    conv("model.7.conv", V(cat11, c5), h16, h16, V(a7), c4, c5, 3, 2, 1);
+    c2f("model.8", V(a7), c5, V(a8), c5, ns, true, h32, h32);
+    // SPPF
+    const int hc = c5 / 2;
+    conv("model.9.cv1.conv", V(a8), h32, h32, V(cats, 0), c5, hc, 1, 1, 1);
+    pool(V(cats, 0), V(cats, hc), h32, h32, hc, 5, 1);
+    pool(V(cats, hc), V(cats, 2 * hc), h32, h32, hc, 5, 1);
+    pool(V(cats, 2 * hc), V(cats, 3 * hc), h32, h32, hc, 5, 1);
+    conv("model.9.cv2.conv", V(cats, 0), h32, h32, V(cat20, c4), 4 * hc, c5, 1, 1, 1);
+    // FPN top-down
+    upsample(V(cat20, c4), V(cat11, 0), h32, h32, c5);
+    c2f("model.12", V(cat11, 0), c5 + c4, V(cat17, c3), c4, ns, false, h16, h16);
+    upsample(V(cat17, c3), V(cat14, 0), h16, h16, c4);
+    c2f("model.15", V(cat14, 0), c4 + c3, V(o3), c3, ns, false, h8, h8);
+    // PAN bottom-up
+    conv("model.16.conv", V(o3), h8, h8, V(cat17, 0), c3, c3, 3, 2, 1);
+    c2f("model.18", V(cat17, 0), c3 + c4, V(o4), c4, ns, false, h16, h16);
+    conv("model.19.conv", V(o4), h16, h16, V(cat20, 0), c4, c4, 3, 2, 1);
+    c2f("model.21", V(cat20, 0), c4 + c5, V(o5), c5, ns, false, h32, h32);
+    // Detect
+    const int lvl_in[3] = {o3, o4, o5};
+    const int lvl_c[3] = {c3, c4, c5};
+    const int lvl_h[3] = {h8, h16, h32};
+    long long anchor_base = 0;
+    for (int l = 0; l < 3; ++l) {
+      const int hh = lvl_h[l];
+      const int b1 = buf(hh, hh, cb), b2 = buf(hh, hh, cb), k1 = buf(hh, hh, cc), k2 = buf(hh, hh, cc);
+      const std::string p2 = "model.22.cv2." + std::to_string(l), p3 = "model.22.cv3." + std::to_string(l);
+      const long long eoff = anchor_base * e->out_cstride;
+      conv(p2 + ".0.conv", V(lvl_in[l]), hh, hh, V(b1), lvl_c[l], cb, 3, 1, 1);
+      conv(p2 + ".1.conv", V(b1), hh, hh, V(b2), cb, cb, 3, 1, 1);
+      conv(p2 + ".2", V(b2), hh, hh, V(-2, 0, eoff), cb, AICAM_HEAD_DFL, 1, 1, 0, View(), 0, 1);
+      conv(p3 + ".0.conv", V(lvl_in[l]), hh, hh, V(k1), lvl_c[l], cc, 3, 1, 1);
+      conv(p3 + ".1.conv", V(k1), hh, hh, V(k2), cc, cc, 3, 1, 1);
+      conv(p3 + ".2", V(k2), hh, hh, V(-2, AICAM_HEAD_DFL, eoff), cc, nc, 1, 1, 0, View(), 0, 1);
+      anchor_base += static_cast<long long>(hh) * hh;
+    }
+  }
+
+  void build_reid() {
+    const int H = AICAM_REID_H, W = AICAM_REID_W;
+    e->in_h = H; e->in_w = W;
+    const int s0 = buf(H, W, 64);
+    conv("conv.0", V(-1), H, W, V(s0), 3, 64, 3, 1, 2);
+    int h = H / 2, w = W / 2, c = 64;
+    int cur = buf(h, w, c);
+    pool(V(s0), V(cur), H, W, 64, 3, 2);
+    const int widths[4] = {64, 128, 256, 512};
+    for (int li = 0; li < 4; ++li) {
+      const int cout = widths[li];
+      for (int b = 0; b < 2; ++b) {
+        const std::string name = "layer" + std::to_string(li + 1) + "." + std::to_string(b);
+        const int s = (li > 0 && b == 0) ? 2 : 1;
+        const int ho = h / s, wo = w / s;
+        const int t = buf(ho, wo, cout), o = buf(ho, wo, cout);
+        conv(name + ".conv1", V(cur), h, w, V(t), c, cout, 3, s, 2);
+        int resbuf = cur;
+        if (tensors->count(name + ".downsample.0.weight")) {
+          resbuf = buf(ho, wo, cout);
+          conv(name + ".downsample.0", V(cur), h, w, V(resbuf), c, cout, 1, s, 0);
+        }
+        conv(name + ".conv2", V(t), ho, wo, V(o), cout, cout, 3, 1, 2, V(resbuf), 2);
+        cur = o; h = ho; w = wo; c = cout;
+      }
+    }
+    e->feat_buf = cur;
+    e->out_cstride = c;
+    Op op; op.type = Op::AVGL2; op.in = V(cur); op.h = h; op.w = w; op.c = c;
+    e->ops.push_back(op);
+  }
+};
+
+int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStream_t stream,
+            const int* n_dev = nullptr) {
+  for (const Op& op : e->ops) {
+    auto geom = [&](const View& v, int fallback_c, const __nv_bfloat16** ptr, long long* img_stride, int* cstride) {
+      if (v.buf >= 0) {
+        const Buffer& b = e->buffers[v.buf];
+        *ptr = b.ptr; *cstride = b.c; *img_stride = static_cast<long long>(b.h) * b.w * b.c;
+      } else if (v.buf == -1) {
+        *ptr = static_cast<const __nv_bfloat16*>(input); *cstride = 4;
+        *img_stride = static_cast<long long>(e->in_h) * e->in_w * 4;
+      } else {
+        *ptr = nullptr; *cstride = e->out_cstride; *img_stride = e->out_img_stride;
+      }
+      (void)fallback_c;
+    };
+    const __nv_bfloat16 *ip = nullptr, *op_ = nullptr, *rp = nullptr;
+    long long is = 0, os = 0, rs = 0;
+    int ic = 0, oc = 0, rc_ = 0;
+    geom(op.in, 0, &ip, &is, &ic);
+    int rc = AICAM_OK;
+    switch (op.type) {
+      case Op::CONV: {
+        geom(op.out, 0, &op_, &os, &oc);
+        ConvLaunch L;
+        const PackedConv& pc = e->convs[op.conv];
+        L.in = ip; L.in_img_stride = is; L.in_cstride = ic; L.in_coff = op.in.coff;
+        L.batch = batch; L.h = op.h; L.w = op.w;
+        L.ho = (op.h + 2 * (op.k / 2) - op.k) / op.stride + 1;
+        L.wo = (op.w + 2 * (op.k / 2) - op.k) / op.stride + 1;
+        if (op.out.buf == -2) {
+          L.out = static_cast<float*>(output) + op.out.eoff;
+        } else {
+          L.out = const_cast<__nv_bfloat16*>(op_) + op.out.eoff;
+        }
+        L.out_img_stride = os; L.out_cstride = oc; L.out_coff = op.out.coff; L.out_f32 = op.out_f32;
+        L.res = nullptr; L.res_img_stride = 0; L.res_cstride = 0; L.res_coff = 0; L.res_mode = 0;
+        if (op.res_mode) {
+          geom(op.res, 0, &rp, &rs, &rc_);
+          L.res = rp; L.res_img_stride = rs; L.res_cstride = rc_; L.res_coff = op.res.coff; L.res_mode = op.res_mode;
+        }
+        L.act = op.act;
+        L.batch_dev = n_dev;
+        rc = launch_conv(pc, L, stream);
+        break;
+      }
+      case Op::MAXPOOL:
+        geom(op.out, 0, &op_, &os, &oc);
+        rc = launch_maxpool(ip, is, ic, op.in.coff, batch, op.h, op.w, op.c, op.k, op.stride,
+                            const_cast<__nv_bfloat16*>(op_), os, oc, op.out.coff, stream, n_dev);
+        break;
+      case Op::UPSAMPLE:
+        geom(op.out, 0, &op_, &os, &oc);
+        rc = launch_upsample2x(ip, is, ic, op.in.coff, batch, op.h, op.w, op.c, const_cast<__nv_bfloat16*>(op_), os,
+                               oc, op.out.coff, stream);
+        break;
+      case Op::AVGL2:
+        rc = launch_avgpool_l2norm(ip, batch, op.h * op.w, op.c, static_cast<float*>(output), stream, n_dev);
+        break;
+    }
+    if (rc) return rc;
+  }
+  return AICAM_OK;
+}
+
+}  // namespace
+
+}  // namespace aicam
+
+using namespace aicam;
+
+extern "C" {
+
+int aicam_engine_create(const char* blob_path, int device, int max_batch, aicam_engine** out) {
+  if (!blob_path || !out || max_batch <= 0) return fail(AICAM_ERR_INVALID_ARG, "engine_create: bad arguments");
+  *out = nullptr;
+  std::ifstream f(blob_path, std::ios::binary | std::ios::ate);
+  if (!f) return fail(AICAM_ERR_IO, std::string("engine_create: weight blob not found: ") + blob_path);
+  const size_t size = static_cast<size_t>(f.tellg());
+  std::vector<char> raw(size);
+  f.seekg(0);
+  f.read(raw.data(), size);
+  if (size < 48 || std::memcmp(raw.data(), "AICW0001", 8) != 0)
+    return fail(AICAM_ERR_IO, std::string("engine_create: not an AICW0001 weight blob: ") + blob_path);
+  uint32_t head[10];
+  std::memcpy(head, raw.data() + 8, sizeof(head));
+  const uint32_t kind = head[0], n_tensors = head[9];
+  const size_t entry = 64 + 4 + 16 + 8 + 8;
+  if (48 + n_tensors * entry > size) return fail(AICAM_ERR_IO, "engine_create: truncated blob header");
+  std::map<std::string, BlobTensor> tensors;
+  for (uint32_t i = 0; i < n_tensors; ++i) {
+    const char* p = raw.data() + 48 + i * entry;
+    char name[65] = {0};
+    std::memcpy(name, p, 64);
+    uint32_t nd, dims[4];
+    uint64_t off, nbytes;
+    std::memcpy(&nd, p + 64, 4);
+    std::memcpy(dims, p + 68, 16);
+    std::memcpy(&off, p + 84, 8);
+    std::memcpy(&nbytes, p + 92, 8);
+    if (off + nbytes > size || nd > 4) return fail(AICAM_ERR_IO, "engine_create: corrupt tensor entry");
+    BlobTensor t;
+    for (uint32_t d = 0; d < nd; ++d) t.dims.push_back(static_cast<int>(dims[d]));
+    t.data = reinterpret_cast<const float*>(raw.data() + off);
+    t.count = nbytes / 4;
+    tensors[name] = t;
+  }
+  AICAM_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  AICAM_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(AICAM_ERR_UNSUPPORTED, "engine_create: this library contains sm_100a code only (tcgen05/TMEM)");
+  aicam_engine* e = new aicam_engine();
+  e->kind = static_cast<int>(kind);
+  e->device = device;
+  e->max_batch = max_batch;
+  std::memcpy(e->params, head + 1, 32);
+  Builder b{e, &tensors};
+  if (kind == AICAM_KIND_YOLOV8) {
+    b.build_yolov8();
+  } else if (kind == AICAM_KIND_REID) {
+    b.build_reid();
+  } else {
+    delete e;
+    return fail(AICAM_ERR_IO, "engine_create: unknown model kind in blob");
+  }
+  if (b.err) {
+    aicam_engine_destroy(e);
+    return b.err;
+  }
+  AICAM_CUDA_OK(cudaDeviceSynchronize());
+  *out = e;
+  return AICAM_OK;
+}
+
+void aicam_engine_destroy(aicam_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  for (auto& c : e->convs) free_packed_conv(&c);
+  for (auto& b : e->buffers)
+    if (b.ptr) cudaFree(b.ptr);
+  delete e;
+}
+
+int aicam_engine_kind(const aicam_engine* e) { return e ? e->kind : 0; }
+int aicam_engine_max_batch(const aicam_engine* e) { return e ? e->max_batch : 0; }
+int aicam_engine_num_classes(const aicam_engine* e) {
+  if (!e) return 0;
+  return e->kind == AICAM_KIND_YOLOV8 ? static_cast<int>(e->params[7]) : e->out_cstride;
+}
+int aicam_engine_num_anchors(const aicam_engine* e) { return e ? e->num_anchors : 0; }
+double aicam_engine_flops_per_item(const aicam_engine* e) { return e ? 2.0 * e->macs_per_item : 0.0; }
+int aicam_engine_num_launches(const aicam_engine* e) { return e ? static_cast<int>(e->ops.size()) : 0; }
+
+int aicam_engine_set_bias(aicam_engine* e, const char* name, const float* host, int n) {
+  if (!e || !name || !host) return fail(AICAM_ERR_INVALID_ARG, "engine_set_bias: bad arguments");
+  auto it = e->conv_by_name.find(name);
+  if (it == e->conv_by_name.end()) return fail(AICAM_ERR_INVALID_ARG, std::string("engine_set_bias: no layer ") + name);
+  PackedConv& pc = e->convs[it->second];
+  if (n != pc.cout) return fail(AICAM_ERR_INVALID_ARG, "engine_set_bias: length differs from the layer's cout");
+  AICAM_CUDA_OK(cudaSetDevice(e->device));
+  AICAM_CUDA_OK(cudaMemcpy(pc.bias, host, sizeof(float) * n, cudaMemcpyHostToDevice));
+  return AICAM_OK;
+}
+
+int aicam_engine_get_bias(aicam_engine* e, const char* name, float* host, int n) {
+  if (!e || !name || !host) return fail(AICAM_ERR_INVALID_ARG, "engine_get_bias: bad arguments");
+  auto it = e->conv_by_name.find(name);
+  if (it == e->conv_by_name.end()) return fail(AICAM_ERR_INVALID_ARG, std::string("engine_get_bias: no layer ") + name);
+  PackedConv& pc = e->convs[it->second];
+  if (n != pc.cout) return fail(AICAM_ERR_INVALID_ARG, "engine_get_bias: length differs from the layer's cout");
+  AICAM_CUDA_OK(cudaSetDevice(e->device));
+  AICAM_CUDA_OK(cudaMemcpy(host, pc.bias, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  return AICAM_OK;
+}
+
+int aicam_yolo_forward(aicam_engine* e, const void* in_nhwc4, int batch, float* head, void* stream) {
+  if (!e || e->kind != AICAM_KIND_YOLOV8) return fail(AICAM_ERR_INVALID_ARG, "yolo_forward: not a yolov8 engine");
+  if (!in_nhwc4 || !head) return fail(AICAM_ERR_INVALID_ARG, "yolo_forward: null tensor");
+  if (batch < 0 || batch > e->max_batch) return fail(AICAM_ERR_CAPACITY, "yolo_forward: batch exceeds max_batch");
+  return run_ops(e, in_nhwc4, batch, head, static_cast<cudaStream_t>(stream));
+}
+
+int aicam_reid_forward(aicam_engine* e, const void* crops_nhwc4, int n, const int32_t* n_dev, float* feats,
+                       void* stream) {
+  if (!e || e->kind != AICAM_KIND_REID) return fail(AICAM_ERR_INVALID_ARG, "reid_forward: not a reid engine");
+  if (!crops_nhwc4 || !feats) return fail(AICAM_ERR_INVALID_ARG, "reid_forward: null tensor");
+  if (n < 0) return fail(AICAM_ERR_INVALID_ARG, "reid_forward: negative batch");
+  if (n_dev) {
+    if (n > e->max_batch) return fail(AICAM_ERR_CAPACITY, "reid_forward: capacity exceeds max_batch");
+    return run_ops(e, crops_nhwc4, n, feats, static_cast<cudaStream_t>(stream), n_dev);
+  }
+  // crops beyond the engine's workspace are processed in slices of max_batch
+  const long long in_stride = static_cast<long long>(AICAM_REID_H) * AICAM_REID_W * 4;
+  for (int s = 0; s < n; s += e->max_batch) {
+    const int nb = std::min(e->max_batch, n - s);
+    int rc = run_ops(e, static_cast<const __nv_bfloat16*>(crops_nhwc4) + s * in_stride, nb,
+                     feats + static_cast<long long>(s) * e->out_cstride, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+  }
+  return AICAM_OK;
+}
+
+int aicam_nchw_to_nhwc4(const float* in, int n, int h, int w, void* out, void* stream) {
+  if (!in || !out || n < 0) return fail(AICAM_ERR_INVALID_ARG, "nchw_to_nhwc4: bad arguments");
+  return launch_nchw_to_nhwc4(in, n, h, w, static_cast<__nv_bfloat16*>(out), static_cast<cudaStream_t>(stream));
+}
+
+int aicam_conv2d(const aicam_conv_desc* d, const void* in, const float* w, const float* bias, const void* res,
+                 void* out, void* stream) {
+  if (!d || !in || !w || !out) return fail(AICAM_ERR_INVALID_ARG, "conv2d: null argument");
+  PackedConv pc;
+  if (int rc = pack_conv_weights(w, bias, d->cout, d->cin, d->ksize, d->stride, &pc)) return rc;
+  ConvLaunch L;
+  const int cs = pc.cin_pad;
+  L.in = static_cast<const __nv_bfloat16*>(in);
+  L.in_img_stride = static_cast<long long>(d->h) * d->w * cs; L.in_cstride = cs; L.in_coff = 0;
+  L.batch = d->batch; L.h = d->h; L.w = d->w;
+  L.ho = (d->h + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
+  L.wo = (d->w + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
+  L.out = out; L.out_img_stride = static_cast<long long>(L.ho) * L.wo * d->cout; L.out_cstride = d->cout;
+  L.out_coff = 0; L.out_f32 = d->out_f32;
+  L.res = static_cast<const __nv_bfloat16*>(res); L.res_img_stride = L.out_img_stride; L.res_cstride = d->cout;
+  L.res_coff = 0; L.res_mode = res ? d->res_mode : 0;
+  L.act = d->act;
+  int rc = launch_conv(pc, L, static_cast<cudaStream_t>(stream));
+  cudaError_t se = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  free_packed_conv(&pc);
+  if (rc) return rc;
+  if (se != cudaSuccess) return fail(AICAM_ERR_CUDA, std::string("conv2d: ") + cudaGetErrorString(se));
+  return AICAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// Small NHWC bf16 layers around the convolutions: max-pool (SPPF 5x5 s1, ReID 3x3 s2),
+// nearest 2x upsample into a concat slice, global average pool + L2 normalise, and the
+// fp32 NCHW -> bf16 NHWC4 converter used by the TRTEngine-shaped facade.
+// All are HBM/L2-bound elementwise kernels: 16-byte vector accesses, one 8-channel group
+// per thread, consecutive threads on consecutive channel groups (coalesced).
+#include "layers.cuh"
+
+namespace aicam {
+
+extern void count_launch();
+
+namespace {
+
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
+  __nv_bfloat162 y = *reinterpret_cast<__nv_bfloat162*>(&b);
+  __nv_bfloat162 r = __hmax2(x, y);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// out[n][oy][ox][coff_out + c] = max over k x k window (pad k/2, -inf padding) of in[..][coff_in + c]
+__global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ in, long long in_img_stride, int in_cstride,
+                               int in_coff, int h, int w, int c8, int k, int stride, int ho, int wo,
+                               __nv_bfloat16* __restrict__ out, long long out_img_stride, int out_cstride,
+                               int out_coff, long long total, const int* __restrict__ n_dev) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % c8);
+  long long p = idx / c8;
+  const int ox = static_cast<int>(p % wo); p /= wo;
+  const int oy = static_cast<int>(p % ho);
+  const int n = static_cast<int>(p / ho);
+  if (n_dev && n >= __ldg(n_dev)) return;
+  const int pad = k / 2;
+  const uint32_t ninf = 0xFF80FF80u;  // two bf16 -inf
+  uint4 m = make_uint4(ninf, ninf, ninf, ninf);
+  const __nv_bfloat16* base = in + n * in_img_stride + in_coff + g * 8;
+  for (int dy = 0; dy < k; ++dy) {
+    const int iy = oy * stride - pad + dy;
+    if (iy < 0 || iy >= h) continue;
+    for (int dx = 0; dx < k; ++dx) {
+      const int ix = ox * stride - pad + dx;
+      if (ix < 0 || ix >= w) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(iy) * w + ix) * in_cstride));
+      m.x = bf16x2_max(m.x, v.x); m.y = bf16x2_max(m.y, v.y);
+      m.z = bf16x2_max(m.z, v.z); m.w = bf16x2_max(m.w, v.w);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + n * out_img_stride + (static_cast<long long>(oy) * wo + ox) * out_cstride +
+                            out_coff + g * 8) = m;
+}
+
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, long long in_img_stride, int in_cstride,
+                                  int in_coff, int h, int w, int c8, __nv_bfloat16* __restrict__ out,
+                                  long long out_img_stride, int out_cstride, int out_coff, long long total) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % c8);
+  long long p = idx / c8;
+  const int ox = static_cast<int>(p % (2 * w)); p /= (2 * w);
+  const int oy = static_cast<int>(p % (2 * h));
+  const int n = static_cast<int>(p / (2 * h));
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+      in + n * in_img_stride + (static_cast<long long>(oy >> 1) * w + (ox >> 1)) * in_cstride + in_coff + g * 8));
+  *reinterpret_cast<uint4*>(out + n * out_img_stride + (static_cast<long long>(oy) * 2 * w + ox) * out_cstride +
+                            out_coff + g * 8) = v;
+}
+
+// One block per image: mean over hw pixels of each of c channels, then x / ||x||_2 (fp32).
+__global__ void avgpool_l2norm_kernel(const __nv_bfloat16* __restrict__ in, int hw, int c, float* __restrict__ out,
+                                      const int* __restrict__ n_dev) {
+  extern __shared__ float red[];
+  const int n = blockIdx.x;
+  if (n_dev && n >= __ldg(n_dev)) return;
+  const __nv_bfloat16* base = in + static_cast<long long>(n) * hw * c;
+  float ss = 0.0f;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.0f;
+    for (int p = 0; p < hw; ++p) s += __bfloat162float(base[static_cast<long long>(p) * c + ch]);
+    s /= static_cast<float>(hw);
+    out[static_cast<long long>(n) * c + ch] = s;
+    ss += s * s;
+  }
+  red[threadIdx.x] = ss;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float inv = 1.0f / sqrtf(red[0]);
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) out[static_cast<long long>(n) * c + ch] *= inv;
+}
+
+__global__ void nchw_to_nhwc4_kernel(const float* __restrict__ in, int hw, __nv_bfloat16* __restrict__ out,
+                                     long long total) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const long long n = idx / hw;
+  const long long p = idx - n * hw;
+  const float* b = in + n * 3 * hw + p;
+  uint2 o;
+  o.x = pack_bf16x2(b[0], b[hw]);
+  o.y = pack_bf16x2(b[2 * static_cast<long long>(hw)], 0.0f);
+  reinterpret_cast<uint2*>(out)[idx] = o;
+}
+
+}  // namespace
+
+int launch_maxpool(const __nv_bfloat16* in, long long in_img_stride, int in_cstride, int in_coff, int batch, int h,
+                   int w, int c, int k, int stride, __nv_bfloat16* out, long long out_img_stride, int out_cstride,
+                   int out_coff, cudaStream_t stream, const int* n_dev) {
+  if (c % 8 || in_cstride % 8 || in_coff % 8 || out_cstride % 8 || out_coff % 8)
+    return fail(AICAM_ERR_INVALID_ARG, "maxpool: channel counts/offsets must be multiples of 8");
+  const int pad = k / 2;
+  const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+  const long long total = static_cast<long long>(batch) * ho * wo * (c / 8);
+  if (total == 0) return AICAM_OK;
+  maxpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      in, in_img_stride, in_cstride, in_coff, h, w, c / 8, k, stride, ho, wo, out, out_img_stride, out_cstride,
+      out_coff, total, n_dev);
+  count_launch();
+  return last_launch("maxpool_kernel");
+}
+
+int launch_upsample2x(const __nv_bfloat16* in, long long in_img_stride, int in_cstride, int in_coff, int batch, int h,
+                      int w, int c, __nv_bfloat16* out, long long out_img_stride, int out_cstride, int out_coff,
+                      cudaStream_t stream) {
+  if (c % 8 || in_cstride % 8 || in_coff % 8 || out_cstride % 8 || out_coff % 8)
+    return fail(AICAM_ERR_INVALID_ARG, "upsample: channel counts/offsets must be multiples of 8");
+  const long long total = static_cast<long long>(batch) * 4 * h * w * (c / 8);
+  if (total == 0) return AICAM_OK;
+  upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      in, in_img_stride, in_cstride, in_coff, h, w, c / 8, out, out_img_stride, out_cstride, out_coff, total);
+  count_launch();
+  return last_launch("upsample2x_kernel");
+}
+
+int launch_avgpool_l2norm(const __nv_bfloat16* in, int batch, int hw, int c, float* out, cudaStream_t stream,
+                          const int* n_dev) {
+  if (batch == 0) return AICAM_OK;
+  avgpool_l2norm_kernel<<<batch, 256, 256 * sizeof(float), stream>>>(in, hw, c, out, n_dev);
+  count_launch();
+  return last_launch("avgpool_l2norm_kernel");
+}
+
+int launch_nchw_to_nhwc4(const float* in, int n, int h, int w, __nv_bfloat16* out, cudaStream_t stream) {
+  const long long total = static_cast<long long>(n) * h * w;
+  if (total == 0) return AICAM_OK;
+  nchw_to_nhwc4_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, h * w, out, total);
+  count_launch();
+  return last_launch("nchw_to_nhwc4_kernel");
+}
+
+}  // namespace aicam

@@ -1,0 +1,214 @@
+// K5: detection filter + ROI crop / resize / normalise of every tracked detection of every
+// stream into one batched ReID input tensor.
+//
+// Replaces DeepSORT.update steps 1-2 (confidence/class filter,
+// /root/reference/src/tracker/deepsort_tracker.py:88-101), _extract_image_crops (:143-159,
+// int() truncation + clamp; empty rectangle -> no feature), preprocess_reid_input
+// (src/utils/image_processing.py:105-138: cv2.resize INTER_LINEAR to 64x128, BGR->RGB,
+// (x/255 - mean)/std, CHW) and the concat + H2D of src/tracker/reid_model.py:83-101.
+//
+// The resize is OpenCV's fixed-point bilinear (see preprocess.cu), evaluated per crop: the
+// coefficient tables depend on the crop size, so each CTA derives them in shared memory with
+// the same double -> float -> 11-bit rounding steps (explicit _rn intrinsics; the file is also
+// compiled with --fmad=false), then every thread interpolates its pixels.  Result: the uint8
+// resized crop, and therefore the float tensor, equals the reference's bit for bit.
+// HBM-bound: reads ~crop bytes, writes 128*64*8 B (NHWC4 bf16) per crop.
+#include "common.cuh"
+
+namespace aicam {
+
+extern void count_launch();
+
+namespace {
+
+constexpr int RH = AICAM_REID_H, RW = AICAM_REID_W;
+
+// One block, one thread per frame: stable filter of the frame's detections, crop rectangles,
+// and (via a block-wide exclusive scan) deterministic crop rows.
+__global__ void __launch_bounds__(1024) filter_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                                                      const int* __restrict__ labels, const int* __restrict__ num_dets,
+                                                      int batch, int stride_k, int h, int w, float min_conf,
+                                                      unsigned long long mask_lo, unsigned long long mask_hi,
+                                                      int max_crops, int* __restrict__ det_index,
+                                                      int* __restrict__ det_count, int* __restrict__ crop_slot,
+                                                      int* __restrict__ crop_rect, int* __restrict__ crop_count) {
+  __shared__ int s_scan[1024];
+  __shared__ int s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < batch; b0 += blockDim.x) {
+    const int b = b0 + threadIdx.x;
+    int nvalid = 0, nkeep = 0;
+    if (b < batch) {
+      const int n = min(num_dets[b], stride_k);
+      for (int i = 0; i < n; ++i) {
+        const long long o = static_cast<long long>(b) * stride_k + i;
+        const int cls = labels[o];
+        const bool tracked = cls >= 0 && cls < 128 && (((cls < 64 ? mask_lo >> cls : mask_hi >> (cls - 64)) & 1ull) != 0);
+        if (!(scores[o] >= min_conf && tracked)) continue;
+        const float4 bx = reinterpret_cast<const float4*>(boxes)[o];
+        const int x1 = max(0, static_cast<int>(bx.x)), y1 = max(0, static_cast<int>(bx.y));
+        const int x2 = min(w, static_cast<int>(bx.z)), y2 = min(h, static_cast<int>(bx.w));
+        det_index[static_cast<long long>(b) * stride_k + nkeep] = i;
+        // provisional: local crop ordinal or -1; rebased after the scan
+        crop_slot[static_cast<long long>(b) * stride_k + nkeep] = (x1 < x2 && y1 < y2) ? nvalid : -1;
+        if (x1 < x2 && y1 < y2) ++nvalid;
+        ++nkeep;
+      }
+      det_count[b] = nkeep;
+    }
+    // exclusive scan of nvalid over the block
+    s_scan[threadIdx.x] = nvalid;
+    __syncthreads();
+    for (int o = 1; o < static_cast<int>(blockDim.x); o <<= 1) {
+      const int v = threadIdx.x >= static_cast<unsigned>(o) ? s_scan[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_scan[threadIdx.x] += v;
+      __syncthreads();
+    }
+    const int base = s_base + s_scan[threadIdx.x] - nvalid;
+    if (b < batch) {
+      const int n = min(num_dets[b], stride_k);
+      int k = 0;
+      for (int i = 0; i < n && k < nkeep; ++i) {
+        const long long o = static_cast<long long>(b) * stride_k + i;
+        if (det_index[static_cast<long long>(b) * stride_k + k] != i) continue;
+        const long long ko = static_cast<long long>(b) * stride_k + k;
+        if (crop_slot[ko] >= 0) {
+          const int slot = base + crop_slot[ko];
+          if (slot < max_crops) {
+            const float4 bx = reinterpret_cast<const float4*>(boxes)[o];
+            crop_slot[ko] = slot;
+            crop_rect[slot * 5 + 0] = b;
+            crop_rect[slot * 5 + 1] = max(0, static_cast<int>(bx.x));
+            crop_rect[slot * 5 + 2] = max(0, static_cast<int>(bx.y));
+            crop_rect[slot * 5 + 3] = min(w, static_cast<int>(bx.z));
+            crop_rect[slot * 5 + 4] = min(h, static_cast<int>(bx.w));
+          } else {
+            crop_slot[ko] = -1;
+          }
+        }
+        ++k;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_base += s_scan[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *crop_count = min(s_base, max_crops);
+}
+
+// cv2 linear-resize tables for one axis, one entry per thread
+__device__ __forceinline__ void axis_entry(int src, int dst, int d, bool horizontal, int* i0, int* i1, int* w0, int* w1) {
+  const double scale = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(dst), static_cast<double>(src)));
+  float f = __double2float_rn(__dsub_rn(__dmul_rn(static_cast<double>(d) + 0.5, scale), 0.5));
+  int s = __float2int_rd(f);
+  f = __fsub_rn(f, static_cast<float>(s));
+  if (horizontal) {
+    if (s < 0) { f = 0.0f; s = 0; }
+    if (s >= src - 1) { f = 0.0f; s = src - 1; }
+    *i0 = s;
+    *i1 = min(s + 1, src - 1);
+  } else {
+    *i0 = min(max(s, 0), src - 1);
+    *i1 = min(max(s + 1, 0), src - 1);
+  }
+  *w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.0f, f), 2048.0f));
+  *w1 = __float2int_rn(__fmul_rn(f, 2048.0f));
+}
+
+template <int FORMAT>
+__global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ frames, int h, int w,
+                                                   const int* __restrict__ crop_rect,
+                                                   const int* __restrict__ crop_count, void* __restrict__ out) {
+  const int slot = blockIdx.x;
+  if (slot >= *crop_count) return;
+  __shared__ int tx[4][RW];
+  __shared__ int ty[4][RH];
+  const int b = crop_rect[slot * 5], x1 = crop_rect[slot * 5 + 1], y1 = crop_rect[slot * 5 + 2];
+  const int cw = crop_rect[slot * 5 + 3] - x1, ch = crop_rect[slot * 5 + 4] - y1;
+  const int mode = (cw == RW && ch == RH) ? 2 : ((cw == 2 * RW && ch == 2 * RH) ? 1 : 0);
+  if (mode == 0) {
+    const int t = threadIdx.x;
+    if (t < RW) axis_entry(cw, RW, t, true, &tx[0][t], &tx[1][t], &tx[2][t], &tx[3][t]);
+    else if (t < RW + RH) axis_entry(ch, RH, t - RW, false, &ty[0][t - RW], &ty[1][t - RW], &ty[2][t - RW], &ty[3][t - RW]);
+  }
+  __syncthreads();
+  const uint8_t* src = frames + (static_cast<long long>(b) * h + y1) * w * 3 + static_cast<long long>(x1) * 3;
+  const long long rs = static_cast<long long>(w) * 3;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (int p = threadIdx.x; p < RH * RW; p += blockDim.x) {
+    const int oy = p / RW, ox = p - oy * RW;
+    int v[3];
+    if (mode == 2) {
+      const uint8_t* s = src + oy * rs + ox * 3;
+      v[0] = __ldg(s); v[1] = __ldg(s + 1); v[2] = __ldg(s + 2);
+    } else if (mode == 1) {
+      const uint8_t* s0 = src + (2 * oy) * rs + (2 * ox) * 3;
+      const uint8_t* s1 = s0 + rs;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = (__ldg(s0 + c) + __ldg(s0 + 3 + c) + __ldg(s1 + c) + __ldg(s1 + 3 + c) + 2) >> 2;
+    } else {
+      const int sx0 = tx[0][ox], sx1 = tx[1][ox], a0 = tx[2][ox], a1 = tx[3][ox];
+      const int b0 = ty[2][oy], b1 = ty[3][oy];
+      const uint8_t* r0 = src + ty[0][oy] * rs;
+      const uint8_t* r1 = src + ty[1][oy] * rs;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        int h0 = 0, h1 = 0;
+        if (b0 != 0) {
+          h0 = __ldg(r0 + sx0 * 3 + c) * a0;
+          if (a1 != 0) h0 += __ldg(r0 + sx1 * 3 + c) * a1;
+        }
+        if (b1 != 0) {
+          h1 = __ldg(r1 + sx0 * 3 + c) * a0;
+          if (a1 != 0) h1 += __ldg(r1 + sx1 * 3 + c) * a1;
+        }
+        const int o = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        v[c] = min(max(o, 0), 255);
+      }
+    }
+    float rgb[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)  // BGR -> RGB, (x/255 - mean)/std in float32
+      rgb[c] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v[2 - c]), 255.0f), mean[c]), stdv[c]);
+    if (FORMAT == 0) {
+      float* o = static_cast<float*>(out) + static_cast<long long>(slot) * 3 * RH * RW + p;
+      o[0] = rgb[0]; o[RH * RW] = rgb[1]; o[2 * RH * RW] = rgb[2];
+    } else {
+      uint2 q;
+      q.x = pack_bf16x2(rgb[0], rgb[1]);
+      q.y = pack_bf16x2(rgb[2], 0.0f);
+      reinterpret_cast<uint2*>(out)[static_cast<long long>(slot) * RH * RW + p] = q;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace aicam
+
+using namespace aicam;
+
+extern "C" int aicam_reid_crops(const uint8_t* frames, int batch, int h, int w, const float* boxes, const float* scores,
+                                const int32_t* labels, const int32_t* num_dets, int stride_k, float min_confidence,
+                                uint64_t class_mask_lo, uint64_t class_mask_hi, int format, int max_crops,
+                                int32_t* det_index, int32_t* det_count, int32_t* crop_slot, int32_t* crop_rect,
+                                void* crops, int32_t* crop_count, void* stream) {
+  if (!boxes || !scores || !labels || !num_dets || !det_index || !det_count || !crop_slot || !crop_rect || !crop_count)
+    return fail(AICAM_ERR_INVALID_ARG, "reid_crops: null argument");
+  if (batch < 0 || stride_k <= 0 || h <= 0 || w <= 0 || max_crops < 0 || (format != 0 && format != 1))
+    return fail(AICAM_ERR_INVALID_ARG, "reid_crops: bad shape arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  filter_kernel<<<1, 1024, 0, st>>>(boxes, scores, labels, num_dets, batch, stride_k, h, w, min_confidence,
+                                    class_mask_lo, class_mask_hi, max_crops, det_index, det_count, crop_slot, crop_rect,
+                                    crop_count);
+  count_launch();
+  if (int rc = last_launch("filter_kernel")) return rc;
+  if (max_crops == 0 || !frames || !crops) return AICAM_OK;  // filter only
+  if (format == 0)
+    crop_kernel<0><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
+  else
+    crop_kernel<1><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
+  count_launch();
+  return last_launch("crop_kernel");
+}

@@ -1,0 +1,801 @@
+// K7-K12: the whole DeepSORT association on device, one CTA per video stream.
+//
+// Replaces /root/reference/src/tracker/core/ (kalman_filter.py, track.py, detection.py,
+// matching.py, linear_assignment.py, tracker_core.py) and the formatting loop of
+// DeepSORT.update (src/tracker/deepsort_tracker.py:123-141).
+//
+// Bit-exactness.  The reference tracker is float32 end to end and its Kalman algebra only
+// ever touches four 2x2 blocks of the covariance, so every BLAS/LAPACK call reduces to a
+// fixed sequence of correctly rounded float32 operations (oracle/kalman.py, SURVEY.md
+// Appendix C).  This file spells those sequences out and is compiled with --fmad=false, so
+// no product-sum is contracted.  The assignment follows scipy's rectangular LSAP step by
+// step in float64 (oracle/lsap.py): the column scan is spread over
+// the 32 lanes of one warp, and the (value, first position, last unassigned position)
+// reduction reproduces the sequential tie rule exactly.  The only value that is NOT
+// bit-reproducible is the cosine distance (a BLAS sgemm in the reference): parity there is
+// a tolerance, and assignments are bit-exact given the same cost matrix.
+//
+// State layout in HBM (struct of arrays, per stream, indexed by a track SLOT):
+//   mean[S][T][8] cov[S][T][16] f32 | id/state/hits/age/tsu/class[S][T] i32 | conf[S][T] f32
+//   gallery[S][T][G][F] f32 (L2-normalised at insert; ring buffer: head, count)
+//   order[S][T]: slots of the live tracks in creation order (the reference's track list)
+//   free_slots[S][T] stack, next_id[S]
+#include <vector>
+
+#include "common.cuh"
+
+namespace aicam {
+
+extern void count_launch();
+
+namespace {
+
+constexpr int TENTATIVE = 1, CONFIRMED = 2, DELETED = 3;  // track.py:10-14
+constexpr float INFTY_COST = 1e5f;                         // linear_assignment.py:9
+constexpr float CHI2_GATE = 9.487729036781154f;            // kalman_filter.py:16, compared in float32
+constexpr int ASSOC_THREADS = 128;
+
+struct Dev {
+  int S, T, D, F, G;
+  float thr_cos, clamp_cos, thr_iou, clamp_iou;
+  int max_age, n_init;
+  float* mean; float* cov;
+  int* track_id; int* state; int* hits; int* age; int* tsu; int* cls; float* conf;
+  int* gal_count; int* gal_head; float* gallery;
+  int* order; int* n_tracks; int* free_slots; int* n_free; int* next_id; int* overflow;
+  float* app_cost;  // [S][T][D] by (slot, det)
+  float* cost_ws;   // [S][T*D]
+  float* featn;     // [S][D][F]
+};
+
+// ---- float32 building blocks (oracle/kalman.py) ------------------------------------------------
+__device__ __forceinline__ float sq_via_double(float x) {
+  const double d = static_cast<double>(x);
+  return static_cast<float>(d * d);
+}
+__device__ __forceinline__ float c_wp() { return static_cast<float>(1.0 / 20); }
+__device__ __forceinline__ float c_wv() { return static_cast<float>(1.0 / 160); }
+__device__ __forceinline__ float c_wp2() { return static_cast<float>(2 * (1.0 / 20)); }
+__device__ __forceinline__ float c_wv10() { return static_cast<float>(10 * (1.0 / 160)); }
+__device__ __forceinline__ float c_sq_1e2() { return static_cast<float>(1e-2 * 1e-2); }
+__device__ __forceinline__ float c_sq_1e5() { return static_cast<float>(1e-5 * 1e-5); }
+__device__ __forceinline__ float c_sq_1e1() { return static_cast<float>(1e-1 * 1e-1); }
+
+// kalman_filter.py:55-83
+__device__ void kf_initiate(const float z[4], float* mean, float* cov) {
+  for (int i = 0; i < 4; ++i) { mean[i] = z[i]; mean[4 + i] = 0.0f; }
+  const float sp = sq_via_double(c_wp2() * z[3]);
+  const float sv = sq_via_double(c_wv10() * z[3]);
+  for (int i = 0; i < 4; ++i) {
+    cov[i] = (i == 2) ? c_sq_1e2() : sp;
+    cov[4 + i] = 0.0f;
+    cov[8 + i] = 0.0f;
+    cov[12 + i] = (i == 2) ? c_sq_1e5() : sv;
+  }
+}
+
+// kalman_filter.py:85-120  (P' = F (P F^T) + Q)
+__device__ void kf_predict(float* mean, float* cov) {
+  const float h = mean[3];
+  const float sp = sq_via_double(c_wp() * h);
+  const float sv = sq_via_double(c_wv() * h);
+  for (int i = 0; i < 4; ++i) {
+    const float a = cov[i], b = cov[4 + i], c = cov[8 + i], d = cov[12 + i];
+    const float qp = (i == 2) ? c_sq_1e2() : sp;
+    const float qv = (i == 2) ? c_sq_1e5() : sv;
+    mean[i] = mean[i] + mean[4 + i];
+    const float y00 = a + b;
+    const float y10 = c + d;
+    cov[i] = (y00 + y10) + qp;
+    cov[4 + i] = b + d;
+    cov[8 + i] = y10;
+    cov[12 + i] = d + qv;
+  }
+}
+
+// diagonal of S = H P H^T + R, kalman_filter.py:122-151
+__device__ __forceinline__ float kf_innov(const float* mean, const float* cov, int i) {
+  const float r = (i == 2) ? c_sq_1e1() : sq_via_double(c_wp() * mean[3]);
+  return cov[i] + r;
+}
+
+// kalman_filter.py:206-249; n_meas selects the OpenBLAS path the reference takes
+__device__ float kf_gating(const float* mean, const float* cov, const float z[4], int n_meas) {
+  float q[4];
+  for (int i = 0; i < 4; ++i) {
+    const float L = sqrtf(kf_innov(mean, cov, i));
+    const float delta = z[i] - mean[i];
+    const float y = (n_meas >= 2) ? delta * (1.0f / L) : delta / L;
+    q[i] = y * y;
+  }
+  return ((q[0] + q[1]) + q[2]) + q[3];
+}
+
+// kalman_filter.py:153-204
+__device__ void kf_update(float* mean, float* cov, const float z[4]) {
+  float nm[8], nc[16];
+  for (int i = 0; i < 4; ++i) {
+    const float a = cov[i], b = cov[4 + i], c = cov[8 + i], d = cov[12 + i];
+    const float s = kf_innov(mean, cov, i);
+    const float inv = 1.0f / sqrtf(s);
+    const float k0 = (a * inv) * inv;
+    const float k1 = (c * inv) * inv;
+    const float e = z[i] - mean[i];
+    nm[i] = mean[i] + k0 * e;
+    nm[4 + i] = mean[4 + i] + k1 * e;
+    const float s0 = s * k0, s1 = s * k1;
+    nc[i] = a - k0 * s0;
+    nc[4 + i] = b - k0 * s1;
+    nc[8 + i] = c - k1 * s0;
+    nc[12 + i] = d - k1 * s1;
+  }
+  for (int i = 0; i < 8; ++i) mean[i] = nm[i];
+  for (int i = 0; i < 16; ++i) cov[i] = nc[i];
+}
+
+// detection.py:36-47
+__device__ __forceinline__ void tlwh_to_xyah(const float t[4], float z[4]) {
+  z[0] = t[0] + t[2] / 2.0f;
+  z[1] = t[1] + t[3] / 2.0f;
+  z[2] = t[3] > 0.0f ? t[2] / t[3] : 0.0f;
+  z[3] = t[3];
+}
+
+// track.py:133-151
+__device__ __forceinline__ void mean_to_tlwh(const float* mean, float t[4]) {
+  float h = mean[3], w;
+  if (h > 0.0f) { w = mean[2] * h; } else { w = 0.0f; h = fmaxf(0.0f, h); }
+  t[0] = mean[0] - w / 2.0f;
+  t[1] = mean[1] - h / 2.0f;
+  t[2] = w;
+  t[3] = h;
+}
+
+// matching.py:13-54, cost = 1 - IoU (matching.py:104)
+__device__ __forceinline__ float iou_cost(const float a[4], const float c[4]) {
+  const float abx = a[0] + a[2], aby = a[1] + a[3];
+  const float cbx = c[0] + c[2], cby = c[1] + c[3];
+  const float tlx = fmaxf(a[0], c[0]), tly = fmaxf(a[1], c[1]);
+  const float brx = fminf(abx, cbx), bry = fminf(aby, cby);
+  const float iw = fmaxf(0.0f, brx - tlx), ih = fmaxf(0.0f, bry - tly);
+  const float inter = iw * ih;
+  const float area_a = a[2] * a[3], area_c = c[2] * c[3];
+  const float uni = (area_a + area_c) - inter;
+  const float iou = inter / fmaxf(uni, 1e-7f);
+  return 1.0f - iou;
+}
+
+// ---- warp-level rectangular LSAP (scipy _lsap) -------------------------------------------------
+struct LsapMem {
+  double* u; double* v; double* spc;
+  int* path; int* col4row; int* row4col; int* remaining;
+  unsigned char* SR; unsigned char* SC;
+};
+
+__device__ __forceinline__ double warp_min_d(double x) {
+  for (int o = 16; o > 0; o >>= 1) x = fmin(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+
+// cost(r, c) = cost[r * ld + c] for r < nr, c < nc.  Writes col_for_row[r] (or -1) for r < nr.
+// Must be called by one full warp; every array lives in shared memory.
+__device__ void lsap_warp(const float* cost, int ld, int nr, int nc, const LsapMem& m, int* col_for_row, int lane) {
+  const bool tr = nc < nr;  // scipy transposes so that rows <= cols
+  const int R = tr ? nc : nr, C = tr ? nr : nc;
+  const int si = tr ? 1 : ld, sj = tr ? ld : 1;
+  for (int i = lane; i < R; i += 32) { m.u[i] = 0.0; m.col4row[i] = -1; }
+  for (int j = lane; j < C; j += 32) { m.v[j] = 0.0; m.row4col[j] = -1; m.path[j] = -1; }
+  __syncwarp();
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  for (int cur = 0; cur < R; ++cur) {
+    for (int j = lane; j < C; j += 32) { m.spc[j] = inf; m.SC[j] = 0; m.remaining[j] = C - 1 - j; }
+    for (int i = lane; i < R; i += 32) m.SR[i] = 0;
+    __syncwarp();
+    double min_val = 0.0;
+    int i = cur, num_remaining = C, sink = -1;
+    while (sink == -1) {
+      if (lane == 0) m.SR[i] = 1;
+      const double ui = m.u[i];
+      const float* crow = cost + static_cast<long long>(i) * si;
+      double lowest = inf;
+      int first_it = 0x7fffffff, last_un = -1;
+      for (int it = lane; it < num_remaining; it += 32) {
+        const int j = m.remaining[it];
+        const double r = ((min_val + static_cast<double>(crow[static_cast<long long>(j) * sj])) - ui) - m.v[j];
+        double sv = m.spc[j];
+        if (r < sv) { m.path[j] = i; m.spc[j] = r; sv = r; }
+        const bool unassigned = m.row4col[j] == -1;
+        if (sv < lowest) { lowest = sv; first_it = it; last_un = unassigned ? it : -1; }
+        else if (sv == lowest && unassigned) { last_un = it; }
+      }
+      const double mn = warp_min_d(lowest);
+      int f = (lowest == mn) ? first_it : 0x7fffffff;
+      int lu = (lowest == mn) ? last_un : -1;
+      for (int o = 16; o > 0; o >>= 1) {
+        f = min(f, __shfl_xor_sync(0xffffffffu, f, o));
+        lu = max(lu, __shfl_xor_sync(0xffffffffu, lu, o));
+      }
+      const int index = lu >= 0 ? lu : f;
+      min_val = mn;
+      const int j = m.remaining[index];
+      const int owner = m.row4col[j];
+      __syncwarp();
+      if (owner == -1) sink = j; else i = owner;
+      if (lane == 0) { m.SC[j] = 1; m.remaining[index] = m.remaining[num_remaining - 1]; }
+      --num_remaining;
+      __syncwarp();
+    }
+    if (lane == 0) m.u[cur] += min_val;
+    for (int i2 = lane; i2 < R; i2 += 32)
+      if (m.SR[i2] && i2 != cur) m.u[i2] += min_val - m.spc[m.col4row[i2]];
+    for (int j2 = lane; j2 < C; j2 += 32)
+      if (m.SC[j2]) m.v[j2] -= min_val - m.spc[j2];
+    __syncwarp();
+    if (lane == 0) {
+      int j = sink;
+      for (;;) {
+        const int ii = m.path[j];
+        m.row4col[j] = ii;
+        const int t = m.col4row[ii];
+        m.col4row[ii] = j;
+        j = t;
+        if (ii == cur) break;
+      }
+    }
+    __syncwarp();
+  }
+  for (int r = lane; r < nr; r += 32) col_for_row[r] = -1;
+  __syncwarp();
+  if (tr) { for (int k = lane; k < R; k += 32) col_for_row[m.col4row[k]] = k; }
+  else    { for (int k = lane; k < R; k += 32) col_for_row[k] = m.col4row[k]; }
+  __syncwarp();
+}
+
+__host__ __device__ inline size_t lsap_bytes(int n) {
+  return (static_cast<size_t>(n) * (3 * 8 + 4 * 4 + 2) + 64 + 15) / 16 * 16;
+}
+__device__ inline LsapMem lsap_carve(uint8_t* p, int n) {
+  LsapMem m;
+  m.u = reinterpret_cast<double*>(p); m.v = m.u + n; m.spc = m.v + n;
+  m.path = reinterpret_cast<int*>(m.spc + n); m.col4row = m.path + n; m.row4col = m.col4row + n;
+  m.remaining = m.row4col + n;
+  m.SR = reinterpret_cast<unsigned char*>(m.remaining + n); m.SC = m.SR + n;
+  return m;
+}
+
+// ---- kernels -------------------------------------------------------------------------------------
+// detection features -> L2-normalised copies (matching.py:125-130), one block per (det, stream)
+__global__ void __launch_bounds__(128) normalize_kernel(Dev t, const int* __restrict__ det_count,
+                                                        const int* __restrict__ crop_slot, int stride_k,
+                                                        const float* __restrict__ feats) {
+  const int s = blockIdx.y, d = blockIdx.x;
+  if (d >= min(det_count[s], t.D)) return;
+  const int row = crop_slot[static_cast<long long>(s) * stride_k + d];
+  if (row < 0) return;
+  __shared__ float red[128];
+  const float* f = feats + static_cast<long long>(row) * t.F;
+  float ss = 0.0f;
+  for (int k = threadIdx.x; k < t.F; k += blockDim.x) { const float v = f[k]; ss += v * v; }
+  red[threadIdx.x] = ss;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float nrm = fmaxf(sqrtf(red[0]), 1e-7f);
+  float* o = t.featn + (static_cast<long long>(s) * t.D + d) * t.F;
+  for (int k = threadIdx.x; k < t.F; k += blockDim.x) o[k] = f[k] / nrm;
+}
+
+// K8: cost[slot][d] = min over the gallery of max(0, 1 - <g, f_d>)  (matching.py:109-217)
+constexpr int APP_DT = 16;  // detections per shared-memory tile
+__global__ void __launch_bounds__(256) appearance_kernel(Dev t, const int* __restrict__ det_count,
+                                                         const int* __restrict__ crop_slot, int stride_k) {
+  extern __shared__ float sm_f[];  // [APP_DT][F] detection tile, then [8][APP_DT] per-warp minima
+  const int s = blockIdx.y, ti = blockIdx.x;
+  if (ti >= t.n_tracks[s]) return;
+  const int slot = t.order[static_cast<long long>(s) * t.T + ti];
+  const long long ts = static_cast<long long>(s) * t.T + slot;
+  if (t.state[ts] != CONFIRMED) return;  // only confirmed tracks enter the appearance cascade
+  const int nd = min(det_count[s], t.D);
+  const int ng = t.gal_count[ts];
+  const float* gal = t.gallery + ts * t.G * t.F;
+  float* out = t.app_cost + ts * t.D;
+  float* tile = sm_f;
+  float* wmin = sm_f + APP_DT * t.F;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int d0 = 0; d0 < nd; d0 += APP_DT) {
+    const int dn = min(APP_DT, nd - d0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < dn * t.F; idx += blockDim.x) {
+      const int dd = idx / t.F, k = idx - dd * t.F;
+      const bool has = crop_slot[static_cast<long long>(s) * stride_k + d0 + dd] >= 0;
+      tile[idx] = has ? t.featn[(static_cast<long long>(s) * t.D + d0 + dd) * t.F + k] : 0.0f;
+    }
+    __syncthreads();
+    float best = INFTY_COST;  // lane dd < dn tracks the minimum for detection d0 + dd
+    for (int g = warp; g < ng; g += 8) {
+      const float* grow = gal + static_cast<long long>(g) * t.F;
+      float acc[APP_DT];
+#pragma unroll
+      for (int dd = 0; dd < APP_DT; ++dd) acc[dd] = 0.0f;
+      for (int k = lane; k < t.F; k += 32) {
+        const float gv = grow[k];
+#pragma unroll
+        for (int dd = 0; dd < APP_DT; ++dd) acc[dd] = fmaf(gv, tile[dd * t.F + k], acc[dd]);
+      }
+#pragma unroll
+      for (int dd = 0; dd < APP_DT; ++dd) {
+        float v = acc[dd];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == dd) best = fminf(best, fmaxf(1.0f - v, 0.0f));
+      }
+    }
+    if (lane < APP_DT) wmin[warp * APP_DT + lane] = best;
+    __syncthreads();
+    if (threadIdx.x < dn) {
+      float v = INFTY_COST;
+      for (int w = 0; w < 8; ++w) v = fminf(v, wmin[w * APP_DT + threadIdx.x]);
+      const bool has = crop_slot[static_cast<long long>(s) * stride_k + d0 + threadIdx.x] >= 0;
+      out[d0 + threadIdx.x] = (has && ng > 0) ? v : INFTY_COST;
+    }
+  }
+}
+
+struct StepIO {
+  const float* boxes; const float* scores; const int* labels; int stride_k;
+  const int* det_index; const int* det_count; const int* crop_slot;
+  int* out_tracks; float* out_conf; int* out_count;
+};
+
+// K7 + K9-K12: predict, cascade, IoU stage, update, initiate, prune, output.  One CTA per stream.
+__global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = t.T, Dm = t.D;
+  // shared-memory carve-up
+  uint8_t* p = smraw;
+  float* d_tlwh = reinterpret_cast<float*>(p); p += sizeof(float) * 4 * Dm;
+  float* d_xyah = reinterpret_cast<float*>(p); p += sizeof(float) * 4 * Dm;
+  int* U = reinterpret_cast<int*>(p); p += sizeof(int) * Dm;          // unmatched detections, ordered
+  int* Utmp = reinterpret_cast<int*>(p); p += sizeof(int) * Dm;
+  int* conf_list = reinterpret_cast<int*>(p); p += sizeof(int) * T;   // order positions of confirmed tracks
+  int* tent_list = reinterpret_cast<int*>(p); p += sizeof(int) * T;
+  int* L = reinterpret_cast<int*>(p); p += sizeof(int) * T;           // rows of the current problem (order positions)
+  int* match = reinterpret_cast<int*>(p); p += sizeof(int) * T;       // by order position: detection or -1
+  int* cfr = reinterpret_cast<int*>(p); p += sizeof(int) * T;         // col_for_row of the current LSAP
+  int* det_used = reinterpret_cast<int*>(p); p += sizeof(int) * Dm;
+  p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~static_cast<uintptr_t>(15));
+  const int nmax = max(T, Dm);
+  LsapMem lm = lsap_carve(p, nmax);
+  __shared__ int s_nconf, s_ntent, s_nU, s_nL, s_levels[8], s_nt;
+
+  const long long sb = static_cast<long long>(s) * T;
+  int nt = t.n_tracks[s];
+  int nd = io.det_count[s];
+  if (nd > Dm) { nd = Dm; if (tid == 0) atomicOr(&t.overflow[s], 2); }
+  int* order = t.order + sb;
+
+  // -- K7 predict (tracker_core.py:44-49, track.py:76-80)
+  for (int k = tid; k < nt; k += ASSOC_THREADS) {
+    const long long ts = sb + order[k];
+    float mean[8], cov[16];
+    for (int i = 0; i < 8; ++i) mean[i] = t.mean[ts * 8 + i];
+    for (int i = 0; i < 16; ++i) cov[i] = t.cov[ts * 16 + i];
+    kf_predict(mean, cov);
+    for (int i = 0; i < 8; ++i) t.mean[ts * 8 + i] = mean[i];
+    for (int i = 0; i < 16; ++i) t.cov[ts * 16 + i] = cov[i];
+    t.age[ts] += 1;
+    t.tsu[ts] += 1;
+    match[k] = -1;
+  }
+  // -- detections (deepsort_tracker.py:180-198, detection.py:15-47)
+  for (int k = tid; k < nd; k += ASSOC_THREADS) {
+    const long long o = static_cast<long long>(s) * io.stride_k + io.det_index[static_cast<long long>(s) * io.stride_k + k];
+    const float4 b = reinterpret_cast<const float4*>(io.boxes)[o];
+    float tl[4] = {b.x, b.y, b.z - b.x, b.w - b.y}, z[4];
+    tlwh_to_xyah(tl, z);
+    for (int i = 0; i < 4; ++i) { d_tlwh[4 * k + i] = tl[i]; d_xyah[4 * k + i] = z[i]; }
+    U[k] = k;
+    det_used[k] = 0;
+  }
+  if (tid < 8) s_levels[tid] = 0;
+  __syncthreads();
+  // -- confirmed / tentative lists in track-list order (tracker_core.py:112-117)
+  if (tid == 0) {
+    int nc = 0, nn = 0;
+    for (int k = 0; k < nt; ++k) {
+      const long long ts = sb + order[k];
+      if (t.state[ts] == CONFIRMED) {
+        conf_list[nc++] = k;
+        const int lv = t.tsu[ts];
+        if (lv >= 1 && lv <= t.max_age && lv < 256) s_levels[lv >> 5] |= 1u << (lv & 31);
+      } else if (t.state[ts] == TENTATIVE) {
+        tent_list[nn++] = k;
+      }
+    }
+    s_nconf = nc; s_ntent = nn; s_nU = nd;
+  }
+  __syncthreads();
+
+  float* cm = t.cost_ws + static_cast<long long>(s) * T * Dm;
+  // One matching problem: rows L[0..nL), columns U[0..nU); metric 0 = gated appearance, 1 = IoU.
+  auto solve = [&](int metric, float thr, float clamp) {
+    const int nL = s_nL, nU = s_nU;
+    for (int idx = tid; idx < nL * nU; idx += ASSOC_THREADS) {
+      const int i = idx / nU, j = idx - i * nU;
+      const long long ts = sb + order[L[i]];
+      const int d = U[j];
+      float c;
+      if (metric == 0) {
+        c = t.app_cost[ts * Dm + d];
+        // linear_assignment.py:160-212: gate by the squared Mahalanobis distance (4 dof, strict >)
+        const float g = kf_gating(t.mean + ts * 8, t.cov + ts * 16, d_xyah + 4 * d, nU);
+        if (g > CHI2_GATE) c = INFTY_COST;
+      } else {
+        float tl[4];
+        mean_to_tlwh(t.mean + ts * 8, tl);
+        c = iou_cost(tl, d_tlwh + 4 * d);
+      }
+      if (c > thr) c = clamp;  // linear_assignment.py:58
+      cm[idx] = c;
+    }
+    __syncthreads();
+    if (warp == 0) lsap_warp(cm, nU, nL, nU, lm, cfr, lane);
+    __syncthreads();
+    // linear_assignment.py:64-88: keep pairs with cost <= max_distance, unmatched lists keep their order
+    for (int i = tid; i < nL; i += ASSOC_THREADS) {
+      const int j = cfr[i];
+      if (j >= 0 && cm[i * nU + j] <= thr) { match[L[i]] = U[j]; det_used[U[j]] = 1; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int n = 0;
+      for (int j = 0; j < nU; ++j)
+        if (!det_used[U[j]]) Utmp[n++] = U[j];
+      for (int j = 0; j < n; ++j) U[j] = Utmp[j];
+      s_nU = n;
+    }
+    __syncthreads();
+  };
+
+  // -- stage 1: matching cascade over confirmed tracks (linear_assignment.py:91-157)
+  for (int level = 1; level <= t.max_age; ++level) {
+    if (level < 256 && !((s_levels[level >> 5] >> (level & 31)) & 1u)) continue;  // no track at this level
+    if (s_nU == 0) break;
+    if (tid == 0) {
+      int n = 0;
+      for (int k = 0; k < s_nconf; ++k)
+        if (t.tsu[sb + order[conf_list[k]]] == level) L[n++] = conf_list[k];
+      s_nL = n;
+    }
+    __syncthreads();
+    if (s_nL > 0) solve(0, t.thr_cos, t.clamp_cos);
+    __syncthreads();
+  }
+  // -- stage 2: IoU matching (tracker_core.py:138-166)
+  if (tid == 0) {
+    int n = 0;
+    for (int k = 0; k < s_ntent; ++k) L[n++] = tent_list[k];
+    for (int k = 0; k < s_nconf; ++k) {
+      const int pos = conf_list[k];
+      if (match[pos] < 0 && t.tsu[sb + order[pos]] == 1) L[n++] = pos;
+    }
+    s_nL = n;
+  }
+  __syncthreads();
+  if (s_nL > 0 && s_nU > 0) solve(1, t.thr_iou, t.clamp_iou);
+
+  // -- update matched tracks / mark missed (tracker_core.py:62-68, track.py:82-119)
+  for (int k = warp; k < nt; k += ASSOC_THREADS / 32) {
+    const long long ts = sb + order[k];
+    const int d = match[k];
+    if (d >= 0) {
+      const int row = io.crop_slot[static_cast<long long>(s) * io.stride_k + d];
+      if (row >= 0) {  // track.py:70-74: append to the gallery, FIFO at the budget
+        const int cnt = t.gal_count[ts], head = t.gal_head[ts];
+        const int pos = cnt < t.G ? (head + cnt) % t.G : head;
+        float* dst = t.gallery + (ts * t.G + pos) * t.F;
+        const float* src = t.featn + (static_cast<long long>(s) * Dm + d) * t.F;
+        for (int f = lane; f < t.F; f += 32) dst[f] = src[f];
+        if (lane == 0) {
+          if (cnt < t.G) t.gal_count[ts] = cnt + 1; else t.gal_head[ts] = (head + 1) % t.G;
+        }
+      }
+      if (lane == 0) {
+        float mean[8], cov[16];
+        for (int i = 0; i < 8; ++i) mean[i] = t.mean[ts * 8 + i];
+        for (int i = 0; i < 16; ++i) cov[i] = t.cov[ts * 16 + i];
+        kf_update(mean, cov, d_xyah + 4 * d);
+        for (int i = 0; i < 8; ++i) t.mean[ts * 8 + i] = mean[i];
+        for (int i = 0; i < 16; ++i) t.cov[ts * 16 + i] = cov[i];
+        const long long o = static_cast<long long>(s) * io.stride_k + io.det_index[static_cast<long long>(s) * io.stride_k + d];
+        const int hits = t.hits[ts] + 1;
+        t.hits[ts] = hits;
+        t.tsu[ts] = 0;
+        t.conf[ts] = io.scores[o];
+        t.cls[ts] = io.labels[o];
+        if (t.state[ts] == TENTATIVE && hits >= t.n_init) t.state[ts] = CONFIRMED;
+      }
+    } else if (lane == 0) {
+      if (t.state[ts] == TENTATIVE) t.state[ts] = DELETED;
+      else if (t.state[ts] == CONFIRMED && t.tsu[ts] > t.max_age) t.state[ts] = DELETED;
+    }
+  }
+  __syncthreads();
+  // -- prune deleted tracks, then initiate one track per unmatched detection in ascending order
+  //    (tracker_core.py:70-75, :180-194; ids come from the stream's own counter)
+  if (tid == 0) {
+    int n = 0;
+    int nfree = t.n_free[s];
+    for (int k = 0; k < nt; ++k) {
+      const int slot = order[k];
+      if (t.state[sb + slot] == DELETED) t.free_slots[sb + nfree++] = slot; else order[n++] = slot;
+    }
+    const int nU = s_nU;
+    int created = 0;
+    for (int j = 0; j < nU; ++j) {
+      if (nfree == 0) { atomicOr(&t.overflow[s], 1); break; }
+      const int slot = t.free_slots[sb + --nfree];
+      order[n++] = slot;
+      Utmp[created++] = slot;
+      const long long ts = sb + slot;
+      t.track_id[ts] = t.next_id[s]++;
+      t.state[ts] = TENTATIVE;
+      t.hits[ts] = 1; t.age[ts] = 1; t.tsu[ts] = 0;
+      t.gal_count[ts] = 0; t.gal_head[ts] = 0;
+    }
+    t.n_free[s] = nfree;
+    t.n_tracks[s] = n;
+    s_nt = n;
+    s_nL = created;
+  }
+  __syncthreads();
+  for (int j = warp; j < s_nL; j += ASSOC_THREADS / 32) {
+    const int d = U[j];
+    const long long ts = sb + Utmp[j];
+    const int row = io.crop_slot[static_cast<long long>(s) * io.stride_k + d];
+    if (row >= 0) {
+      float* dst = t.gallery + ts * t.G * t.F;
+      const float* src = t.featn + (static_cast<long long>(s) * Dm + d) * t.F;
+      for (int f = lane; f < t.F; f += 32) dst[f] = src[f];
+      if (lane == 0) t.gal_count[ts] = 1;
+    }
+    if (lane == 0) {
+      float mean[8], cov[16];
+      kf_initiate(d_xyah + 4 * d, mean, cov);
+      for (int i = 0; i < 8; ++i) t.mean[ts * 8 + i] = mean[i];
+      for (int i = 0; i < 16; ++i) t.cov[ts * 16 + i] = cov[i];
+      const long long o = static_cast<long long>(s) * io.stride_k + io.det_index[static_cast<long long>(s) * io.stride_k + d];
+      t.conf[ts] = io.scores[o];
+      t.cls[ts] = io.labels[o];
+    }
+  }
+  __syncthreads();
+  // -- output (deepsort_tracker.py:125-141): confirmed and updated this frame, track-list order
+  if (tid == 0) {
+    int n = 0;
+    const int ntn = s_nt;
+    for (int k = 0; k < ntn; ++k) {
+      const long long ts = sb + order[k];
+      if (t.state[ts] != CONFIRMED || t.tsu[ts] != 0) continue;
+      float tl[4];
+      mean_to_tlwh(t.mean + ts * 8, tl);
+      const float w = tl[2] > 0.0f ? tl[2] : 0.0f, h = tl[3] > 0.0f ? tl[3] : 0.0f;
+      int* o = io.out_tracks + (sb + n) * 6;
+      o[0] = __float2int_rn(tl[0]);
+      o[1] = __float2int_rn(tl[1]);
+      o[2] = __float2int_rn(tl[0] + w);
+      o[3] = __float2int_rn(tl[1] + h);
+      o[4] = t.track_id[ts];
+      o[5] = t.cls[ts];
+      io.out_conf[sb + n] = t.conf[ts];
+      ++n;
+    }
+    io.out_count[s] = n;
+  }
+}
+
+__global__ void reset_kernel(Dev t) {
+  const int s = blockIdx.x;
+  const long long sb = static_cast<long long>(s) * t.T;
+  for (int k = threadIdx.x; k < t.T; k += blockDim.x) {
+    t.free_slots[sb + k] = t.T - 1 - k;  // slot 0 is popped first
+    t.state[sb + k] = DELETED;
+    t.gal_count[sb + k] = 0;
+    t.gal_head[sb + k] = 0;
+  }
+  if (threadIdx.x == 0) { t.n_tracks[s] = 0; t.n_free[s] = t.T; t.next_id[s] = 1; t.overflow[s] = 0; }
+}
+
+__global__ void lsap_kernel(const float* cost, int nr, int nc, int* col_for_row) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  LsapMem m = lsap_carve(smraw, max(nr, nc));
+  int* cfr = reinterpret_cast<int*>(smraw + lsap_bytes(max(nr, nc)));
+  lsap_warp(cost + static_cast<long long>(blockIdx.x) * nr * nc, nc, nr, nc, m, cfr, threadIdx.x);
+  for (int r = threadIdx.x; r < nr; r += 32) col_for_row[static_cast<long long>(blockIdx.x) * nr + r] = cfr[r];
+}
+
+__global__ void gating_kernel(const float* state, const float* meas, int n, int m, float* d2) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * m) return;
+  const int i = idx / m;
+  d2[idx] = kf_gating(state + static_cast<long long>(i) * 24, state + static_cast<long long>(i) * 24 + 8,
+                      meas + static_cast<long long>(idx) * 4, m);
+}
+
+size_t assoc_smem(int T, int D) {
+  return sizeof(float) * 8 * D + sizeof(int) * (3 * D + 5 * T) + 16 + lsap_bytes(std::max(T, D));
+}
+
+}  // namespace
+}  // namespace aicam
+
+struct aicam_tracker {
+  aicam::Dev d;
+  aicam_tracker_config cfg;
+  std::vector<void*> allocs;
+};
+
+using namespace aicam;
+
+namespace {
+template <typename Tp>
+int dev_alloc(aicam_tracker* t, Tp** p, size_t n) {
+  void* q = nullptr;
+  if (cudaMalloc(&q, n * sizeof(Tp)) != cudaSuccess) return fail(AICAM_ERR_CUDA, "tracker_create: cudaMalloc failed");
+  cudaMemset(q, 0, n * sizeof(Tp));
+  t->allocs.push_back(q);
+  *p = static_cast<Tp*>(q);
+  return AICAM_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int aicam_tracker_create(const aicam_tracker_config* cfg, aicam_tracker** out) {
+  if (!cfg || !out) return fail(AICAM_ERR_INVALID_ARG, "tracker_create: null argument");
+  *out = nullptr;
+  if (cfg->n_streams <= 0 || cfg->max_tracks <= 0 || cfg->max_dets <= 0 || cfg->feature_dim <= 0)
+    return fail(AICAM_ERR_INVALID_ARG, "tracker_create: sizes must be positive");
+  if (cfg->max_tracks > 1024 || cfg->max_dets > 1024)
+    return fail(AICAM_ERR_CAPACITY, "tracker_create: max_tracks and max_dets are limited to 1024");
+  if (cfg->nn_budget <= 0)
+    return fail(AICAM_ERR_UNSUPPORTED, "tracker_create: nn_budget must be positive (unbounded galleries unsupported)");
+  if (cfg->max_age < 1 || cfg->max_age > 255 || cfg->n_init < 1)
+    return fail(AICAM_ERR_INVALID_ARG, "tracker_create: max_age must be in 1..255 and n_init >= 1");
+  AICAM_CUDA_OK(cudaSetDevice(cfg->device));
+  aicam_tracker* t = new aicam_tracker();
+  t->cfg = *cfg;
+  Dev& d = t->d;
+  d.S = cfg->n_streams; d.T = cfg->max_tracks; d.D = cfg->max_dets; d.F = cfg->feature_dim; d.G = cfg->nn_budget;
+  d.thr_cos = static_cast<float>(cfg->max_cosine_distance);
+  d.clamp_cos = static_cast<float>(cfg->max_cosine_distance + 1e-5);
+  d.thr_iou = static_cast<float>(cfg->max_iou_distance);
+  d.clamp_iou = static_cast<float>(cfg->max_iou_distance + 1e-5);
+  d.max_age = cfg->max_age; d.n_init = cfg->n_init;
+  const size_t ST = static_cast<size_t>(d.S) * d.T;
+  int rc = 0;
+  rc |= dev_alloc(t, &d.mean, ST * 8);  rc |= dev_alloc(t, &d.cov, ST * 16);
+  rc |= dev_alloc(t, &d.track_id, ST);  rc |= dev_alloc(t, &d.state, ST);  rc |= dev_alloc(t, &d.hits, ST);
+  rc |= dev_alloc(t, &d.age, ST);       rc |= dev_alloc(t, &d.tsu, ST);    rc |= dev_alloc(t, &d.cls, ST);
+  rc |= dev_alloc(t, &d.conf, ST);      rc |= dev_alloc(t, &d.gal_count, ST); rc |= dev_alloc(t, &d.gal_head, ST);
+  rc |= dev_alloc(t, &d.gallery, ST * d.G * d.F);
+  rc |= dev_alloc(t, &d.order, ST);     rc |= dev_alloc(t, &d.free_slots, ST);
+  rc |= dev_alloc(t, &d.n_tracks, d.S); rc |= dev_alloc(t, &d.n_free, d.S); rc |= dev_alloc(t, &d.next_id, d.S);
+  rc |= dev_alloc(t, &d.overflow, d.S);
+  rc |= dev_alloc(t, &d.app_cost, ST * d.D); rc |= dev_alloc(t, &d.cost_ws, ST * d.D);
+  rc |= dev_alloc(t, &d.featn, static_cast<size_t>(d.S) * d.D * d.F);
+  if (rc) { aicam_tracker_destroy(t); return AICAM_ERR_CUDA; }
+  const size_t sm = assoc_smem(d.T, d.D);
+  if (sm > 200 * 1024) { aicam_tracker_destroy(t); return fail(AICAM_ERR_CAPACITY, "tracker_create: max_tracks/max_dets need too much shared memory"); }
+  cudaFuncSetAttribute(assoc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+  cudaFuncSetAttribute(appearance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       static_cast<int>((APP_DT * d.F + 8 * APP_DT) * sizeof(float)));
+  if (int r2 = aicam_tracker_reset(t, nullptr)) { aicam_tracker_destroy(t); return r2; }
+  AICAM_CUDA_OK(cudaDeviceSynchronize());
+  *out = t;
+  return AICAM_OK;
+}
+
+void aicam_tracker_destroy(aicam_tracker* t) {
+  if (!t) return;
+  cudaSetDevice(t->cfg.device);
+  for (void* p : t->allocs) cudaFree(p);
+  delete t;
+}
+
+int aicam_tracker_reset(aicam_tracker* t, void* stream) {
+  if (!t) return fail(AICAM_ERR_INVALID_ARG, "tracker_reset: null handle");
+  reset_kernel<<<t->d.S, 128, 0, static_cast<cudaStream_t>(stream)>>>(t->d);
+  count_launch();
+  return last_launch("reset_kernel");
+}
+
+int aicam_tracker_step(aicam_tracker* t, const float* boxes, const float* scores, const int32_t* labels, int stride_k,
+                       const int32_t* det_index, const int32_t* det_count, const int32_t* crop_slot, const float* feats,
+                       int32_t* out_tracks, float* out_conf, int32_t* out_count, void* stream) {
+  if (!t || !boxes || !scores || !labels || !det_index || !det_count || !crop_slot || !out_tracks || !out_conf || !out_count)
+    return fail(AICAM_ERR_INVALID_ARG, "tracker_step: null argument");
+  if (stride_k <= 0) return fail(AICAM_ERR_INVALID_ARG, "tracker_step: stride_k must be positive");
+  const Dev& d = t->d;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (feats) {
+    normalize_kernel<<<dim3(d.D, d.S), 128, 0, st>>>(d, det_count, crop_slot, stride_k, feats);
+    count_launch();
+    if (int rc = last_launch("normalize_kernel")) return rc;
+    const size_t sm = (APP_DT * d.F + 8 * APP_DT) * sizeof(float);
+    appearance_kernel<<<dim3(d.T, d.S), 256, sm, st>>>(d, det_count, crop_slot, stride_k);
+    count_launch();
+    if (int rc = last_launch("appearance_kernel")) return rc;
+  }
+  StepIO io{boxes, scores, labels, stride_k, det_index, det_count, crop_slot, out_tracks, out_conf, out_count};
+  assoc_kernel<<<d.S, ASSOC_THREADS, assoc_smem(d.T, d.D), st>>>(d, io);
+  count_launch();
+  return last_launch("assoc_kernel");
+}
+
+int aicam_tracker_snapshot(aicam_tracker* t, int stream_index, int32_t* ints, float* floats, int capacity) {
+  if (!t || !ints || !floats || stream_index < 0 || stream_index >= t->d.S)
+    return fail(AICAM_ERR_INVALID_ARG, "tracker_snapshot: bad arguments");
+  const Dev& d = t->d;
+  AICAM_CUDA_OK(cudaSetDevice(t->cfg.device));
+  AICAM_CUDA_OK(cudaDeviceSynchronize());
+  int n = 0;
+  AICAM_CUDA_OK(cudaMemcpy(&n, d.n_tracks + stream_index, sizeof(int), cudaMemcpyDeviceToHost));
+  if (n > capacity) return fail(AICAM_ERR_CAPACITY, "tracker_snapshot: capacity too small");
+  const size_t T = d.T, sb = static_cast<size_t>(stream_index) * T;
+  std::vector<int> order(T), id(T), state(T), hits(T), age(T), tsu(T), cls(T), gc(T);
+  std::vector<float> mean(T * 8), cov(T * 16), conf(T);
+  auto get = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); };
+  AICAM_CUDA_OK(get(order.data(), d.order + sb, T * 4));
+  AICAM_CUDA_OK(get(id.data(), d.track_id + sb, T * 4));
+  AICAM_CUDA_OK(get(state.data(), d.state + sb, T * 4));
+  AICAM_CUDA_OK(get(hits.data(), d.hits + sb, T * 4));
+  AICAM_CUDA_OK(get(age.data(), d.age + sb, T * 4));
+  AICAM_CUDA_OK(get(tsu.data(), d.tsu + sb, T * 4));
+  AICAM_CUDA_OK(get(cls.data(), d.cls + sb, T * 4));
+  AICAM_CUDA_OK(get(gc.data(), d.gal_count + sb, T * 4));
+  AICAM_CUDA_OK(get(conf.data(), d.conf + sb, T * 4));
+  AICAM_CUDA_OK(get(mean.data(), d.mean + sb * 8, T * 8 * 4));
+  AICAM_CUDA_OK(get(cov.data(), d.cov + sb * 16, T * 16 * 4));
+  for (int k = 0; k < n; ++k) {
+    const int sl = order[k];
+    int* io = ints + k * 7;
+    io[0] = id[sl]; io[1] = state[sl]; io[2] = hits[sl]; io[3] = age[sl]; io[4] = tsu[sl]; io[5] = cls[sl]; io[6] = gc[sl];
+    float* fo = floats + k * 25;
+    for (int i = 0; i < 8; ++i) fo[i] = mean[sl * 8 + i];
+    for (int i = 0; i < 16; ++i) fo[8 + i] = cov[sl * 16 + i];
+    fo[24] = conf[sl];
+  }
+  return n;
+}
+
+int aicam_tracker_overflow(aicam_tracker* t, int32_t* flags_host) {
+  if (!t || !flags_host) return fail(AICAM_ERR_INVALID_ARG, "tracker_overflow: null argument");
+  AICAM_CUDA_OK(cudaSetDevice(t->cfg.device));
+  AICAM_CUDA_OK(cudaDeviceSynchronize());
+  AICAM_CUDA_OK(cudaMemcpy(flags_host, t->d.overflow, sizeof(int) * t->d.S, cudaMemcpyDeviceToHost));
+  return AICAM_OK;
+}
+
+int aicam_lsap(const float* cost, int count, int nr, int nc, int32_t* col_for_row, void* stream) {
+  if (!cost || !col_for_row || count < 0 || nr <= 0 || nc <= 0 || nr > 1024 || nc > 1024)
+    return fail(AICAM_ERR_INVALID_ARG, "lsap: bad arguments (sizes are limited to 1024)");
+  if (count == 0) return AICAM_OK;
+  const size_t sm = lsap_bytes(std::max(nr, nc)) + sizeof(int) * nr + 16;
+  cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+  lsap_kernel<<<count, 32, sm, static_cast<cudaStream_t>(stream)>>>(cost, nr, nc, col_for_row);
+  count_launch();
+  return last_launch("lsap_kernel");
+}
+
+int aicam_kf_gating(const float* state, const float* meas, int n, int m, float* d2, void* stream) {
+  if (!state || !meas || !d2 || n < 0 || m <= 0) return fail(AICAM_ERR_INVALID_ARG, "kf_gating: bad arguments");
+  if (n == 0) return AICAM_OK;
+  gating_kernel<<<cdiv(n * m, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(state, meas, n, m, d2);
+  count_launch();
+  return last_launch("gating_kernel");
+}
+
+}  // extern "C"

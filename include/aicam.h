@@ -1,0 +1,230 @@
+/* aicam.h - C ABI of the B200-native AI-Camera hot path (YOLOv8 detect -> DeepSORT track).
+ *
+ * The reference (abdur75648/AI-Camera) is pure Python and has no FFI; its only native seam
+ * is the TensorRT engine object.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference repository root).  All functions:
+ *   - return 0 (AICAM_OK) or a negative AICAM_ERR_* code; aicam_last_error() gives the text;
+ *   - never throw and never exit;
+ *   - take raw DEVICE pointers unless a parameter is marked "host";
+ *   - are asynchronous on the given cudaStream_t (passed as void*; NULL = default stream)
+ *     and do not synchronise unless documented, like TRTEngine.infer
+ *     (src/trt_utils/trt_engine.py:188-201);
+ *   - allocate nothing on the hot path: engines and trackers own their workspaces, sized at
+ *     create time; callers own every I/O buffer.
+ * A handle is bound to one CUDA device and is not thread-safe (one per GPU, as the
+ * reference keeps one engine per process).
+ */
+#ifndef AICAM_H_
+#define AICAM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AICAM_OK 0
+#define AICAM_ERR_INVALID_ARG (-1)
+#define AICAM_ERR_CUDA (-2)
+#define AICAM_ERR_IO (-3)          /* blob missing/corrupt: FileNotFoundError/RuntimeError in trt_engine.py:46-60 */
+#define AICAM_ERR_CAPACITY (-4)    /* batch / crops / tracks exceed what the handle was created for */
+#define AICAM_ERR_UNSUPPORTED (-5)
+
+#define AICAM_KIND_YOLOV8 1
+#define AICAM_KIND_REID 2
+
+#define AICAM_YOLO_INPUT 640       /* src/config.py:16 */
+#define AICAM_REID_H 128           /* src/config.py:32 */
+#define AICAM_REID_W 64
+#define AICAM_HEAD_DFL 64          /* 4 sides x 16 DFL bins */
+
+typedef struct aicam_engine aicam_engine;
+typedef struct aicam_tracker aicam_tracker;
+
+int aicam_version(void);
+const char* aicam_last_error(void);
+/* Number of kernels this library has launched in the calling process (all handles). */
+uint64_t aicam_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Engine: replaces TRTEngine (src/trt_utils/trt_engine.py:15-216): __init__/_init_engine
+ * (deserialize_cuda_engine, :45-60) -> aicam_engine_create on a flat ".aicw" weight blob;
+ * get_input_details/get_output_details (:212-216) -> aicam_engine_io_*; infer (:151-203) ->
+ * aicam_engine_infer.
+ * ---------------------------------------------------------------------------------------- */
+int aicam_engine_create(const char* blob_path, int device, int max_batch, aicam_engine** out);
+void aicam_engine_destroy(aicam_engine* e);
+int aicam_engine_kind(const aicam_engine* e);        /* AICAM_KIND_* */
+int aicam_engine_max_batch(const aicam_engine* e);
+int aicam_engine_num_classes(const aicam_engine* e); /* yolov8: nc; reid: feature dim */
+int aicam_engine_num_anchors(const aicam_engine* e); /* yolov8: 8400 at 640x640 */
+double aicam_engine_flops_per_item(const aicam_engine* e); /* 2*MACs per frame / per crop */
+int aicam_engine_num_launches(const aicam_engine* e);      /* kernels per forward */
+/* Overwrite a bias vector by blob tensor name (host float32 in); used to calibrate the
+ * synthetic detector/ReID heads.  aicam_engine_get_bias reads it back (host out). */
+int aicam_engine_set_bias(aicam_engine* e, const char* name, const float* host, int n);
+int aicam_engine_get_bias(aicam_engine* e, const char* name, float* host, int n);
+
+/* YOLOv8 forward (the engine body behind yolo_detector.py:97).
+ *   in_nhwc4 : bf16 [batch][640][640][4]  (RGB in [0,1] + one zero channel), from aicam_preprocess
+ *   head     : fp32 [batch][num_anchors][64 + nc]  raw DFL logits + class logits, anchors
+ *              level-major (strides 8,16,32) then row-major */
+int aicam_yolo_forward(aicam_engine* e, const void* in_nhwc4, int batch, float* head, void* stream);
+
+/* ReID forward (the engine body behind reid_model.py:115).
+ *   crops_nhwc4 : bf16 [n][128][64][4] ImageNet-normalised RGB (+ zero channel), from aicam_reid_crops
+ *   feats       : fp32 [n][512], L2-normalised
+ *   n_dev       : optional device i32[1]: when not NULL the number of crops is read on the
+ *                 device (clamped to n, which then is the capacity, n <= max_batch), so that
+ *                 the whole frame step needs no host synchronisation (the reference syncs at
+ *                 reid_model.py:126) */
+int aicam_reid_forward(aicam_engine* e, const void* crops_nhwc4, int n, const int32_t* n_dev,
+                       float* feats, void* stream);
+
+/* Reference-layout converters used by the TRTEngine-shaped facade:
+ * fp32 NCHW [n][3][h][w] -> bf16 NHWC4 [n][h][w][4]. */
+int aicam_nchw_to_nhwc4(const float* in, int n, int h, int w, void* out_nhwc4, void* stream);
+
+/* One convolution (+bias, activation, residual) on NHWC bf16 - the operator both engines are
+ * built from; exposed for parity tests.  weights_oihw/bias are HOST float32. */
+typedef struct {
+  int batch, h, w, cin, cout, ksize, stride;
+  int act;        /* 0 none, 1 SiLU, 2 ReLU */
+  int res_mode;   /* 0 none, 1 act(conv)+res, 2 act(conv+res) */
+  int out_f32;    /* 0: bf16 output, 1: fp32 output */
+} aicam_conv_desc;
+int aicam_conv2d(const aicam_conv_desc* d, const void* in_nhwc, const float* weights_oihw,
+                 const float* bias, const void* res_nhwc, void* out_nhwc, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Preprocessing: replaces image_processing.letterbox + preprocess_yolo_input
+ * (src/utils/image_processing.py:7-102, called at yolo_detector.py:86) and the H2D copy of
+ * the fp32 tensor (yolo_detector.py:91).
+ *   frames : u8 [batch][h][w][3] BGR
+ *   format 0: out = fp32 [batch][3][640][640] RGB/255 (the reference tensor, bit-exact)
+ *   format 1: out = bf16 [batch][640][640][4] (what aicam_yolo_forward consumes)
+ * meta (host out, may be NULL): ratio, pad_w, pad_h as the reference returns them. */
+typedef struct {
+  double ratio, pad_w, pad_h;
+} aicam_letterbox;
+int aicam_letterbox_params(int h, int w, aicam_letterbox* meta);
+int aicam_preprocess(const uint8_t* frames, int batch, int h, int w, int format, void* out,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Detection post-processing: the decode + NMS the reference's engine embeds (it returns
+ * num_dets/bboxes/scores/labels, yolo_detector.py:49-54,108-112) and the part of
+ * YOLODetector.detect after the engine (yolo_detector.py:107-149, scale_bboxes
+ * image_processing.py:141-183).
+ *   head        : fp32 [batch][anchors][64+nc]
+ *   num_dets    : i32 [batch]
+ *   boxes_lb    : fp32 [batch][topk][4] xyxy in letterbox pixels (engine output)
+ *   boxes_orig  : fp32 [batch][topk][4] xyxy in frame pixels, clipped (detect() output), may be NULL
+ *   scores      : fp32 [batch][topk]       labels : i32 [batch][topk]
+ * Entries past num_dets[b] are zero.  Order: score descending, anchor index ascending. */
+typedef struct {
+  float score_thr;   /* src/config.py:17 */
+  float iou_thr;     /* src/config.py:18 */
+  int topk;          /* <= 1024 */
+  int max_candidates;/* <= 4096, pre-NMS candidates kept per frame */
+  int frame_h, frame_w; /* for boxes_orig */
+} aicam_nms_params;
+int aicam_decode_nms(const float* head, int batch, int anchors, int nc, const aicam_nms_params* p,
+                     int32_t* num_dets, float* boxes_lb, float* boxes_orig, float* scores,
+                     int32_t* labels, void* workspace, size_t workspace_bytes, void* stream);
+size_t aicam_decode_nms_workspace(int batch, int anchors, const aicam_nms_params* p);
+/* Decode only: per-anchor boxes [batch][anchors][4], best score, best label. */
+int aicam_decode(const float* head, int batch, int anchors, int nc, float* boxes, float* scores,
+                 int32_t* labels, void* stream);
+/* NMS only, on caller-provided per-anchor boxes/scores/labels (bit-exact parity entry). */
+int aicam_nms(const float* boxes, const float* scores, const int32_t* labels, int batch, int anchors,
+              const aicam_nms_params* p, int32_t* num_dets, float* boxes_lb, float* boxes_orig,
+              float* out_scores, int32_t* out_labels, int32_t* keep_index, void* workspace,
+              size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ReID crops: replaces DeepSORT.update steps 1-2 (class/confidence filter,
+ * src/tracker/deepsort_tracker.py:88-101), _extract_image_crops (:143-159),
+ * preprocess_reid_input (image_processing.py:105-138) and the batch concat + H2D
+ * (reid_model.py:83-101).
+ *   frames : u8 [batch][h][w][3] BGR;  boxes fp32 [batch][stride_k][4] xyxy frame px
+ *   det_index : i32 [batch][stride_k]  out: indices (into the frame's detections) that pass
+ *               the filter, in order; det_count i32 [batch]
+ *   crop_slot : i32 [batch][stride_k]  out: row in `crops` of the filtered detection's crop,
+ *               or -1 when the crop rectangle is empty (feature None, :155-158)
+ *   crops     : format 0: fp32 [max_crops][3][128][64] (reference tensor, bit-exact)
+ *               format 1: bf16 [max_crops][128][64][4]
+ *   crop_rect : i32 [max_crops][5] out: frame index, x1, y1, x2, y2 (int()-truncated, clamped)
+ *   crop_count: i32 [1] total crops written (<= max_crops; crops beyond capacity are dropped
+ *               and their crop_slot is -1)
+ * class_mask_lo/hi: bit c set = COCO class c is tracked (src/config.py:53 -> ids 0,2,3,5,7). */
+int aicam_reid_crops(const uint8_t* frames, int batch, int h, int w, const float* boxes,
+                     const float* scores, const int32_t* labels, const int32_t* num_dets,
+                     int stride_k, float min_confidence, uint64_t class_mask_lo,
+                     uint64_t class_mask_hi, int format, int max_crops, int32_t* det_index,
+                     int32_t* det_count, int32_t* crop_slot, int32_t* crop_rect, void* crops,
+                     int32_t* crop_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tracker: replaces TrackerCore / Track / KalmanFilter / matching / linear_assignment
+ * (all modules under src/tracker/core/) and the formatting loop of DeepSORT.update
+ * (deepsort_tracker.py:123-141).  One handle holds n_streams independent trackers, each
+ * with its own id counter starting at 1 (track.py:21 is a process-global; one reference
+ * process per stream gives the same ids).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int n_streams;
+  int max_tracks;          /* live tracks per stream (capacity) */
+  int max_dets;            /* filtered detections per frame per stream (capacity) */
+  int feature_dim;         /* 512 */
+  double max_cosine_distance; /* src/config.py:23 (a Python float: kept as double so that
+                                 max_distance + 1e-5 rounds as in linear_assignment.py:58) */
+  double max_iou_distance;    /* src/config.py:26 */
+  int max_age;               /* src/config.py:27 */
+  int n_init;                /* src/config.py:28 */
+  int nn_budget;             /* src/config.py:29 */
+  int device;
+} aicam_tracker_config;
+int aicam_tracker_create(const aicam_tracker_config* cfg, aicam_tracker** out);
+void aicam_tracker_destroy(aicam_tracker* t);
+int aicam_tracker_reset(aicam_tracker* t, void* stream);
+
+/* One frame for every stream: predict, cascade + IoU matching, update, initiate, prune,
+ * format.  Inputs describe, per stream b, the detections of the frame (as returned by
+ * detect()/aicam_decode_nms) and which of them reach the tracker:
+ *   boxes fp32 [n_streams][stride_k][4], scores fp32 [..][stride_k], labels i32 [..][stride_k]
+ *   det_index/det_count/crop_slot as written by aicam_reid_crops
+ *   feats fp32 [rows][feature_dim] indexed by crop_slot
+ * Outputs (device):
+ *   out_tracks i32 [n_streams][max_tracks][6] = x1,y1,x2,y2,track_id,class_id (rounded half-even)
+ *   out_conf   fp32 [n_streams][max_tracks]     out_count i32 [n_streams]
+ * in the reference's order (track list order, confirmed and updated this frame only). */
+int aicam_tracker_step(aicam_tracker* t, const float* boxes, const float* scores,
+                       const int32_t* labels, int stride_k, const int32_t* det_index,
+                       const int32_t* det_count, const int32_t* crop_slot, const float* feats,
+                       int32_t* out_tracks, float* out_conf, int32_t* out_count, void* stream);
+
+/* Snapshot of the live tracks of one stream in track-list order (host out; synchronises):
+ *   ints  [n][7]  = track_id, state(1 tentative, 2 confirmed), hits, age, time_since_update,
+ *                   class_id, gallery size
+ *   floats[n][25] = mean[8], covariance blocks a[4] b[4] c[4] d[4], confidence
+ * returns n (>= 0) or a negative error. */
+int aicam_tracker_snapshot(aicam_tracker* t, int stream_index, int32_t* ints, float* floats,
+                           int capacity);
+/* Sticky per-stream overflow flags since the last reset (host out i32[n_streams]):
+ * bit 0 = track capacity exceeded, bit 1 = detection capacity exceeded. */
+int aicam_tracker_overflow(aicam_tracker* t, int32_t* flags_host);
+
+/* Stand-alone pieces of the association, exposed for bit-exact parity tests. */
+/* scipy.optimize.linear_sum_assignment (linear_assignment.py:62) on `count` fp32 cost
+ * matrices [count][nr][nc]; col_for_row i32 [count][nr] (-1 = unassigned). */
+int aicam_lsap(const float* cost, int count, int nr, int nc, int32_t* col_for_row, void* stream);
+/* KalmanFilter.gating_distance (kalman_filter.py:206-249): state fp32 [n][24] (mean8+cov16),
+ * meas fp32 [n][m][4] -> d2 fp32 [n][m]. */
+int aicam_kf_gating(const float* state, const float* meas, int n, int m, float* d2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AICAM_H_ */

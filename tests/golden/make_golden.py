@@ -190,19 +190,11 @@ def make_kalman(kfm):
         len(out["init"]), len(out["pred_in"]), len(out["upd_in"]), len(out["gate_in"])))
 
 
-def synth_image(rng, h, w):
-    """Smooth-ish random image so that bilinear interpolation is exercised on gradients and noise."""
-    base = rng.integers(0, 256, (h // 8 + 2, w // 8 + 2, 3)).astype(np.float32)
-    import cv2
-    img = cv2.resize(base, (w, h), interpolation=cv2.INTER_CUBIC)
-    img += rng.normal(0, 12, img.shape)
-    return np.clip(img, 0, 255).astype(np.uint8)
-
-
 def make_imageops(ip):
-    rng = np.random.default_rng(77)
+    from scenarios import IMAGEOPS_SEED, LETTERBOX_SIZES, REID_CROP_SIZES, synth_image
+    rng = np.random.default_rng(IMAGEOPS_SEED)
     rec = {}
-    sizes = [(1080, 1920), (540, 960), (720, 1280), (480, 640), (300, 500), (1000, 700), (641, 1283)]
+    sizes = LETTERBOX_SIZES
     for k, (h, w) in enumerate(sizes):
         img = synth_image(rng, h, w)
         t, ratios, pad = ip.preprocess_yolo_input(img, (640, 640))
@@ -216,7 +208,7 @@ def make_imageops(ip):
         assert np.array_equal((u8.astype(np.float32) / 255.0), t[0])
         rec["yolo%d_rows" % k] = u8[:, ::37, ::41].copy()
     # ReID crops: (crop h, crop w) incl. upscaling, heavy downscaling, 1-pixel extents
-    crops = [(300, 120), (128, 64), (64, 32), (17, 9), (500, 333), (1, 1), (2, 200), (200, 3), (90, 41)]
+    crops = REID_CROP_SIZES
     for k, (h, w) in enumerate(crops):
         img = synth_image(rng, max(h, 16), max(w, 16))[:h, :w]
         t = ip.preprocess_reid_input(np.ascontiguousarray(img), (128, 64))

@@ -96,3 +96,21 @@ GOLDEN_SCENARIOS = {
 GOLDEN_TRACKER_KW = {
     "fifo": dict(nn_budget=4, n_init=2, max_age=4),
 }
+
+
+def synth_image(rng, h, w):
+    """Seeded HxWx3 uint8 test image: blocky low-frequency colour + a ramp + noise, so that
+    bilinear interpolation sees edges, gradients and texture.  numpy only."""
+    base = rng.integers(0, 256, (h // 8 + 2, w // 8 + 2, 3)).astype(np.float32)
+    img = np.kron(base, np.ones((8, 8, 1), np.float32))[:h, :w]
+    ramp = (np.arange(w, dtype=np.float32)[None, :, None] * 0.11 +
+            np.arange(h, dtype=np.float32)[:, None, None] * 0.07)
+    img = 0.6 * img + 0.4 * (ramp % 256.0) + rng.normal(0, 12, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+LETTERBOX_SIZES = [(1080, 1920), (540, 960), (720, 1280), (480, 640), (300, 500), (1000, 700),
+                   (641, 1283), (640, 640), (100, 37)]
+REID_CROP_SIZES = [(300, 120), (128, 64), (64, 32), (17, 9), (500, 333), (1, 1), (2, 200), (200, 3),
+                   (90, 41), (256, 128)]
+IMAGEOPS_SEED = 77

@@ -1,0 +1,62 @@
+"""tcgen05 implicit-GEMM convolution vs a PyTorch fp32 reference of the same op (-m gpu).
+
+Operands are bf16 on the device; the reference convolves the same bf16-rounded values in fp32.
+Tolerance: bf16 output rounding (2^-9 relative) plus fp32 accumulation-order noise."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, B, H, W, cin, cout, k, s, act, res_mode, out_f32
+    ("1x1_16_32", 2, 20, 20, 16, 32, 1, 1, 1, 0, False),
+    ("3x3_16_16_res1", 1, 24, 24, 16, 16, 3, 1, 1, 1, False),
+    ("3x3s2_32_64", 2, 32, 32, 32, 64, 3, 2, 1, 0, False),
+    ("stem_3_16", 2, 64, 64, 3, 16, 3, 2, 1, 0, False),
+    ("stem_reid_3_64_s1", 3, 32, 16, 3, 64, 3, 1, 2, 0, False),
+    ("cout80", 1, 20, 20, 64, 80, 3, 1, 1, 0, False),
+    ("cout256_res2_relu", 5, 8, 4, 128, 256, 3, 1, 2, 2, False),
+    ("cin48_1x1", 1, 40, 40, 48, 32, 1, 1, 1, 0, False),
+    ("tail_7x9", 1, 7, 9, 32, 32, 3, 1, 1, 0, False),
+    ("f32_out_1x1", 1, 20, 20, 64, 64, 1, 1, 0, 0, True),
+    ("bigk_512", 4, 8, 4, 512, 512, 3, 1, 2, 0, False),
+    ("1x1s2_down", 2, 16, 8, 64, 128, 1, 2, 0, 0, False),
+    ("yolo_160_c32", 2, 160, 160, 32, 32, 3, 1, 1, 0, False),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_matches_torch(case):
+    import gpu_util as G
+    name, B, H, W, cin, cout, k, s, act, res_mode, out_f32 = case
+    rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
+    cpad = 4 if cin <= 4 else (cin + 7) // 8 * 8
+    x = G.bf16_round_np(rng.normal(0, 1, (B, H, W, cin)))
+    xp = np.zeros((B, H, W, cpad), np.float32)
+    xp[..., :cin] = x
+    w = G.bf16_round_np(rng.normal(0, 1.0 / np.sqrt(cin * k * k), (cout, cin, k, k)))
+    b = rng.normal(0, 0.5, cout).astype(np.float32)
+    ho, wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+    res = G.bf16_round_np(rng.normal(0, 1, (B, ho, wo, cout))) if res_mode else None
+    xd = torch.from_numpy(xp).to(G.DEV).to(torch.bfloat16)
+    rd = torch.from_numpy(res).to(G.DEV).to(torch.bfloat16) if res_mode else None
+    got = G.conv2d(xd, w, b, k, s, act, rd, res_mode, out_f32).float().cpu().numpy()
+
+    y = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(w), torch.from_numpy(b), stride=s,
+                 padding=k // 2)
+    r = torch.from_numpy(res).permute(0, 3, 1, 2) if res_mode else None
+    if res_mode == 2:
+        y = y + r
+    y = F.silu(y) if act == 1 else (F.relu(y) if act == 2 else y)
+    if res_mode == 1:
+        y = y + r
+    want = y.permute(0, 2, 3, 1).numpy()
+    assert got.shape == want.shape
+    err = np.abs(got - want)
+    tol = 2e-2 + 1e-2 * np.abs(want) if not out_f32 else 2e-3 + 1e-3 * np.abs(want)
+    bad = err > tol
+    assert not bad.any(), "%s: %d/%d elements off, max abs err %.4g at %s (got %.5g want %.5g)" % (
+        name, bad.sum(), bad.size, err.max(), np.unravel_index(err.argmax(), err.shape),
+        got.flat[err.argmax()], want.flat[err.argmax()])

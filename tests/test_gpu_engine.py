@@ -1,0 +1,111 @@
+"""YOLOv8 / ReID engines (bf16 tcgen05 convolutions) vs the PyTorch-CPU fp32 oracle nets (-m gpu).
+
+Tolerances are the ones BASELINE.json's north_star states: boxes within 1e-2 relative after
+NMS, embeddings cosine >= 0.999."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from scenarios import synth_image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def blobs(tmp_path_factory):
+    from ai_camera_b200 import weights as W
+    d = tmp_path_factory.mktemp("blobs")
+    paths = {}
+    for name, gen in (("yolov8n", lambda: W.synth_yolov8_weights("n", seed=0)),
+                      ("reid", lambda: W.synth_reid_weights(seed=1))):
+        kind, params, tensors = gen()
+        paths[name] = str(d / (name + ".aicw"))
+        W.write_blob(paths[name], kind, params, tensors)
+    return paths
+
+
+def _engine(path, max_batch):
+    import gpu_util as G
+    h = C.c_void_p()
+    G.check(G.lib().aicam_engine_create(path.encode(), 0, max_batch, C.byref(h)))
+    return h
+
+
+def test_yolov8n_head_matches_oracle(blobs):
+    import gpu_util as G
+    from oracle import image_ops, nets
+    rng = np.random.default_rng(0)
+    frames = np.stack([synth_image(rng, 540, 960), rng.integers(0, 256, (540, 960, 3), dtype=np.uint8)])
+    x = G.preprocess(torch.from_numpy(frames).to(G.DEV), 1)
+    e = _engine(blobs["yolov8n"], 2)
+    try:
+        assert abs(G.lib().aicam_engine_flops_per_item(e) / 1e9 - 8.74) < 0.1
+        head = torch.empty((2, 8400, 144), dtype=torch.float32, device=G.DEV)
+        G.check(G.lib().aicam_yolo_forward(e, G.ptr(x), 2, G.ptr(head), None))
+        G.sync()
+    finally:
+        G.lib().aicam_engine_destroy(e)
+    net = nets.load_net(blobs["yolov8n"])
+    xin = np.concatenate([image_ops.preprocess_yolo_input(f)[0] for f in frames])
+    want = net.head_flat(torch.from_numpy(xin)).numpy()
+    got = head.cpu().numpy()
+    err = np.abs(got - want)
+    scale = np.abs(want).max()
+    print("head: max abs err %.4f (logit range %.2f), mean abs err %.5f" % (err.max(), scale, err.mean()))
+    assert err.mean() < 0.02 and err.max() < 0.35
+    # boxes after NMS within 1e-2 relative (of the box size) for detections both sides keep
+    from oracle import detect_post
+    for b in range(2):
+        gb, gs, gl = detect_post.decode(got[b])
+        wb, ws, wl = detect_post.decode(want[b])
+        top = np.argsort(-ws)[:200]
+        size = np.maximum(wb[top, 2] - wb[top, 0], wb[top, 3] - wb[top, 1])[:, None]
+        assert (np.abs(gb[top] - wb[top]) / size).max() < 1e-2
+        assert np.abs(gs[top] - ws[top]).max() < 2e-2
+
+
+def test_reid_embeddings_match_oracle(blobs):
+    import gpu_util as G
+    from oracle import image_ops, nets
+    rng = np.random.default_rng(1)
+    frame = synth_image(rng, 540, 960)
+    rects = []
+    for _ in range(21):
+        x, y = int(rng.integers(0, 800)), int(rng.integers(0, 300))
+        rects.append((x, y, x + int(rng.integers(20, 150)), y + int(rng.integers(40, 230))))
+    xin = image_ops.reid_batch(frame, rects)
+    xd = torch.from_numpy(xin).to(G.DEV)
+    nhwc = torch.empty((21, 128, 64, 4), dtype=torch.bfloat16, device=G.DEV)
+    G.check(G.lib().aicam_nchw_to_nhwc4(G.ptr(xd), 21, 128, 64, G.ptr(nhwc), None))
+    e = _engine(blobs["reid"], 8)  # 21 crops through a workspace of 8: sliced
+    try:
+        assert abs(G.lib().aicam_engine_flops_per_item(e) / 1e9 - 2.242) < 0.05
+        feats = torch.empty((21, 512), dtype=torch.float32, device=G.DEV)
+        G.check(G.lib().aicam_reid_forward(e, G.ptr(nhwc), 21, None, G.ptr(feats), None))
+        # device-side count: capacity 8, only 5 present
+        feats2 = torch.zeros((8, 512), dtype=torch.float32, device=G.DEV)
+        n_dev = torch.tensor([5], dtype=torch.int32, device=G.DEV)
+        G.check(G.lib().aicam_reid_forward(e, G.ptr(nhwc), 8, G.ptr(n_dev), G.ptr(feats2), None))
+        G.sync()
+    finally:
+        G.lib().aicam_engine_destroy(e)
+    want = nets.load_net(blobs["reid"]).forward(torch.from_numpy(xin)).numpy()
+    got = feats.cpu().numpy()
+    cos = (got * want).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(want, axis=1))
+    print("reid cosine min %.6f" % cos.min())
+    assert cos.min() >= 0.999
+    assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+    f2 = feats2.cpu().numpy()
+    assert np.array_equal(f2[:5], got[:5]) and not f2[5:].any()
+
+
+def test_engine_errors(blobs, tmp_path):
+    import gpu_util as G
+    h = C.c_void_p()
+    assert G.lib().aicam_engine_create(str(tmp_path / "missing.aicw").encode(), 0, 1, C.byref(h)) == -3
+    bad = tmp_path / "bad.aicw"
+    bad.write_bytes(b"not a blob at all, definitely" * 4)
+    assert G.lib().aicam_engine_create(str(bad).encode(), 0, 1, C.byref(h)) == -3
+    assert b"AICW0001" in G.lib().aicam_last_error()

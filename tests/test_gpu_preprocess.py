@@ -1,0 +1,41 @@
+"""K1 (fused letterbox / BGR->RGB / normalise / layout) vs the oracle, bit for bit (-m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+from scenarios import IMAGEOPS_SEED, LETTERBOX_SIZES, synth_image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("hw", LETTERBOX_SIZES + [(2160, 3840), (360, 640), (1280, 1280)], ids=str)
+def test_preprocess_bit_exact(hw):
+    import gpu_util as G
+    from oracle import image_ops
+    rng = np.random.default_rng(IMAGEOPS_SEED + hw[0] * 7 + hw[1])
+    frames = np.stack([synth_image(rng, *hw), rng.integers(0, 256, (*hw, 3), dtype=np.uint8)])
+    fd = torch.from_numpy(frames).to(G.DEV)
+    got0 = G.preprocess(fd, 0).cpu().numpy()
+    got1 = G.preprocess(fd, 1).float().cpu().numpy()
+    for i in range(2):
+        want, ratios, pad = image_ops.preprocess_yolo_input(frames[i])
+        assert np.array_equal(got0[i].view(np.uint32), want[0].view(np.uint32)), \
+            "fp32 NCHW differs: %d px" % (got0[i] != want[0]).sum()
+        wb = torch.from_numpy(want[0]).to(torch.bfloat16).float().numpy().transpose(1, 2, 0)
+        assert np.array_equal(got1[i][..., :3], wb)
+        assert not got1[i][..., 3].any()
+    m = __import__("ai_camera_b200._lib", fromlist=["Letterbox"]).Letterbox()
+    import ctypes as C
+    G.check(G.lib().aicam_letterbox_params(hw[0], hw[1], C.byref(m)))
+    assert (m.ratio, m.pad_w, m.pad_h) == (ratios[0], pad[0], pad[1])
+
+
+def test_preprocess_full_batch_checksum():
+    """BASELINE config 2 size: 64 x 1080p frames; the exact 3:1 case is a pure gather."""
+    import gpu_util as G
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    frames = torch.randint(0, 256, (64, 1080, 1920, 3), dtype=torch.uint8, generator=g)
+    out = G.preprocess(frames.to(G.DEV), 0).cpu()
+    want = torch.full((64, 3, 640, 640), 114.0 / 255.0)
+    want[:, :, 140:500, :] = (frames[:, 1::3, 1::3, :].flip(-1).permute(0, 3, 1, 2).float() / 255.0)
+    assert torch.equal(out, want)
