@@ -48,6 +48,8 @@ SIGNATURES = {
     "aicam_version": (_I, []),
     "aicam_last_error": (C.c_char_p, []),
     "aicam_launch_count": (C.c_uint64, []),
+    "aicam_profile_enable": (_I, [_I]),
+    "aicam_profile_conv": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "aicam_engine_create": (_I, [C.c_char_p, _I, _I, C.POINTER(_P)]),
     "aicam_engine_destroy": (None, [_P]),
     "aicam_engine_kind": (_I, [_P]),

@@ -1,5 +1,7 @@
 // Error state, version and launch accounting shared by every entry point of the C ABI.
 #include <atomic>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -15,6 +17,24 @@ int fail(int code, const std::string& msg) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// ---- per-launch event timing of the convolution kernel ------------------------------------
+static bool g_profile = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
+static size_t g_events_used = 0;
+
+bool profile_begin(cudaStream_t st, size_t* slot) {
+  if (!g_profile) return false;
+  if (g_events_used == g_events.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return false;
+    g_events.emplace_back(a, b);
+  }
+  *slot = g_events_used++;
+  cudaEventRecord(g_events[*slot].first, st);
+  return true;
+}
+void profile_end(cudaStream_t st, size_t slot) { cudaEventRecord(g_events[slot].second, st); }
+
 }  // namespace aicam
 
 extern "C" {
@@ -22,5 +42,26 @@ extern "C" {
 int aicam_version(void) { return 100; }
 const char* aicam_last_error(void) { return aicam::g_error.c_str(); }
 uint64_t aicam_launch_count(void) { return aicam::g_launches.load(); }
+
+int aicam_profile_enable(int on) {
+  aicam::g_profile = on != 0;
+  return AICAM_OK;
+}
+
+int aicam_profile_conv(double* total_ms, uint64_t* launches) {
+  if (!total_ms || !launches) return aicam::fail(AICAM_ERR_INVALID_ARG, "profile_conv: null argument");
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return aicam::fail(AICAM_ERR_CUDA, std::string("profile_conv: ") + cudaGetErrorString(e));
+  double sum = 0.0;
+  for (size_t i = 0; i < aicam::g_events_used; ++i) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, aicam::g_events[i].first, aicam::g_events[i].second);
+    sum += ms;
+  }
+  *total_ms = sum;
+  *launches = aicam::g_events_used;
+  aicam::g_events_used = 0;
+  return AICAM_OK;
+}
 
 }  // extern "C"

@@ -390,6 +390,8 @@ int pick_n_tile(int cout_pad) {
 }  // namespace
 
 extern void count_launch();
+bool profile_begin(cudaStream_t st, size_t* slot);
+void profile_end(cudaStream_t st, size_t slot);
 
 int pack_conv_weights(const float* w, const float* bias, int cout, int cin, int ksize, int stride,
                       PackedConv* out) {
@@ -466,7 +468,10 @@ int launch_conv(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream) 
     attr_set = true;
   }
   dim3 grid(cdiv(a.m_total, TILE_M), a.cout_pad / a.n_tile);
+  size_t slot = 0;
+  const bool prof = profile_begin(stream, &slot);
   conv_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(a);
+  if (prof) profile_end(stream, slot);
   count_launch();
   return last_launch("conv_tc_kernel");
 }

@@ -1,0 +1,168 @@
+"""Batched, device-resident detect -> track path over many video streams.
+
+The reference processes one frame of one stream per call, on the CPU except for the two
+TensorRT engines (``/root/reference/src/aicamera_tracker.py:169-240``).  Here a batch of
+frames (one per stream) goes through K1-K12 without leaving the GPU and without a host
+synchronisation: detections, crop counts and track tables stay in fixed-capacity device
+buffers.  ``YOLODetector`` / ``DeepSORT`` (the reference-shaped facades) are thin single-stream
+wrappers around ``BatchDetector`` / ``BatchTracker``.
+"""
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib, config
+from .trt_engine import TRTEngine
+
+
+class BatchDetector:
+    """K1-K4 + detect() post-processing for ``batch`` frames of one size."""
+
+    def __init__(self, engine_path, batch: int, device=None, conf_threshold=config.YOLO_CONF_THRESHOLD,
+                 nms_threshold=config.YOLO_NMS_THRESHOLD, topk=config.YOLO_TOPK,
+                 max_candidates=config.YOLO_MAX_CANDIDATES):
+        self.engine = TRTEngine(engine_path, device, max_batch=batch, topk=topk,
+                                score_threshold=min(conf_threshold, config.YOLO_CONF_THRESHOLD),
+                                nms_threshold=nms_threshold, max_candidates=max_candidates)
+        if self.engine.kind != _lib.KIND_YOLOV8:
+            raise RuntimeError("BatchDetector needs a yolov8 weight blob")
+        self.lib = _lib.load()
+        self.device = self.engine.device
+        self.batch, self.topk = batch, topk
+        self.conf_threshold = conf_threshold
+        e, dev = self.engine, self.device
+        self.num_dets = torch.zeros(batch, dtype=torch.int32, device=dev)
+        self.boxes_lb = torch.zeros((batch, topk, 4), dtype=torch.float32, device=dev)
+        self.boxes = torch.zeros((batch, topk, 4), dtype=torch.float32, device=dev)
+        self.scores = torch.zeros((batch, topk), dtype=torch.float32, device=dev)
+        self.labels = torch.zeros((batch, topk), dtype=torch.int32, device=dev)
+        self._nms = _lib.NmsParams(e.score_threshold, e.nms_threshold, topk, e.max_candidates, 0, 0)
+
+    def detect(self, frames: torch.Tensor):
+        """frames: uint8 cuda [n<=batch, H, W, 3] BGR.  Returns device tensors (num_dets [n],
+        boxes [n,topk,4] in frame pixels, scores [n,topk], labels [n,topk]); views of internal
+        buffers, valid until the next call; asynchronous on the current stream."""
+        n, h, w, _ = frames.shape
+        if n > self.batch:
+            raise _lib.AicamError(-4, "detect: %d frames exceed the detector's batch %d" % (n, self.batch))
+        e, st = self.engine, _lib.stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aicam_preprocess(_lib.ptr(frames), n, h, w, 1, _lib.ptr(e._nhwc), st))
+            _lib.check(self.lib.aicam_yolo_forward(e.handle, _lib.ptr(e._nhwc), n, _lib.ptr(e._head), st))
+            self._nms.frame_h, self._nms.frame_w = h, w
+            _lib.check(self.lib.aicam_decode_nms(
+                _lib.ptr(e._head), n, e.anchors, e.nc, C.byref(self._nms), _lib.ptr(self.num_dets),
+                _lib.ptr(self.boxes_lb), _lib.ptr(self.boxes), _lib.ptr(self.scores), _lib.ptr(self.labels),
+                _lib.ptr(e._ws), e._ws.numel(), st))
+        return self.num_dets[:n], self.boxes[:n], self.scores[:n], self.labels[:n]
+
+    def launches_per_step(self):
+        return 1 + self.engine.launches_per_forward() + 2
+
+
+class BatchTracker:
+    """K5-K12 for ``n_streams`` independent streams (one DeepSORT state each)."""
+
+    def __init__(self, reid_engine_path, n_streams: int, device=None, max_dets=config.YOLO_TOPK,
+                 max_tracks: int = 256, max_crops: Optional[int] = None,
+                 max_cosine_distance=config.DEEPSORT_MAX_DIST, nn_budget=config.DEEPSORT_NN_BUDGET,
+                 max_iou_distance=config.DEEPSORT_MAX_IOU_DISTANCE, max_age=config.DEEPSORT_MAX_AGE,
+                 n_init=config.DEEPSORT_N_INIT, min_detection_confidence=config.DEEPSORT_MIN_CONFIDENCE):
+        self.max_crops = int(max_crops if max_crops is not None else min(n_streams * max_dets, 4096))
+        self.reid = TRTEngine(reid_engine_path, device, max_batch=self.max_crops)
+        if self.reid.kind != _lib.KIND_REID:
+            raise RuntimeError("BatchTracker needs a reid weight blob")
+        if nn_budget is None:
+            raise RuntimeError("nn_budget=None (unbounded galleries) is not supported on the device")
+        self.lib = _lib.load()
+        self.device = dev = self.reid.device
+        self.S, self.K, self.T = n_streams, max_dets, max_tracks
+        self.min_conf = float(min_detection_confidence)
+        self.F = self.reid.feature_dim
+        cfg = _lib.TrackerConfig(n_streams, max_tracks, max_dets, self.F, float(max_cosine_distance),
+                                 float(max_iou_distance), int(max_age), int(n_init), int(nn_budget), dev.index)
+        self._h = C.c_void_p()
+        _lib.check(self.lib.aicam_tracker_create(C.byref(cfg), C.byref(self._h)))
+        S, K = n_streams, max_dets
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.det_index = torch.zeros((S, K), **i32)
+        self.det_count = torch.zeros(S, **i32)
+        self.crop_slot = torch.zeros((S, K), **i32)
+        self.crop_rect = torch.zeros((self.max_crops, 5), **i32)
+        self.crop_count = torch.zeros(1, **i32)
+        self.crops = torch.zeros((self.max_crops, config.REID_INPUT_SHAPE[0], config.REID_INPUT_SHAPE[1], 4),
+                                 dtype=torch.bfloat16, device=dev)
+        self.feats = torch.zeros((self.max_crops, self.F), dtype=torch.float32, device=dev)
+        self.out_tracks = torch.zeros((S, max_tracks, 6), **i32)
+        self.out_conf = torch.zeros((S, max_tracks), dtype=torch.float32, device=dev)
+        self.out_count = torch.zeros(S, **i32)
+        self._mask = config.tracked_class_mask()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self.lib.aicam_tracker_destroy(h)
+            self._h = None
+
+    def reset(self):
+        _lib.check(self.lib.aicam_tracker_reset(self._h, _lib.stream_ptr(self.device)))
+
+    def update(self, frames, num_dets, boxes, scores, labels):
+        """One frame per stream.  frames uint8 cuda [S,H,W,3]; detections as BatchDetector returns
+        them ([S], [S,K,4], [S,K], [S,K]).  Returns device (out_tracks [S,T,6] int32 =
+        x1,y1,x2,y2,id,class, out_conf [S,T], out_count [S]); asynchronous."""
+        S, h, w, _ = frames.shape
+        if S != self.S or boxes.shape[1] != self.K:
+            raise _lib.AicamError(-4, "update: expected %d streams x %d detections" % (self.S, self.K))
+        st = _lib.stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aicam_reid_crops(
+                _lib.ptr(frames), S, h, w, _lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(labels), _lib.ptr(num_dets),
+                self.K, self.min_conf, self._mask[0], self._mask[1], 1, self.max_crops, _lib.ptr(self.det_index),
+                _lib.ptr(self.det_count), _lib.ptr(self.crop_slot), _lib.ptr(self.crop_rect), _lib.ptr(self.crops),
+                _lib.ptr(self.crop_count), st))
+            _lib.check(self.lib.aicam_reid_forward(self.reid.handle, _lib.ptr(self.crops), self.max_crops,
+                                                   _lib.ptr(self.crop_count), _lib.ptr(self.feats), st))
+            _lib.check(self.lib.aicam_tracker_step(
+                self._h, _lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(labels), self.K, _lib.ptr(self.det_index),
+                _lib.ptr(self.det_count), _lib.ptr(self.crop_slot), _lib.ptr(self.feats), _lib.ptr(self.out_tracks),
+                _lib.ptr(self.out_conf), _lib.ptr(self.out_count), st))
+        return self.out_tracks, self.out_conf, self.out_count
+
+    def overflow(self):
+        import numpy as np
+        f = np.zeros(self.S, np.int32)
+        _lib.check(self.lib.aicam_tracker_overflow(self._h, _lib.ptr(f)))
+        return f
+
+    def snapshot(self, stream_index=0):
+        import numpy as np
+        ints = np.zeros((self.T, 7), np.int32)
+        floats = np.zeros((self.T, 25), np.float32)
+        n = self.lib.aicam_tracker_snapshot(self._h, stream_index, _lib.ptr(ints), _lib.ptr(floats), self.T)
+        if n < 0:
+            _lib.check(n)
+        return ints[:n], floats[:n]
+
+    def launches_per_step(self):
+        return 2 + self.reid.launches_per_forward() + 3
+
+
+class TrackingPipeline:
+    """detect + track for ``n_streams`` streams of one frame size; one call per time step."""
+
+    def __init__(self, yolo_engine_path, reid_engine_path, n_streams: int, device=None, max_tracks: int = 256,
+                 max_crops: Optional[int] = None, **tracker_kw):
+        self.detector = BatchDetector(yolo_engine_path, n_streams, device)
+        self.tracker = BatchTracker(reid_engine_path, n_streams, self.detector.device, max_dets=self.detector.topk,
+                                    max_tracks=max_tracks, max_crops=max_crops, **tracker_kw)
+        self.device = self.detector.device
+        self.n_streams = n_streams
+
+    def step(self, frames: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        num, boxes, scores, labels = self.detector.detect(frames)
+        return self.tracker.update(frames, num, boxes, scores, labels)
+
+    def launches_per_step(self):
+        return self.detector.launches_per_step() + self.tracker.launches_per_step()

@@ -1,0 +1,104 @@
+"""Synthetic workload for benchmarks, smoke tests and end-to-end parity tests.
+
+There is no network and the reference ships neither weights nor labelled video, so:
+  * weights are seeded synthetic weights of the named architectures (weights.py);
+  * video is a seeded texture per stream translated by a constant velocity (ping-pong over a
+    ring of frames), so that detections move coherently and tracks persist;
+  * the synthetic detector's operating point (a constant added to every class logit) is
+    chosen so that a target number of tracked-class detections per frame survives NMS -
+    the clip the reference ships has 30-50 people per frame, BASELINE config 2 is quoted at
+    D = 16.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import config, weights
+
+
+def make_blobs(directory, scale="n", yolo_seed=0, reid_seed=1):
+    """Write the two synthetic weight blobs (if absent) and return their paths."""
+    os.makedirs(directory, exist_ok=True)
+    yolo = os.path.join(directory, "yolov8%s_seed%d.aicw" % (scale, yolo_seed))
+    reid = os.path.join(directory, "deepsort_reid_seed%d.aicw" % reid_seed)
+    if not os.path.exists(yolo):
+        weights.write_blob(yolo + ".tmp", *weights.synth_yolov8_weights(scale, seed=yolo_seed))
+        os.replace(yolo + ".tmp", yolo)
+    if not os.path.exists(reid):
+        weights.write_blob(reid + ".tmp", *weights.synth_reid_weights(seed=reid_seed))
+        os.replace(reid + ".tmp", reid)
+    return yolo, reid
+
+
+class SynthVideo:
+    """ring[t][s] = texture of stream s shifted by t * velocity_s; uint8 [T,S,H,W,3] on `device`."""
+
+    def __init__(self, n_streams, frame_hw=(1080, 1920), n_frames=16, device="cuda:0", seed=1234, block=24,
+                 first_stream=0):
+        H, W = frame_hw
+        self.n_streams, self.frame_hw, self.n_frames = n_streams, frame_hw, n_frames
+        self.ring = torch.empty((n_frames, n_streams, H, W, 3), dtype=torch.uint8, device=device)
+        max_shift = 6 * n_frames
+        for s in range(n_streams):
+            g = torch.Generator(device="cpu").manual_seed(seed + first_stream + s)
+            hb, wb = (H + 2 * max_shift) // block + 2, (W + 2 * max_shift) // block + 2
+            coarse = torch.randint(0, 256, (hb, wb, 3), generator=g, dtype=torch.uint8)
+            fine = torch.randint(0, 48, (H + 2 * max_shift, W + 2 * max_shift, 3), generator=g, dtype=torch.uint8)
+            vx, vy = (int(v) for v in torch.randint(-2, 3, (2,), generator=g))
+            tex = coarse.to(device).repeat_interleave(block, 0).repeat_interleave(block, 1)
+            tex = tex[:H + 2 * max_shift, :W + 2 * max_shift]
+            tex = (tex.to(torch.int16) * 3 // 4 + fine.to(device).to(torch.int16)).clamp_(0, 255).to(torch.uint8)
+            for t in range(n_frames):
+                oy, ox = max_shift + 3 * vy * t, max_shift + 3 * vx * t  # 3 source px = 1 network px
+                self.ring[t, s] = tex[oy:oy + H, ox:ox + W]
+
+    def index(self, step):
+        """Ping-pong index into the ring: 0,1,..,T-1,T-2,..,1,0,1,.."""
+        T = self.n_frames
+        if T == 1:
+            return 0
+        k = step % (2 * T - 2)
+        return k if k < T else 2 * T - 2 - k
+
+    def frames(self, step):
+        return self.ring[self.index(step)]
+
+
+CLS_LAYERS = ["model.22.cv3.%d.2" % l for l in range(3)]
+
+
+def calibrate_detector(detector, frames, target_tracked=16.0, iters=12):
+    """Shift every class logit by one constant so that, on `frames`, the mean number of
+    tracked-class detections per frame is close to `target_tracked`.  Returns the bias
+    vectors set ({layer name: float32 array}) so a CPU run can apply the same ones."""
+    eng = detector.engine
+    base = {n: eng.get_bias(n).numpy().copy() for n in CLS_LAYERS}
+    lo_mask, hi_mask = config.tracked_class_mask()
+    tracked = torch.tensor([c for c in range(64) if (lo_mask >> c) & 1] + [64 + c for c in range(64) if (hi_mask >> c) & 1],
+                           device=detector.device, dtype=torch.int32)
+
+    def count(delta):
+        for n in CLS_LAYERS:
+            eng.set_bias(n, base[n] + np.float32(delta))
+        num, boxes, scores, labels = detector.detect(frames)
+        k = torch.arange(labels.shape[1], device=labels.device)[None, :] < num[:, None]
+        ok = k & torch.isin(labels, tracked) & (scores >= config.DEEPSORT_MIN_CONFIDENCE)
+        return ok.sum().item() / frames.shape[0]
+
+    lo, hi = -6.0, 3.0
+    best = (None, 1e9)
+    for _ in range(iters):
+        mid = 0.5 * (lo + hi)
+        c = count(mid)
+        if abs(c - target_tracked) < best[1]:
+            best = (mid, abs(c - target_tracked))
+        if c > target_tracked:
+            hi = mid
+        else:
+            lo = mid
+    delta = best[0]
+    final = {n: (base[n] + np.float32(delta)).astype(np.float32) for n in CLS_LAYERS}
+    for n in CLS_LAYERS:
+        eng.set_bias(n, final[n])
+    return delta, final

@@ -122,19 +122,24 @@ def _bf16_round(x):
     return r.astype(np.uint32).view(np.float32).reshape(np.shape(x))
 
 
-def _synth_conv(rng, cin, cout, k, gain, with_bn, eps):
+def _synth_conv(rng, cin, cout, k, gain, with_bn, eps, zero_mean=False, bias_std=0.1):
     fan_in = cin * k * k
     w = rng.normal(0.0, gain / np.sqrt(fan_in), (cout, cin, k, k)).astype(np.float32)
+    if zero_mean:
+        # zero-sum filters: the positive mean of post-activation features then adds no constant
+        # per-channel offset, which would otherwise dominate a random network's output and make
+        # all embeddings / score maps look alike
+        w = w - w.mean(axis=(1, 2, 3), keepdims=True)
     if with_bn:
         gamma = rng.uniform(0.8, 1.2, cout).astype(np.float32)
-        beta = rng.normal(0, 0.1, cout).astype(np.float32)
-        mean = rng.normal(0, 0.1, cout).astype(np.float32)
+        beta = rng.normal(0, bias_std, cout).astype(np.float32)
+        mean = rng.normal(0, bias_std, cout).astype(np.float32)
         var = rng.uniform(0.8, 1.2, cout).astype(np.float32)
         s = gamma / np.sqrt(var + np.float32(eps))
         w = w * s[:, None, None, None]
         b = beta - mean * s
     else:
-        b = rng.normal(0, 0.1, cout).astype(np.float32)
+        b = rng.normal(0, bias_std, cout).astype(np.float32)
     # weights are bf16-representable by construction: the device path (bf16 operands) and
     # the fp32 CPU restatement then multiply by identical weight values
     return _bf16_round(w), b.astype(np.float32)
@@ -154,7 +159,7 @@ def synth_yolov8_weights(scale="n", nc=80, seed=0, cls_bias=-6.0, cls_gain=15.0,
     tensors = OrderedDict()
     for name, cin, cout, k, s, act in yolov8_conv_specs(scale, nc):
         if act == "silu":
-            w, b = _synth_conv(rng, cin, cout, k, 1.55, True, 1e-3)
+            w, b = _synth_conv(rng, cin, cout, k, 1.55, True, 1e-3, zero_mean=cin > 3)
         elif ".cv3." in name:
             w, b = _synth_conv(rng, cin, cout, k, cls_gain, False, 0.0)
             b = (b + np.float32(cls_bias)).astype(np.float32)
@@ -175,7 +180,7 @@ def synth_reid_weights(seed=1):
     tensors = OrderedDict()
     for name, cin, cout, k, s, act in reid_conv_specs():
         gain = 1.35 if act == "relu" else 0.7
-        w, b = _synth_conv(rng, cin, cout, k, gain, True, 1e-5)
+        w, b = _synth_conv(rng, cin, cout, k, gain, True, 1e-5, zero_mean=cin > 3, bias_std=0.01)
         tensors[name + ".weight"] = w
         tensors[name + ".bias"] = b
     return KIND_REID, [512, 0, 0, 0, 0, 0, 0, 0], tensors

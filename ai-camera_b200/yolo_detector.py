@@ -1,0 +1,83 @@
+"""``YOLODetector`` with the reference's interface (``/root/reference/src/detector/yolo_detector.py``):
+``YOLODetector(engine_path, input_shape, conf_threshold, nms_threshold, device)`` (:15-21) and
+``detect(frame_bgr) -> (bboxes_xyxy, scores, class_ids, filtered_indices)`` (:68-149).
+
+What changes underneath: the frame is uploaded as uint8 (6.2 MB for 1080p) instead of being
+letterboxed on the CPU and uploaded as fp32 (:86-91); letterbox, network, decode, NMS,
+confidence filter and un-letterboxing all run on the device; one D2H copy returns the
+result.  Return types and the empty-result convention (:126) are the reference's."""
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from . import config
+from .pipeline import BatchDetector
+
+
+class YOLODetector:
+    def __init__(self,
+                 engine_path: str = str(config.YOLO_ENGINE_PATH),
+                 input_shape: Tuple[int, int] = config.YOLO_INPUT_SHAPE,
+                 conf_threshold: float = config.YOLO_CONF_THRESHOLD,
+                 nms_threshold: float = config.YOLO_NMS_THRESHOLD,
+                 device: torch.device = torch.device('cuda:0' if torch.cuda.is_available() else 'cpu')):
+        if tuple(input_shape) != tuple(config.YOLO_INPUT_SHAPE):
+            raise RuntimeError("this build supports the 640x640 network input only")
+        self.engine_path = engine_path
+        self.input_shape = input_shape
+        self.conf_threshold = conf_threshold
+        self.nms_threshold = nms_threshold
+        self.device = torch.device(device)
+        self._det = BatchDetector(engine_path, 1, self.device, conf_threshold, nms_threshold)
+        self.trt_engine = self._det.engine
+        self.device = self._det.device
+        self.input_name = self.trt_engine.get_input_details()[0].name
+        self.output_names = {'num_dets': 'num_dets', 'bboxes': 'bboxes', 'scores': 'scores', 'labels': 'labels'}
+        k = self._det.topk
+        # one pinned staging buffer for the result: [num | boxes 4k | scores k | labels k] as 32-bit words
+        self._host = torch.empty(1 + 6 * k, dtype=torch.int32).pin_memory()
+        self._pack = torch.empty(1 + 6 * k, dtype=torch.int32, device=self.device)
+        self._frame_dev = None
+        self._frame_host = None
+        print(f"YOLODetector initialized with engine: {engine_path}")
+        print(f"  Input name: {self.input_name}, Input shape: {self.input_shape}")
+
+    def _upload(self, frame_bgr: np.ndarray) -> torch.Tensor:
+        shape = tuple(frame_bgr.shape)
+        if self._frame_host is None or tuple(self._frame_host.shape[1:]) != shape:
+            self._frame_host = torch.empty((1,) + shape, dtype=torch.uint8).pin_memory()
+            self._frame_dev = torch.empty((1,) + shape, dtype=torch.uint8, device=self.device)
+        self._frame_host[0].numpy()[...] = frame_bgr
+        self._frame_dev.copy_(self._frame_host, non_blocking=True)
+        return self._frame_dev
+
+    def detect(self, frame_bgr: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+        empty = (np.empty((0, 4)), np.empty(0), np.empty(0), np.empty(0, dtype=int))
+        if frame_bgr.ndim != 3 or frame_bgr.shape[2] != 3 or frame_bgr.dtype != np.uint8:
+            raise ValueError("detect expects an HxWx3 uint8 BGR frame")
+        k = self._det.topk
+        try:
+            num, boxes, scores, labels = self._det.detect(self._upload(frame_bgr))
+            p = self._pack
+            p[0:1].copy_(num)
+            p[1:1 + 4 * k].view(torch.float32).copy_(boxes.reshape(-1))
+            p[1 + 4 * k:1 + 5 * k].view(torch.float32).copy_(scores.reshape(-1))
+            p[1 + 5 * k:].copy_(labels.reshape(-1))
+            self._host.copy_(p, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        except Exception as e:  # yolo_detector.py:117-122: report and return empty
+            print(f"Error processing engine outputs: {e}")
+            return empty
+        h = self._host.numpy()
+        n = int(h[0])
+        if n == 0:
+            return empty
+        bboxes = h[1:1 + 4 * k].view(np.float32).reshape(k, 4)[:n].copy()
+        sc = h[1 + 4 * k:1 + 5 * k].view(np.float32)[:n].copy()
+        cls = h[1 + 5 * k:][:n].astype(np.int32)
+        confident = sc >= self.conf_threshold  # yolo_detector.py:131
+        bboxes, sc, cls = bboxes[confident], sc[confident], cls[confident]
+        if bboxes.shape[0] == 0:
+            return empty
+        return bboxes, sc, cls, np.where(confident)[0]

@@ -46,6 +46,12 @@ int aicam_version(void);
 const char* aicam_last_error(void);
 /* Number of kernels this library has launched in the calling process (all handles). */
 uint64_t aicam_launch_count(void);
+/* Profiling of the convolution kernel (the dominant kernel of the path): while enabled, every
+ * conv launch is bracketed by CUDA events on its own stream.  aicam_profile_conv synchronises,
+ * returns the summed kernel time and the number of launches since the last call, and resets.
+ * Not for use under CUDA-graph capture. */
+int aicam_profile_enable(int on);
+int aicam_profile_conv(double* total_ms, uint64_t* launches);
 
 /* ------------------------------------------------------------------------------------------
  * Engine: replaces TRTEngine (src/trt_utils/trt_engine.py:15-216): __init__/_init_engine

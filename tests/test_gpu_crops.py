@@ -12,7 +12,8 @@ def test_crops_bit_exact_and_filter():
     import gpu_util as G
     from ai_camera_b200.config import tracked_class_mask
     from oracle import image_ops
-    from oracle.tracker import DeepSORT, crop_rect
+    from oracle.tracker import DeepSORT
+    from oracle.tracker import crop_rect as oracle_crop_rect
     rng = np.random.default_rng(42)
     B, H, W, K = 3, 540, 960, 24
     frames = np.stack([synth_image(rng, H, W) for _ in range(B)])
@@ -55,7 +56,7 @@ def test_crops_bit_exact_and_filter():
         keep = ds.filter_indices(scores[b, :num[b]], labels[b, :num[b]])
         assert dc[b] == len(keep) and np.array_equal(di[b, :dc[b]], keep)
         for k, i in enumerate(keep):
-            r = crop_rect(boxes[b, i], H, W)
+            r = oracle_crop_rect(boxes[b, i], H, W)
             if r is None:
                 assert cs[b, k] == -1
                 continue
