@@ -32,6 +32,7 @@ struct ConvLaunch {
   int res_mode;  // 0 none, 1 act(conv)+res, 2 act(conv+res)
   int act;       // 0 none, 1 SiLU, 2 ReLU
   const int* batch_dev = nullptr;  // optional device-side image count (<= batch)
+  long long* trace = nullptr;      // debug: clock64 stamps of CTA 0
 };
 
 // host: pack OIHW fp32 weights (host) into the device layout above

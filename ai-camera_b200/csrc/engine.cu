@@ -10,6 +10,7 @@
 // (C2f, SPPF, the FPN/PAN joins) are never materialised by a copy: producers write straight
 // into channel slices of the wider buffer (conv out_coff/out_cstride), and consumers read a
 // slice (in_coff/in_cstride).
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -473,6 +474,74 @@ int aicam_conv2d(const aicam_conv_desc* d, const void* in, const float* w, const
   free_packed_conv(&pc);
   if (rc) return rc;
   if (se != cudaSuccess) return fail(AICAM_ERR_CUDA, std::string("conv2d: ") + cudaGetErrorString(se));
+  return AICAM_OK;
+}
+
+int aicam_conv2d_bench(const aicam_conv_desc* d, int iters, double* mean_ms, void* stream) {
+  if (!d || !mean_ms || iters <= 0) return fail(AICAM_ERR_INVALID_ARG, "conv2d_bench: bad arguments");
+  std::vector<float> w(static_cast<size_t>(d->cout) * d->cin * d->ksize * d->ksize), b(d->cout, 0.1f);
+  uint32_t seed = 12345u;
+  for (auto& v : w) { seed = seed * 1664525u + 1013904223u; v = (static_cast<int>(seed >> 16) % 2001 - 1000) * 1e-4f; }
+  PackedConv pc;
+  if (int rc = pack_conv_weights(w.data(), b.data(), d->cout, d->cin, d->ksize, d->stride, &pc)) return rc;
+  ConvLaunch L;
+  const int cs = pc.cin_pad;
+  const int ho = (d->h + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
+  const int wo = (d->w + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
+  const size_t in_elems = static_cast<size_t>(d->batch) * d->h * d->w * cs;
+  const size_t out_elems = static_cast<size_t>(d->batch) * ho * wo * d->cout;
+  __nv_bfloat16 *in = nullptr, *res = nullptr;
+  void* out = nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AICAM_CUDA_OK(cudaMalloc(&in, in_elems * 2));
+  AICAM_CUDA_OK(cudaMalloc(&out, out_elems * (d->out_f32 ? 4 : 2)));
+  AICAM_CUDA_OK(cudaMemset(in, 0x3c, in_elems * 2));  // bf16 0x3c3c ~ 0.0115
+  if (d->res_mode) {
+    AICAM_CUDA_OK(cudaMalloc(&res, out_elems * 2));
+    AICAM_CUDA_OK(cudaMemset(res, 0x3c, out_elems * 2));
+  }
+  L.in = in; L.in_img_stride = static_cast<long long>(d->h) * d->w * cs; L.in_cstride = cs; L.in_coff = 0;
+  L.batch = d->batch; L.h = d->h; L.w = d->w; L.ho = ho; L.wo = wo;
+  L.out = out; L.out_img_stride = static_cast<long long>(ho) * wo * d->cout; L.out_cstride = d->cout; L.out_coff = 0;
+  L.out_f32 = d->out_f32;
+  L.res = res; L.res_img_stride = L.out_img_stride; L.res_cstride = d->cout; L.res_coff = 0; L.res_mode = d->res_mode;
+  L.act = d->act;
+  int rc = AICAM_OK;
+  for (int i = 0; i < 3 && !rc; ++i) rc = launch_conv(pc, L, st);
+  if (getenv("AICAM_CONV_TRACE")) {  // per-phase clock64 stamps of CTA 0 (debug aid)
+    long long* tr = nullptr;
+    cudaMalloc(&tr, 512 * 8);
+    cudaMemset(tr, 0, 512 * 8);
+    L.trace = tr;
+    launch_conv(pc, L, st);
+    cudaStreamSynchronize(st);
+    L.trace = nullptr;
+    std::vector<long long> h(512);
+    cudaMemcpy(h.data(), tr, 512 * 8, cudaMemcpyDeviceToHost);
+    cudaFree(tr);
+    const long long t0 = h[0];
+    printf("trace (cycles since first gather): kb: gather_start gather_issued mma_ready mma_committed\n");
+    for (int k = 0; k < 30 && h[k * 4]; ++k)
+      printf("  kb %2d: %7lld %7lld %7lld %7lld\n", k, h[k * 4] - t0, h[k * 4 + 1] - t0, h[k * 4 + 2] - t0, h[k * 4 + 3] - t0);
+    for (int t = 0; t < 4 && h[240 + t * 4]; ++t)
+      printf("  tile %d epilogue: start %7lld tmem_read_done %7lld stores_done %7lld\n", t, h[240 + t * 4] - t0,
+             h[240 + t * 4 + 1] - t0, h[240 + t * 4 + 2] - t0);
+    fflush(stdout);
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters && !rc; ++i) rc = launch_conv(pc, L, st);
+  cudaEventRecord(e1, st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(in); cudaFree(out); if (res) cudaFree(res);
+  free_packed_conv(&pc);
+  if (rc) return rc;
+  if (se != cudaSuccess) return fail(AICAM_ERR_CUDA, std::string("conv2d_bench: ") + cudaGetErrorString(se));
+  *mean_ms = ms / iters;
   return AICAM_OK;
 }
 

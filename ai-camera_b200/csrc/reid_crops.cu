@@ -198,6 +198,7 @@ extern "C" int aicam_reid_crops(const uint8_t* frames, int batch, int h, int w, 
     return fail(AICAM_ERR_INVALID_ARG, "reid_crops: null argument");
   if (batch < 0 || stride_k <= 0 || h <= 0 || w <= 0 || max_crops < 0 || (format != 0 && format != 1))
     return fail(AICAM_ERR_INVALID_ARG, "reid_crops: bad shape arguments");
+  if (reinterpret_cast<uintptr_t>(boxes) % 16) return fail(AICAM_ERR_INVALID_ARG, "reid_crops: boxes must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   filter_kernel<<<1, 1024, 0, st>>>(boxes, scores, labels, num_dets, batch, stride_k, h, w, min_confidence,
                                     class_mask_lo, class_mask_hi, max_crops, det_index, det_count, crop_slot, crop_rect,

@@ -718,6 +718,7 @@ int aicam_tracker_step(aicam_tracker* t, const float* boxes, const float* scores
   if (!t || !boxes || !scores || !labels || !det_index || !det_count || !crop_slot || !out_tracks || !out_conf || !out_count)
     return fail(AICAM_ERR_INVALID_ARG, "tracker_step: null argument");
   if (stride_k <= 0) return fail(AICAM_ERR_INVALID_ARG, "tracker_step: stride_k must be positive");
+  if (reinterpret_cast<uintptr_t>(boxes) % 16) return fail(AICAM_ERR_INVALID_ARG, "tracker_step: boxes must be 16-byte aligned");
   const Dev& d = t->d;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (feats) {

@@ -42,8 +42,9 @@ class DeepSORT:
         self.frame_count = 0
         self.K, self.T = max_dets, max_tracks
         K, T = self.K, self.T
-        self._in_host = torch.zeros(1 + 6 * K, dtype=torch.int32).pin_memory()
-        self._in_dev = torch.zeros(1 + 6 * K, dtype=torch.int32, device=self.device)
+        # [num, 3 pad words | boxes 4K | scores K | labels K]: the box table must stay 16-byte aligned
+        self._in_host = torch.zeros(4 + 6 * K, dtype=torch.int32).pin_memory()
+        self._in_dev = torch.zeros(4 + 6 * K, dtype=torch.int32, device=self.device)
         self._out_host = torch.zeros(1 + 7 * T, dtype=torch.int32).pin_memory()
         self._out_dev = torch.zeros(1 + 7 * T, dtype=torch.int32, device=self.device)
         self._frame_host = None
@@ -71,16 +72,16 @@ class DeepSORT:
         h = self._in_host.numpy()
         h[0] = n
         if n:
-            h[1:1 + 4 * n].view(np.float32)[:] = np.asarray(yolo_bboxes_xyxy, dtype=np.float32).reshape(-1)
-            h[1 + 4 * K:1 + 4 * K + n].view(np.float32)[:] = np.asarray(yolo_confidences, dtype=np.float32)
-            h[1 + 5 * K:1 + 5 * K + n] = np.asarray(yolo_class_ids).astype(np.int32)
+            h[4:4 + 4 * n].view(np.float32)[:] = np.asarray(yolo_bboxes_xyxy, dtype=np.float32).reshape(-1)
+            h[4 + 4 * K:4 + 4 * K + n].view(np.float32)[:] = np.asarray(yolo_confidences, dtype=np.float32)
+            h[4 + 5 * K:4 + 5 * K + n] = np.asarray(yolo_class_ids).astype(np.int32)
         frames = self._upload(original_frame_bgr)
         d = self._in_dev
         d.copy_(self._in_host, non_blocking=True)
         num = d[0:1]
-        boxes = d[1:1 + 4 * K].view(torch.float32).view(1, K, 4)
-        scores = d[1 + 4 * K:1 + 5 * K].view(torch.float32).view(1, K)
-        labels = d[1 + 5 * K:1 + 6 * K].view(1, K)
+        boxes = d[4:4 + 4 * K].view(torch.float32).view(1, K, 4)
+        scores = d[4 + 4 * K:4 + 5 * K].view(torch.float32).view(1, K)
+        labels = d[4 + 5 * K:4 + 6 * K].view(1, K)
         out_tracks, out_conf, out_count = self._trk.update(frames, num, boxes, scores, labels)
         o = self._out_dev
         o[0:1].copy_(out_count)

@@ -69,7 +69,8 @@ CLS_LAYERS = ["model.22.cv3.%d.2" % l for l in range(3)]
 
 
 def calibrate_detector(detector, frames, target_tracked=16.0, iters=12):
-    """Shift every class logit by one constant so that, on `frames`, the mean number of
+    """Shift every class logit by one constant so that, on `frames` (one batch or a list of
+    batches), the mean number of
     tracked-class detections per frame is close to `target_tracked`.  Returns the bias
     vectors set ({layer name: float32 array}) so a CPU run can apply the same ones."""
     eng = detector.engine
@@ -78,13 +79,18 @@ def calibrate_detector(detector, frames, target_tracked=16.0, iters=12):
     tracked = torch.tensor([c for c in range(64) if (lo_mask >> c) & 1] + [64 + c for c in range(64) if (hi_mask >> c) & 1],
                            device=detector.device, dtype=torch.int32)
 
+    batches = frames if isinstance(frames, (list, tuple)) else [frames]
+
     def count(delta):
         for n in CLS_LAYERS:
             eng.set_bias(n, base[n] + np.float32(delta))
-        num, boxes, scores, labels = detector.detect(frames)
-        k = torch.arange(labels.shape[1], device=labels.device)[None, :] < num[:, None]
-        ok = k & torch.isin(labels, tracked) & (scores >= config.DEEPSORT_MIN_CONFIDENCE)
-        return ok.sum().item() / frames.shape[0]
+        total = 0
+        for fb in batches:
+            num, boxes, scores, labels = detector.detect(fb)
+            k = torch.arange(labels.shape[1], device=labels.device)[None, :] < num[:, None]
+            ok = k & torch.isin(labels, tracked) & (scores >= config.DEEPSORT_MIN_CONFIDENCE)
+            total += ok.sum().item()
+        return total / sum(fb.shape[0] for fb in batches)
 
     lo, hi = -6.0, 3.0
     best = (None, 1e9)

@@ -74,10 +74,13 @@ class TRTEngine(torch.nn.Module):
             self._nhwc = torch.empty((self.max_batch, h, w, 4), dtype=torch.bfloat16, device=self.device)
 
     def __del__(self):
-        h = getattr(self, "_h", None)
-        if h:
-            self._lib.aicam_engine_destroy(h)
-            self._h = None
+        try:
+            h = self.__dict__.get("_h")
+            if h:
+                self.__dict__["_h"] = None
+                self.__dict__["_lib"].aicam_engine_destroy(h)
+        except Exception:  # interpreter shutdown
+            pass
 
     # -- raw entry points used by the batched pipeline ------------------------------------------
     @property

@@ -176,7 +176,7 @@ def main():
     yolo, reid = synth.make_blobs(blob_dir)
     video = synth.SynthVideo(S, FRAME_HW, n_frames=RING, device=dev, first_stream=rank * S)
     pipe = TrackingPipeline(yolo, reid, S, dev, max_tracks=128, max_crops=S * 40)
-    delta, bias = synth.calibrate_detector(pipe.detector, video.frames(0), TARGET_DETS)
+    delta, bias = synth.calibrate_detector(pipe.detector, [video.ring[k] for k in range(0, RING, 3)], TARGET_DETS)
     if rank == 0:
         np.savez(os.path.join(blob_dir, "calibrated_bias.npz"), **bias)
 

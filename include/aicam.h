@@ -102,6 +102,9 @@ typedef struct {
 } aicam_conv_desc;
 int aicam_conv2d(const aicam_conv_desc* d, const void* in_nhwc, const float* weights_oihw,
                  const float* bias, const void* res_nhwc, void* out_nhwc, void* stream);
+/* Micro-benchmark of the same operator on device-resident random data: `iters` launches
+ * bracketed by CUDA events on `stream`; returns the mean kernel time in milliseconds. */
+int aicam_conv2d_bench(const aicam_conv_desc* d, int iters, double* mean_ms, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Preprocessing: replaces image_processing.letterbox + preprocess_yolo_input
