@@ -66,6 +66,22 @@ class SynthVideo:
 
 
 CLS_LAYERS = ["model.22.cv3.%d.2" % l for l in range(3)]
+# Operating point of the seeded synthetic detector (yolov8n seed 0) on SynthVideo frames: the
+# class-logit shift at which ~16 tracked-class detections per 1080p frame survive NMS.  Found
+# once with calibrate_detector() on a B200 and committed, so that the device run and the CPU
+# baseline use the same detector.
+DEFAULT_LOGIT_SHIFT = -0.98
+
+
+def shifted_class_bias(yolo_blob_path, shift=DEFAULT_LOGIT_SHIFT):
+    """{layer name: bias + shift} for the three class-logit convolutions of a yolov8 blob."""
+    tensors = weights.read_blob(yolo_blob_path)[2]
+    return {n: (tensors[n + ".bias"] + np.float32(shift)).astype(np.float32) for n in CLS_LAYERS}
+
+
+def apply_class_bias(engine, bias):
+    for n, b in bias.items():
+        engine.set_bias(n, b)
 
 
 def calibrate_detector(detector, frames, target_tracked=16.0, iters=12):

@@ -112,14 +112,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-    import torch
+    import torch  # noqa: F401
     from ai_camera_b200 import synth
     yolo, reid = synth.make_blobs(os.path.join(ROOT, "gpurun_out", "blobs"))
-    bias = None
-    bias_file = os.path.join(ROOT, "gpurun_out", "blobs", "calibrated_bias.npz")
-    if os.path.exists(bias_file):
-        bias = dict(np.load(bias_file))
+    bias = synth.shifted_class_bias(yolo)
     n_sample = 2  # streams sampled per step (a bounded sample of the 64-stream batch)
     video = synth.SynthVideo(n_sample, FRAME_HW, n_frames=6, device="cpu")
     frames = [[video.ring[t, s].numpy() for t in range(video.n_frames)] for s in range(n_sample)]
@@ -164,7 +160,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
-    from ai_camera_b200 import _lib, synth
+    from ai_camera_b200 import _lib, sharding, synth
     from ai_camera_b200.pipeline import TrackingPipeline
     lib = _lib.load()
     S = args.streams
@@ -174,11 +170,12 @@ def main():
     if world > 1:
         dist.barrier()
     yolo, reid = synth.make_blobs(blob_dir)
-    video = synth.SynthVideo(S, FRAME_HW, n_frames=RING, device=dev, first_stream=rank * S)
+    first_stream, _ = sharding.stream_partition(S * world, world, rank)  # weak scaling: S streams per GPU
+    video = synth.SynthVideo(S, FRAME_HW, n_frames=RING, device=dev, first_stream=first_stream)
     pipe = TrackingPipeline(yolo, reid, S, dev, max_tracks=128, max_crops=S * 40)
-    delta, bias = synth.calibrate_detector(pipe.detector, [video.ring[k] for k in range(0, RING, 3)], TARGET_DETS)
-    if rank == 0:
-        np.savez(os.path.join(blob_dir, "calibrated_bias.npz"), **bias)
+    delta = synth.DEFAULT_LOGIT_SHIFT
+    bias = synth.shifted_class_bias(yolo, delta)
+    synth.apply_class_bias(pipe.detector.engine, bias)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -302,14 +299,7 @@ def main():
     achieved_tflops = flops_step / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step > 0 else 0.0
 
     # ---- gather (the only collective: final stats) -------------------------------------------
-    stats = torch.tensor([total_ms, e2e_s, crops_per_step, float(tracks_out), float(overflow)], device=dev,
-                         dtype=torch.float64)
-    if world > 1:
-        allst = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(allst, stats)
-        allst = torch.stack(allst).cpu().numpy()
-    else:
-        allst = stats.cpu().numpy()[None]
+    allst = np.asarray(sharding.gather_stats([total_ms, e2e_s, crops_per_step, float(tracks_out), float(overflow)], dev))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
