@@ -618,6 +618,7 @@ int pick_n_tile(int cout_pad, bool out_f32) {
 }  // namespace
 
 extern void count_launch();
+int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream);
 bool profile_begin(cudaStream_t st, size_t* slot);
 void profile_end(cudaStream_t st, size_t slot);
 
@@ -708,11 +709,17 @@ int launch_conv(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream) 
     return fail(AICAM_ERR_INVALID_ARG, "launch_conv: input channel stride/offset must be multiples of 8");
   if (a.stem && (L.in_cstride != 4 || L.in_coff != 0))
     return fail(AICAM_ERR_INVALID_ARG, "launch_conv: stem input must be NHWC4");
+  // 3x3 / 1x1 stride-1 layers: patch-based window kernel (conv_win.cu) when the shape is eligible
+  {
+    const int wrc = try_launch_conv_win(pc, L, stream);
+    if (wrc < 0) return wrc;
+    if (wrc == 1) return AICAM_OK;
+  }
   // TMA im2col path: whole 128-pixel x slab-channel tiles per instruction (all layers but the stems)
   alignas(64) CUtensorMap tmap;
   std::memset(&tmap, 0, sizeof(tmap));
   a.tma = 0; a.slab = 0; a.slabs_per_tap = 0; a.sub_per_kb = 0; a.n_sub_total = 0;
-  static const bool no_tma = getenv("AICAM_NO_TMA") != nullptr;
+  static const bool no_tma = getenv("AICAM_TMA_IM2COL") == nullptr;  // opt-in: the cached gather is faster on B200
   if (!a.stem && !no_tma && pc.cin_pad % 16 == 0 && get_encode_im2col() != nullptr) {
     a.slab = pc.cin_pad % 64 == 0 ? 64 : (pc.cin_pad % 32 == 0 ? 32 : 16);
     a.slabs_per_tap = pc.cin_pad / a.slab;

@@ -1,0 +1,754 @@
+// "Window" convolution on tcgen05 tensor cores: 3x3 / stride 1 / pad 1 and 1x1 / stride 1 layers, sm_100a.
+//
+// Same operator as conv_tc.cu (the layers the reference hands to its TensorRT engines,
+// /root/reference/src/trt_utils/trt_engine.py:191), different data movement.  conv_tc.cu builds an
+// im2col A tile per filter tap, so a 3x3 layer pulls every input pixel through L2 nine times and
+// re-streams the whole weight tensor for every 128-pixel tile; measured on B200 that traffic
+// (~57 B/clk/SM), not the tensor pipe, bounds the small-channel layers.  Here:
+//
+//   * ONE tiled TMA load per (tile, 64-channel slab) brings a haloed input patch
+//     [rows][raster width RW = strip width + 2][slab] into shared memory (hardware 32/64/128-byte
+//     swizzle, out-of-image halo pixels zero-filled by the TMA unit = the convolution's padding);
+//   * output positions are enumerated in the patch's own raster (row pitch RW), so the A operand of
+//     filter tap (dy, dx) is the SAME shared-memory patch read through a UMMA descriptor whose start
+//     address is advanced by (dy*RW + dx) pixels: nine taps, zero extra bytes.  The two raster
+//     columns per row that have no output pixel produce junk accumulator rows that are never stored;
+//   * weights stay resident in shared memory for the life of the persistent CTA when they fit
+//     (<= 120 KB, all YOLOv8n 3x3 layers up to 80 channels and the ReID 64-channel stage), otherwise
+//     they stream through a 4-deep ring, each block feeding `mt` (1 or 2) 128-row accumulators;
+//   * accumulators are double-buffered in TMEM (2 x mt x n_tile columns), so the epilogue of tile i
+//     (TMEM -> registers -> bias / residual / activation -> staging -> coalesced 16-byte stores)
+//     overlaps the MMAs of tile i+1; the epilogue is warp-local (no block barriers).
+//
+// Warp roles (608 threads): 0-15 epilogue (four warpgroups split the accumulator columns; TMEM lane
+// quarter = warp % 4), 16 MMA issuer (one thread) + TMEM owner, 17 patch (A) producer, 18 weight (B) producer.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "conv_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace aicam {
+
+extern void count_launch();
+bool profile_begin(cudaStream_t st, size_t* slot);
+void profile_end(cudaStream_t st, size_t slot);
+
+namespace {
+
+using namespace ptx;
+
+constexpr int NWG = 4;                          // epilogue warpgroups
+constexpr int WIN_THREADS = (4 * NWG + 3) * 32;  // + MMA issuer, patch producer, weight producer
+constexpr int MAX_RING = 8;
+constexpr uint32_t OFF_BIAS = 512;      // fp32 bias, <= 512 channels
+constexpr uint32_t OFF_ROWOFF = 2560;   // 2 tile parities x (output, residual) x 8 teams x 32 rows x int64 element offsets
+constexpr uint32_t OFF_RING_A = 11264;   // 1024-byte aligned: swizzle patterns repeat every 1024 B
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+constexpr size_t RESIDENT_LIMIT = 120 * 1024;
+
+struct WinArgs {
+  int mode;  // 0: 3x3 window over 4-D patches, 1: 1x1 over the flat [pixels][channels] matrix
+  int h, w, hw;
+  int rw, tw, strips, tstep, tiles_per_strip, tiles_per_img;
+  float inv_rw;
+  int flat;  // 1x1 mode: output and residual are dense, pixel p of the batch sits at p * cstride
+  int mt, tm;
+  int slab, slabs, taps, cin_pad;
+  int resident, sa, sb;
+  uint32_t patch_bytes, box_bytes, bstage_bytes, wbytes;
+  int n_tile, n_tiles, cout, cout_pad;
+  const __nv_bfloat16* wgt;
+  const float* bias;
+  void* out;
+  long long out_img_stride;
+  int out_cstride, out_coff, out_f32;
+  const __nv_bfloat16* res;
+  long long res_img_stride;
+  int res_cstride, res_coff, res_mode;
+  int act;
+  int batch;
+  const int* batch_dev;
+  uint32_t idesc, tmem_cols;
+  uint32_t off_w, off_b, off_stage, off_res, stage_pitch, res_pitch;
+};
+
+__device__ __forceinline__ float silu_fast(float x) {
+  // x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU instead of two
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+// tcgen05.mma with the two 64-bit descriptors passed as (lo, hi) halves: the issuing warp only
+// ever adds to the low halves (start address >> 4), the high halves are loop constants.  Executed by
+// the whole (converged) warp, performed by the lane whose `leader` predicate is set.
+__device__ __forceinline__ void mma_issue(bool leader, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                          uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(leader))
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_if(bool leader, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar),
+      "r"(static_cast<uint32_t>(leader))
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+template <int ACT>
+__device__ __forceinline__ float activate(float x) {
+  if (ACT == 1) return silu_fast(x);
+  if (ACT == 2) return fmaxf(x, 0.0f);
+  return x;
+}
+
+// One 16-column group of an accumulator row: + bias (+ residual), activation, pack into the staging row.
+template <int ACT>
+__device__ __forceinline__ void finish_group(const uint32_t (&v)[16], const float* bias, const uint8_t* res_row,
+                                             int res_mode, int out_f32, uint8_t* dst) {
+  float x[16];
+  const float4* bp = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 b4 = bp[i];
+    x[4 * i] = __uint_as_float(v[4 * i]) + b4.x;
+    x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+    x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+    x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+  }
+  if (res_mode) {
+    const uint4 q0v = *reinterpret_cast<const uint4*>(res_row);
+    const uint4 q1v = *reinterpret_cast<const uint4*>(res_row + 16);
+    const uint32_t rw_[8] = {q0v.x, q0v.y, q0v.z, q0v.w, q1v.x, q1v.y, q1v.z, q1v.w};
+    if (res_mode == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[2 * i] = activate<ACT>(x[2 * i] + bf16_lo(rw_[i]));
+        x[2 * i + 1] = activate<ACT>(x[2 * i + 1] + bf16_hi(rw_[i]));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[2 * i] = activate<ACT>(x[2 * i]) + bf16_lo(rw_[i]);
+        x[2 * i + 1] = activate<ACT>(x[2 * i + 1]) + bf16_hi(rw_[i]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = activate<ACT>(x[i]);
+  }
+  if (out_f32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(dst + i * 16) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+  } else {
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(x[0], x[1]);   o0.y = pack_bf16x2(x[2], x[3]);
+    o0.z = pack_bf16x2(x[4], x[5]);   o0.w = pack_bf16x2(x[6], x[7]);
+    o1.x = pack_bf16x2(x[8], x[9]);   o1.y = pack_bf16x2(x[10], x[11]);
+    o1.z = pack_bf16x2(x[12], x[13]); o1.w = pack_bf16x2(x[14], x[15]);
+    *reinterpret_cast<uint4*>(dst) = o0;
+    *reinterpret_cast<uint4*>(dst + 16) = o1;
+  }
+}
+
+// Tile index -> image, column strip and first raster position (window mode)
+struct TilePos {
+  int n_img, strip, q0;
+};
+__device__ __forceinline__ TilePos tile_pos(const WinArgs& a, int mt_idx) {
+  TilePos t;
+  t.n_img = mt_idx / a.tiles_per_img;
+  const int r2 = mt_idx - t.n_img * a.tiles_per_img;
+  t.strip = r2 / a.tiles_per_strip;
+  t.q0 = (r2 - t.strip * a.tiles_per_strip) * a.tstep;
+  return t;
+}
+
+template <int SLAB, int TAPS, int MT, int ACT>
+__global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs a, const __grid_constant__ CUtensorMap tmap) {
+  constexpr uint32_t ROW_BYTES = SLAB * 2;
+  constexpr int K16S = SLAB / 16;
+  constexpr uint32_t LTYPE = SLAB == 64 ? 2u : (SLAB == 32 ? 4u : 6u);
+  constexpr int MODE = TAPS == 9 ? 0 : 1;
+  constexpr int TM = 128 * MT;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_a_full = sbase, bar_a_empty = sbase + 64, bar_b_full = sbase + 128, bar_b_empty = sbase + 192;
+  const uint32_t bar_acc_full = sbase + 256, bar_acc_empty = sbase + 272, bar_w_full = sbase + 288;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 320);
+  float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  int batch = a.batch;
+  if (a.batch_dev) batch = min(batch, __ldg(a.batch_dev));
+  long long m_tiles;
+  if (MODE == 0) m_tiles = static_cast<long long>(batch) * a.tiles_per_img;
+  else m_tiles = (static_cast<long long>(batch) * a.hw + TM - 1) / TM;
+  const int total_tiles = static_cast<int>(m_tiles) * a.n_tiles;
+  if (static_cast<int>(blockIdx.x) >= total_tiles) return;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_RING; ++s) {
+      mbar_init(bar_a_full + 8 * s, 1);
+      mbar_init(bar_a_empty + 8 * s, 1);
+      mbar_init(bar_b_full + 8 * s, 1);
+      mbar_init(bar_b_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_acc_full + 8 * s, 1);
+      mbar_init(bar_acc_empty + 8 * s, 128 * NWG);
+    }
+    mbar_init(bar_w_full, 1);
+    mbar_init_fence();
+  }
+  if (warp == 4 * NWG) tc_alloc(smem_u32(tmem_ptr_smem), a.tmem_cols);
+  if (warp == 4 * NWG + 1 && lane == 0) tma_prefetch_desc(&tmap);
+  for (int i = threadIdx.x; i < a.cout_pad; i += WIN_THREADS) bias_s[i] = __ldg(a.bias + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t acc_cols = static_cast<uint32_t>(MT * a.n_tile);
+
+  if (warp < 4 * NWG) {
+    // ================================================================== epilogue (16 warps)
+    // The PARTS warps {wq + 4 p} that share TMEM lane quarter wq (rows 32 wq .. 32 wq + 31 of a
+    // 128-row accumulator) form a team.  TMEM -> staging is split by COLUMNS inside the team (a warp
+    // can only read its own lane quarter), the global <-> staging copies are split by ROWS so that
+    // every copy instruction moves whole contiguous rows.  Two named barriers per tile keep the team
+    // in step.  MT == 1: one team of 4 warps per quarter; MT == 2: two teams of 2 (one per accumulator).
+    constexpr int PARTS = MT == 2 ? 2 : 4;
+    constexpr int ROWS_PER_WARP = 32 / PARTS;
+    const int wg = warp >> 2, wq = warp & 3;
+    const int my_j = MT == 2 ? (wg >> 1) : 0;
+    const int part = MT == 2 ? (wg & 1) : wg;
+    const int row = wq * 32 + lane;          // my accumulator row (TMEM lane)
+    const int bar_id = 1 + my_j * 4 + wq;    // named barrier of my team
+    const int bar_threads = 32 * PARTS;
+    const uint32_t taddr_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+    const int esize = a.out_f32 ? 4 : 2;
+    const uint32_t pitch = a.stage_pitch, rpitch = a.res_pitch;
+    uint8_t* stage_q = smem + a.off_stage + static_cast<size_t>(my_j * 128 + wq * 32) * pitch;  // my team's 32 rows
+    uint8_t* my_stage = stage_q + static_cast<size_t>(lane) * pitch;
+    uint8_t* res_q = smem + a.off_res + static_cast<size_t>(my_j * 128 + wq * 32) * rpitch;
+    const uint8_t* my_res = res_q + static_cast<size_t>(lane) * rpitch;
+    // element offsets of the team's 32 rows in the output / residual tensors (-1: not stored),
+    // double-buffered by tile parity, written by the team's part-0 warp
+    long long* rowoff_base = reinterpret_cast<long long*>(smem + OFF_ROWOFF) + (my_j * 4 + wq) * 32;
+    uint8_t* out_bytes = reinterpret_cast<uint8_t*>(a.out);
+    const long long total_pix = static_cast<long long>(batch) * a.hw;
+
+    // publish where the team's rows of `tile` live (part-0 warp, lane = row)
+    auto publish_rows = [&](int tile, int slot) {
+      const int mt_idx = tile / a.n_tiles;
+      const int n0 = (tile - mt_idx * a.n_tiles) * a.n_tile;
+      bool valid;
+      int img, pix;
+      if (MODE == 0) {
+        const TilePos tp = tile_pos(a, mt_idx);
+        const int rel = my_j * 128 + row;
+        const int q = tp.q0 + rel;
+        const int y = __float2int_rd((static_cast<float>(q) + 0.5f) * a.inv_rw);  // exact: q < 2^18
+        const int xp = q - y * a.rw;
+        const int x = tp.strip * a.tw + xp;
+        valid = rel < a.tstep && y < a.h && xp < a.tw && x < a.w;
+        img = tp.n_img;
+        pix = y * a.w + x;
+      } else {
+        const long long p = static_cast<long long>(mt_idx) * TM + my_j * 128 + row;
+        valid = p < total_pix;
+        if (a.flat) {  // every tensor involved is dense: pixel p of the batch is at p * cstride
+          img = 0;
+          pix = static_cast<int>(p);
+        } else {
+          img = static_cast<int>(p) / a.hw;
+          pix = static_cast<int>(p) - img * a.hw;
+        }
+      }
+      long long* ro = rowoff_base + slot * (2 * 8 * 32);
+      ro[lane] = valid ? img * a.out_img_stride + static_cast<long long>(pix) * a.out_cstride + a.out_coff + n0 : -1;
+      if (a.res_mode)
+        ro[8 * 32 + lane] = valid ? img * a.res_img_stride + static_cast<long long>(pix) * a.res_cstride + a.res_coff + n0 : -1;
+    };
+    // residual rows [ROWS_PER_WARP * part, +ROWS_PER_WARP) of the team's quarter -> residual staging:
+    // 16-byte cp.async, lanes on consecutive chunks of a row (whole rows per instruction)
+    auto prefetch_res = [&](int tile, int slot) {
+      const int n0 = (tile % a.n_tiles) * a.n_tile;
+      const int rcpr = (min(a.n_tile, a.cout - n0) * 2) >> 4;
+      int sh = 0;
+      while ((1 << sh) < rcpr) ++sh;
+      const int ch = lane & ((1 << sh) - 1);
+      const long long* ro = rowoff_base + slot * (2 * 8 * 32) + 8 * 32;
+      for (int rr = lane >> sh; rr < ROWS_PER_WARP; rr += 32 >> sh) {
+        const int r = part * ROWS_PER_WARP + rr;
+        const long long off = ro[r];
+        if (off >= 0 && ch < rcpr) cp_async_16(smem_u32(res_q + static_cast<size_t>(r) * rpitch + ch * 16), a.res + off + ch * 8);
+      }
+    };
+
+    if (part == 0) publish_rows(blockIdx.x, 0);
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+    if (a.res_mode) prefetch_res(blockIdx.x, 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int n0 = (tile % a.n_tiles) * a.n_tile;
+      const int ncols = min(a.n_tile, a.cout - n0);
+      const int groups = (ncols + 15) >> 4;
+      const int c_lo = min(ncols, ((groups * part) / PARTS) << 4);  // my column range in the TMEM phase
+      const int c_hi = min(ncols, ((groups * (part + 1)) / PARTS) << 4);
+      const long long* ro = rowoff_base + buf * (2 * 8 * 32);
+      mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      if (a.res_mode) cp_async_wait_all();
+      // B1: the team's residual rows have landed, its row offsets are published, and every warp of
+      // the team is done copying the previous tile out of the staging rows
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+      const bool valid = ro[lane] >= 0;
+      // ---- TMEM -> registers -> bias / residual / activation -> my staging row (32 columns in flight)
+      const uint32_t taddr = taddr_lane + buf * acc_cols + my_j * a.n_tile;
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+        uint32_t v0[16], v1[16];
+        const bool two = c0 + 16 < c_hi;  // warp-uniform
+        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-row predicated body
+        tc_ld16_nowait(taddr + c0, v0);
+        if (two) tc_ld16_nowait(taddr + c0 + 16, v1);
+        tc_ld_wait();
+        if (valid) {
+          finish_group<ACT>(v0, bias_s + n0 + c0, my_res + c0 * 2, a.res_mode, a.out_f32, my_stage + c0 * esize);
+          if (two)
+            finish_group<ACT>(v1, bias_s + n0 + c0 + 16, my_res + (c0 + 16) * 2, a.res_mode, a.out_f32,
+                              my_stage + (c0 + 16) * esize);
+        }
+      }
+      // my part of the accumulator buffer has been read: the MMA thread may reuse it for tile it + 2
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty + 8 * buf);
+      const int next = tile + static_cast<int>(gridDim.x);
+      if (part == 0 && next < total_tiles) publish_rows(next, buf ^ 1);
+      // B2: the team's staging rows are complete, the residual staging is free, next offsets are published
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+      if (a.res_mode && next < total_tiles) prefetch_res(next, buf ^ 1);
+      // ---- staging -> global, rows [ROWS_PER_WARP * part, +ROWS_PER_WARP): whole rows per instruction
+      {
+        const int cpr = (ncols * esize) >> 4;
+        int sh = 0;
+        while ((1 << sh) < cpr) ++sh;
+        const int ch = lane & ((1 << sh) - 1);
+        for (int rr = lane >> sh; rr < ROWS_PER_WARP; rr += 32 >> sh) {
+          const int r = part * ROWS_PER_WARP + rr;
+          const long long oo = ro[r];
+          if (oo >= 0 && ch < cpr) {
+            const uint4 val = *reinterpret_cast<const uint4*>(stage_q + static_cast<size_t>(r) * pitch + ch * 16);
+            *reinterpret_cast<uint4*>(out_bytes + oo * esize + ch * 16) = val;
+          }
+        }
+      }
+    }
+  } else if (warp == 4 * NWG) {
+    // ================================================================== MMA issuer
+    // The whole warp walks the loop convergently, so every descriptor lives in uniform registers;
+    // only the tcgen05.mma / tcgen05.commit instructions are predicated on one elected lane.
+    {
+      const bool leader = elect_one();
+      const uint32_t a_hi = ((8 * ROW_BYTES) >> 4) | (1u << 14) | (LTYPE << 29);  // SBO | version | swizzle
+      const uint32_t b_hi = (128u >> 4) | (1u << 14);                           // SBO = 128 B, no swizzle
+      const uint32_t a_ring = sbase + OFF_RING_A, b_ring = sbase + a.off_b, w_base = sbase + a.off_w;
+      const uint32_t rw_units = static_cast<uint32_t>(a.rw) * (ROW_BYTES >> 4);  // one raster row, in 16-byte units
+      const uint32_t lbo = static_cast<uint32_t>(a.resident ? a.cout_pad : a.n_tile);  // K-chunk stride, 16-byte units
+      const uint32_t b_k16 = 2 * lbo;
+      const uint32_t b_lo_flags = lbo << 16;
+      const uint32_t idesc = a.idesc;
+      const uint32_t n_tile = static_cast<uint32_t>(a.n_tile);
+      const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+      uint32_t sa = 0, pa = 0, sbi = 0, pb = 0;  // ring slot / phase parity of the A and B rings
+      const uint32_t n_sa = a.sa, n_sb = a.sb;
+      int it = 0;
+      if (a.resident) mbar_wait(bar_w_full, 0);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        uint32_t xp0 = 0;
+        if (MODE == 0) {
+          const int mt_idx = tile / a.n_tiles;
+          const int r2 = mt_idx % a.tiles_per_img;
+          xp0 = static_cast<uint32_t>(((r2 % a.tiles_per_strip) * a.tstep) % a.rw);
+        }
+        mbar_wait(bar_acc_empty + 8 * buf, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem0 + buf * acc_cols;
+        for (int s = 0; s < a.slabs; ++s) {
+          mbar_wait(bar_a_full + 8 * sa, pa);
+          tc_fence_after();
+          // descriptor low word of the patch at raster position xp0: start >> 4 | LBO (unused, 1)
+          const uint32_t a_lo0 = ((a_ring + sa * a.patch_bytes) >> 4) + xp0 * (ROW_BYTES >> 4) + (1u << 16);
+          uint32_t w_lo = ((w_base >> 4) + static_cast<uint32_t>(s * SLAB >> 3) * lbo) | b_lo_flags;
+          const uint32_t w_tap = static_cast<uint32_t>(a.cin_pad >> 3) * lbo;
+#pragma unroll
+          for (int t = 0; t < TAPS; ++t) {
+            const int dy = t / 3, dx = t - dy * 3;  // TAPS == 1: (0, 0)
+            const uint32_t a_lo = a_lo0 + dy * rw_units + dx * (ROW_BYTES >> 4);
+            uint32_t b_lo;
+            if (a.resident) {
+              b_lo = w_lo;
+              w_lo += w_tap;
+            } else {
+              mbar_wait(bar_b_full + 8 * sbi, pb);
+              tc_fence_after();
+              b_lo = ((b_ring + sbi * a.bstage_bytes) >> 4) | b_lo_flags;
+            }
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+#pragma unroll
+              for (int k = 0; k < K16S; ++k)
+                mma_issue(leader, d_tmem + j * n_tile, a_lo + j * (128 * ROW_BYTES >> 4) + k * 2, a_hi, b_lo + k * b_k16, b_hi,
+                          idesc, (s | t | k) != 0 ? 1u : 0u);
+            }
+            if (!a.resident) {
+              tc_commit_if(leader, bar_b_empty + 8 * sbi);
+              if (++sbi == n_sb) { sbi = 0; pb ^= 1; }
+            }
+          }
+          tc_commit_if(leader, bar_a_empty + 8 * sa);
+          if (++sa == n_sa) { sa = 0; pa ^= 1; }
+        }
+        tc_commit_if(leader, bar_acc_full + 8 * buf);
+      }
+      tc_fence_before();
+    }
+  } else if (warp == 4 * NWG + 1) {
+    // ================================================================== patch (A) producer
+    if (lane == 0) {
+      const uint32_t a_ring = sbase + OFF_RING_A;
+      uint32_t sa = 0, pa = 1;
+      const uint32_t n_sa = a.sa;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt_idx = tile / a.n_tiles;
+        int n_img = 0, x_start = 0, y_start = 0;
+        if (MODE == 0) {
+          const TilePos tp = tile_pos(a, mt_idx);
+          n_img = tp.n_img;
+          x_start = tp.strip * a.tw - 1;
+          y_start = tp.q0 / a.rw - 1;
+        }
+        for (int s = 0; s < a.slabs; ++s) {
+          mbar_wait(bar_a_empty + 8 * sa, pa);
+          const uint32_t bar = bar_a_full + 8 * sa;
+          mbar_arrive_expect_tx(bar, a.box_bytes);
+          if (MODE == 0) tma_load_4d(a_ring + sa * a.patch_bytes, &tmap, bar, s * SLAB, x_start, y_start, n_img);
+          else tma_load_2d(a_ring + sa * a.patch_bytes, &tmap, bar, s * SLAB, mt_idx * TM);
+          if (++sa == n_sa) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ================================================================== weight (B) producer
+    if (lane == 0) {
+      if (a.resident) {
+        mbar_arrive_expect_tx(bar_w_full, a.wbytes);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wgt);
+        for (uint32_t off = 0; off < a.wbytes; off += 16384)
+          bulk_g2s(sbase + a.off_w + off, src + off, min(16384u, a.wbytes - off), bar_w_full);
+      } else {
+        const uint32_t b_ring = sbase + a.off_b;
+        const uint32_t chunk_bytes = static_cast<uint32_t>(a.n_tile) * 16;
+        constexpr int nchunks = SLAB / 8;
+        uint32_t sbi = 0, pb = 1;
+        const uint32_t n_sb = a.sb;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int n0 = (tile % a.n_tiles) * a.n_tile;
+          for (int s = 0; s < a.slabs; ++s) {
+            for (int t = 0; t < TAPS; ++t) {
+              mbar_wait(bar_b_empty + 8 * sbi, pb);
+              const uint32_t bar = bar_b_full + 8 * sbi;
+              const uint32_t dst = b_ring + sbi * a.bstage_bytes;
+              mbar_arrive_expect_tx(bar, a.bstage_bytes);
+              const int chunk0 = (t * a.cin_pad + s * SLAB) >> 3;
+              const __nv_bfloat16* src = a.wgt + (static_cast<long long>(chunk0) * a.cout_pad + n0) * 8;
+              if (a.n_tile == a.cout_pad) {
+                bulk_g2s(dst, src, a.bstage_bytes, bar);
+              } else {
+                for (int c = 0; c < nchunks; ++c)
+                  bulk_g2s(dst + c * chunk_bytes, src + static_cast<long long>(c) * a.cout_pad * 8, chunk_bytes, bar);
+              }
+              if (++sbi == n_sb) { sbi = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4 * NWG) {
+    tc_fence_after();
+    tc_dealloc(tmem_base, a.tmem_cols);
+  }
+}
+
+typedef void (*WinKernelFn)(const WinArgs, const CUtensorMap);
+
+template <int SLAB, int TAPS, int MT>
+WinKernelFn pick_act(int act) {
+  if (act == 1) return conv_win_kernel<SLAB, TAPS, MT, 1>;
+  if (act == 2) return conv_win_kernel<SLAB, TAPS, MT, 2>;
+  return conv_win_kernel<SLAB, TAPS, MT, 0>;
+}
+template <int SLAB, int TAPS>
+WinKernelFn pick_mt(int mt, int act) {
+  return mt == 2 ? pick_act<SLAB, TAPS, 2>(act) : pick_act<SLAB, TAPS, 1>(act);
+}
+template <int SLAB>
+WinKernelFn pick_taps(int taps, int mt, int act) {
+  return taps == 9 ? pick_mt<SLAB, 9>(mt, act) : pick_mt<SLAB, 1>(mt, act);
+}
+WinKernelFn pick_kernel(int slab, int taps, int mt, int act) {
+  if (slab == 64) return pick_taps<64>(taps, mt, act);
+  if (slab == 32) return pick_taps<32>(taps, mt, act);
+  return pick_taps<16>(taps, mt, act);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct WinPlan {
+  bool ok = false;
+  double cost = 0.0;
+  int rw = 0, tw = 0, strips = 1, tstep = 0, tiles_per_strip = 0, mt = 1, bh = 0;
+  int sa = 0, sb = 0;
+  uint32_t patch_bytes = 0, box_bytes = 0, off_w = 0, off_b = 0, off_stage = 0;
+  size_t smem = 0;
+  long long tiles = 0;
+};
+
+}  // namespace
+
+// Returns 1 when the layer was launched on the window kernel, 0 when the shape is not eligible
+// (the caller falls back to conv_tc_kernel), negative on error.
+int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream) {
+  static const bool disabled = getenv("AICAM_NO_WIN") != nullptr;
+  static const int force_mt = getenv("AICAM_WIN_MT") ? atoi(getenv("AICAM_WIN_MT")) : 0;
+  if (disabled || get_encode_tiled() == nullptr) return 0;
+  if (pc.stride != 1 || (pc.ksize != 1 && pc.ksize != 3) || pc.cin_pad % 16 != 0 || pc.cin_pad == 4) return 0;
+  if (L.ho != L.h || L.wo != L.w || L.batch <= 0) return 0;
+  const int es = L.out_f32 ? 4 : 2;
+  const int cout_pad = (pc.cout + 15) / 16 * 16;
+  if ((pc.cout * es) % 16 != 0 || (static_cast<long long>(L.out_cstride) * es) % 16 != 0 ||
+      (static_cast<long long>(L.out_coff) * es) % 16 != 0 || (L.out_img_stride * es) % 16 != 0 ||
+      reinterpret_cast<uintptr_t>(L.out) % 16 != 0 || cout_pad > 512)
+    return 0;
+  const int res_mode = L.res ? L.res_mode : 0;
+  if (res_mode && (L.out_f32 || pc.cout % 8 != 0 || L.res_cstride % 8 != 0 || L.res_coff % 8 != 0 || L.res_img_stride % 8 != 0 ||
+                   reinterpret_cast<uintptr_t>(L.res) % 16 != 0))
+    return 0;
+  if (L.in_cstride % 8 != 0 || L.in_coff % 8 != 0 || reinterpret_cast<uintptr_t>(L.in) % 16 != 0) return 0;
+  if (L.in_img_stride != static_cast<long long>(L.h) * L.w * L.in_cstride) return 0;
+  const long long pixels = static_cast<long long>(L.batch) * L.h * L.w;
+  if (pixels >= (1ll << 31)) return 0;
+
+  const int mode = pc.ksize == 3 ? 0 : 1;
+  const int taps = pc.ksize * pc.ksize;
+  const int slab = pc.cin_pad % 64 == 0 ? 64 : (pc.cin_pad % 32 == 0 ? 32 : 16);
+  const int slabs = pc.cin_pad / slab;
+  const uint32_t row_bytes = slab * 2;
+  int n_tile = 16;
+  for (int nt = L.out_f32 ? 80 : 128; nt >= 16; nt -= 16)
+    if (cout_pad % nt == 0) { n_tile = nt; break; }
+  const int n_tiles = cout_pad / n_tile;
+  const size_t wbytes = static_cast<size_t>(pc.q_pad) * cout_pad * 16;
+  if (static_cast<size_t>(pc.q_pad) * 8 != static_cast<size_t>(taps) * pc.cin_pad) return 0;
+  const bool resident = n_tiles == 1 && wbytes <= RESIDENT_LIMIT;
+  if (!resident && slab != 64) return 0;
+  const uint32_t bstage_bytes = static_cast<uint32_t>(slab / 8) * n_tile * 16;
+  const uint32_t stage_pitch = n_tile * es + 16;
+  const uint32_t res_pitch = n_tile * 2 + 16;
+  const int sb = resident ? 0 : 4;
+  const size_t fixed_base = OFF_RING_A + (resident ? (wbytes + 1023) / 1024 * 1024 : static_cast<size_t>(sb) * bstage_bytes);
+
+  // ---- choose the tiling: strips x (linear | row-aligned) x mt, cheapest estimated time
+  WinPlan best;
+  const int k16_total = taps * pc.cin_pad / 16;
+  for (int mt = 1; mt <= 2; ++mt) {
+    if (force_mt && mt != force_mt) continue;
+    const int tm = 128 * mt;
+    if (2 * mt * n_tile > 512) continue;
+    const size_t stage_bytes = static_cast<size_t>(tm) * (stage_pitch + (res_mode ? res_pitch : 0));
+    const size_t fixed = fixed_base + stage_bytes;
+    for (int strips = 1; strips <= (mode == 0 ? 8 : 1); ++strips) {
+      for (int aligned = 0; aligned <= (mode == 0 ? 1 : 0); ++aligned) {
+        WinPlan p;
+        p.mt = mt;
+        p.strips = strips;
+        if (mode == 0) {
+          p.tw = (L.w + strips - 1) / strips;
+          p.rw = p.tw + 2;
+          if (p.rw > 256 || (strips > 1 && p.tw < 8)) continue;
+          if (aligned) {
+            const int th = tm / p.rw;
+            if (th < 1) continue;
+            p.tstep = th * p.rw;
+            p.tiles_per_strip = (L.h + th - 1) / th;
+          } else {
+            p.tstep = tm;
+            p.tiles_per_strip = (L.h * p.rw + tm - 1) / tm;
+          }
+          const int xp0max = aligned ? 0 : p.rw - 1;
+          p.bh = (xp0max + p.tstep - 1 + 2 * p.rw + 2) / p.rw + 1;
+          if (p.bh > 256) continue;
+          p.box_bytes = static_cast<uint32_t>(p.bh) * p.rw * row_bytes;
+          const uint32_t reach = static_cast<uint32_t>(xp0max + tm + 2 * p.rw + 2) * row_bytes;  // junk rows stay inside the stage
+          p.patch_bytes = (std::max(p.box_bytes, reach) + 1023) / 1024 * 1024;
+          p.tiles = static_cast<long long>(L.batch) * strips * p.tiles_per_strip;
+        } else {
+          p.tw = L.w; p.rw = L.w; p.tstep = tm; p.tiles_per_strip = 0; p.bh = 0;
+          p.box_bytes = static_cast<uint32_t>(tm) * row_bytes;
+          p.patch_bytes = (p.box_bytes + 1023) / 1024 * 1024;
+          p.tiles = (pixels + tm - 1) / tm;
+        }
+        if (fixed + 2 * static_cast<size_t>(p.patch_bytes) > SMEM_LIMIT) continue;
+        p.sa = static_cast<int>(std::min<size_t>(MAX_RING, (SMEM_LIMIT - fixed) / p.patch_bytes));
+        // enough patches in flight to cover the HBM latency of a tile, no more
+        p.sa = std::min(p.sa, std::max(4, 2 * slabs));
+        p.smem = fixed + static_cast<size_t>(p.sa) * p.patch_bytes;
+        // estimated cycles per tile: tensor pipe vs L2->SM traffic vs epilogue, plus a fixed hand-off cost
+        const double mma = static_cast<double>(mt) * k16_total * std::max(n_tile / 2.0, 16.0);
+        const double l2 = (static_cast<double>(p.box_bytes) * slabs + (resident ? 0.0 : static_cast<double>(wbytes) / n_tiles)) / 48.0;
+        const int groups = (n_tile + 15) / 16;
+        const int active = mt == 2 ? 2 * std::min(2, groups) : std::min(4, groups);
+        const double epi = (static_cast<double>(mt) * groups / active) * 350.0 + 350.0;
+        const double per_tile = std::max(mma, std::max(l2, epi)) + 250.0;
+        p.cost = static_cast<double>(p.tiles) * n_tiles * per_tile;
+        p.ok = true;
+        if (!best.ok || p.cost < best.cost) best = p;
+      }
+    }
+  }
+  if (!best.ok) return 0;
+  if (mode == 0) {
+    // junk rows / columns must not eat the gain: fall back to the im2col kernel for tiny feature maps
+    const double eff = static_cast<double>(pixels) / (static_cast<double>(best.tiles) * 128 * best.mt);
+    if (eff < 0.6) return 0;
+  }
+
+  WinArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.mode = mode; a.h = L.h; a.w = L.w; a.hw = L.h * L.w;
+  a.rw = best.rw; a.tw = best.tw; a.strips = best.strips; a.tstep = best.tstep;
+  a.tiles_per_strip = best.tiles_per_strip; a.tiles_per_img = best.strips * best.tiles_per_strip;
+  a.mt = best.mt; a.tm = 128 * best.mt;
+  a.slab = slab; a.slabs = slabs; a.taps = taps; a.cin_pad = pc.cin_pad;
+  a.resident = resident ? 1 : 0; a.sa = best.sa; a.sb = resident ? 1 : sb;
+  a.patch_bytes = best.patch_bytes; a.box_bytes = best.box_bytes; a.bstage_bytes = bstage_bytes;
+  a.wbytes = static_cast<uint32_t>(wbytes);
+  a.n_tile = n_tile; a.n_tiles = n_tiles; a.cout = pc.cout; a.cout_pad = cout_pad;
+  a.wgt = pc.w; a.bias = pc.bias;
+  a.out = L.out; a.out_img_stride = L.out_img_stride; a.out_cstride = L.out_cstride; a.out_coff = L.out_coff; a.out_f32 = L.out_f32;
+  a.res = L.res; a.res_img_stride = L.res_img_stride; a.res_cstride = L.res_cstride; a.res_coff = L.res_coff; a.res_mode = res_mode;
+  a.act = L.act;
+  a.batch = L.batch; a.batch_dev = L.batch_dev;
+  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n_tile >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(2 * best.mt * n_tile)) cols <<= 1;
+  a.tmem_cols = cols;
+  const uint32_t ring_a_end = OFF_RING_A + static_cast<uint32_t>(best.sa) * best.patch_bytes;
+  a.off_w = ring_a_end;
+  a.off_b = ring_a_end;
+  a.off_stage = ring_a_end + static_cast<uint32_t>(resident ? (wbytes + 1023) / 1024 * 1024 : static_cast<size_t>(sb) * bstage_bytes);
+  a.stage_pitch = stage_pitch;
+  a.res_pitch = res_pitch;
+  a.off_res = a.off_stage + a.tm * stage_pitch;
+  a.inv_rw = 1.0f / static_cast<float>(best.rw);
+  a.flat = (mode == 1 && L.out_img_stride == static_cast<long long>(a.hw) * L.out_cstride &&
+            (!res_mode || L.res_img_stride == static_cast<long long>(a.hw) * L.res_cstride)) ? 1 : 0;
+  const size_t smem = a.off_stage + static_cast<size_t>(a.tm) * (stage_pitch + (res_mode ? res_pitch : 0));
+  if (smem > SMEM_LIMIT) return 0;
+
+  alignas(64) CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  const CUtensorMapSwizzle sw = slab == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (slab == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  void* base = const_cast<__nv_bfloat16*>(L.in) + L.in_coff;
+  CUresult cr;
+  if (mode == 0) {
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(pc.cin_pad), static_cast<cuuint64_t>(L.w), static_cast<cuuint64_t>(L.h),
+                                static_cast<cuuint64_t>(L.batch)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.in_cstride) * 2, static_cast<cuuint64_t>(L.w) * L.in_cstride * 2,
+                                   static_cast<cuuint64_t>(L.h) * L.w * L.in_cstride * 2};
+    const cuuint32_t box[4] = {static_cast<cuuint32_t>(slab), static_cast<cuuint32_t>(best.rw), static_cast<cuuint32_t>(best.bh), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(pc.cin_pad), static_cast<cuuint64_t>(pixels)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(L.in_cstride) * 2};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(slab), static_cast<cuuint32_t>(a.tm)};
+    const cuuint32_t estr[2] = {1, 1};
+    cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (cr != CUDA_SUCCESS) {
+    if (getenv("AICAM_REQUIRE_WIN")) return fail(AICAM_ERR_CUDA, "conv_win: cuTensorMapEncodeTiled failed with " + std::to_string(static_cast<int>(cr)));
+    return 0;
+  }
+
+  WinKernelFn kernel = pick_kernel(slab, taps, best.mt, L.act);
+  {
+    static std::vector<WinKernelFn> configured;  // opt in to > 48 KB of dynamic shared memory once per instantiation
+    if (std::find(configured.begin(), configured.end(), kernel) == configured.end()) {
+      AICAM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM_LIMIT)));
+      configured.push_back(kernel);
+    }
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    AICAM_CUDA_OK(cudaGetDevice(&dev));
+    AICAM_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long total_tiles = best.tiles * n_tiles;
+  dim3 grid(static_cast<unsigned>(std::min<long long>(total_tiles, num_sms)));
+  size_t slot = 0;
+  const bool prof = profile_begin(stream, &slot);
+  kernel<<<grid, WIN_THREADS, smem, stream>>>(a, tmap);
+  if (prof) profile_end(stream, slot);
+  count_launch();
+  const int rc = last_launch("conv_win_kernel");
+  return rc ? rc : 1;
+}
+
+}  // namespace aicam

@@ -19,7 +19,12 @@ SHAPES = [
     ("yolo.4.m 32->32 @80", 64, 80, 80, 32, 32, 3, 1, 1, 1, 0),
     ("yolo.6.m 64->64 @40", 64, 40, 40, 64, 64, 3, 1, 1, 1, 0),
     ("yolo.8.m 128->128 @20", 64, 20, 20, 128, 128, 3, 1, 1, 1, 0),
+    ("yolo.22.cv2 64->64 @80", 64, 80, 80, 64, 64, 3, 1, 1, 0, 0),
     ("yolo.22.cv3 64->80 @80", 64, 80, 80, 64, 80, 3, 1, 1, 0, 0),
+    ("yolo.22.cv3.1 80->80 @80", 64, 80, 80, 80, 80, 3, 1, 1, 0, 0),
+    ("yolo.22.cv3 128->80 @40", 64, 40, 40, 128, 80, 3, 1, 1, 0, 0),
+    ("yolo.15.cv2 1x1 96->64 @80", 64, 80, 80, 96, 64, 1, 1, 1, 0, 0),
+    ("yolo.12.cv1 1x1 384->128 @40", 64, 40, 40, 384, 128, 1, 1, 1, 0, 0),
     ("yolo.22.cv3.2 1x1 80->80 f32 @80", 64, 80, 80, 80, 80, 1, 1, 0, 0, 1),
     ("reid.stem 3->64 @128x64", 1024, 128, 64, 3, 64, 3, 1, 2, 0, 0),
     ("reid.l1 64->64 @64x32", 1024, 64, 32, 64, 64, 3, 1, 2, 2, 0),

@@ -24,6 +24,21 @@ CASES = [
     ("bigk_512", 4, 8, 4, 512, 512, 3, 1, 2, 0, False),
     ("1x1s2_down", 2, 16, 8, 64, 128, 1, 2, 0, 0, False),
     ("yolo_160_c32", 2, 160, 160, 32, 32, 3, 1, 1, 0, False),
+    # window kernel (conv_win.cu): patch rasters with strips, every swizzle width, resident and
+    # streamed weights, one and two accumulators per tile, residual modes, fp32 output
+    ("win_reid_l1", 3, 64, 32, 64, 64, 3, 1, 2, 2, False),
+    ("win_reid_l2", 3, 32, 16, 128, 128, 3, 1, 2, 2, False),
+    ("win_c16_res1", 2, 40, 56, 16, 16, 3, 1, 1, 1, False),
+    ("win_c32_wide", 1, 24, 200, 32, 32, 3, 1, 1, 0, False),
+    ("win_80_80", 2, 20, 20, 80, 80, 3, 1, 1, 0, False),
+    ("win_128_64_stream", 2, 40, 40, 128, 64, 3, 1, 1, 0, False),
+    ("win_256_80_stream", 1, 20, 20, 256, 80, 3, 1, 1, 0, False),
+    ("win_1x1_384_256", 2, 20, 20, 384, 256, 1, 1, 1, 0, False),
+    ("win_1x1_48_32", 2, 40, 40, 48, 32, 1, 1, 1, 0, False),
+    ("win_1x1_f32_80", 2, 40, 40, 80, 80, 1, 1, 0, 0, True),
+    ("win_1x1_64_dfl_f32", 1, 80, 80, 64, 64, 1, 1, 0, 0, True),
+    ("win_odd_13x17", 2, 13, 17, 64, 64, 3, 1, 1, 0, False),
+    ("win_tall_300x9", 1, 300, 9, 32, 48, 3, 1, 2, 0, False),
 ]
 
 
