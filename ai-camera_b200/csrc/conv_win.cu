@@ -57,6 +57,7 @@ struct WinArgs {
   int flat;  // 1x1 mode: output and residual are dense, pixel p of the batch sits at p * cstride
   int mt, tm;
   int slab, slabs, taps, cin_pad;
+  int ksize, stride, pad, wo, slabs_per_tap;  // im2col mode: filter geometry, output width, channel slabs per tap
   int resident, sa, sb;
   uint32_t patch_bytes, box_bytes, bstage_bytes, wbytes;
   int n_tile, n_tiles, cout, cout_pad;
@@ -186,12 +187,13 @@ __device__ __forceinline__ TilePos tile_pos(const WinArgs& a, int mt_idx) {
   return t;
 }
 
-template <int SLAB, int TAPS, int MT, int ACT>
+template <int SLAB, int AMODE, int MT, int ACT>
 __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs a, const __grid_constant__ CUtensorMap tmap) {
   constexpr uint32_t ROW_BYTES = SLAB * 2;
   constexpr int K16S = SLAB / 16;
   constexpr uint32_t LTYPE = SLAB == 64 ? 2u : (SLAB == 32 ? 4u : 6u);
-  constexpr int MODE = TAPS == 9 ? 0 : 1;
+  constexpr int MODE = AMODE;             // 0: 3x3 window patches, 1: flat 1x1, 2: im2col TMA (any 1x1 / 3x3, stride 1 / 2)
+  constexpr int TAPS = AMODE == 0 ? 9 : 1;  // taps that share one A stage (im2col: every (tap, slab) is its own stage)
   constexpr int TM = 128 * MT;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -444,21 +446,52 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       const uint32_t a_ring = sbase + OFF_RING_A;
       uint32_t sa = 0, pa = 1;
       const uint32_t n_sa = a.sa;
+      const long long total_pix = static_cast<long long>(batch) * a.hw;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt_idx = tile / a.n_tiles;
         int n_img = 0, x_start = 0, y_start = 0;
+        int cn[MT], cw[MT], chh[MT];  // im2col: base pixel (image, column, row) of each 128-row sub-tile
+        uint32_t tx_bytes = a.box_bytes;
         if (MODE == 0) {
           const TilePos tp = tile_pos(a, mt_idx);
           n_img = tp.n_img;
           x_start = tp.strip * a.tw - 1;
           y_start = tp.q0 / a.rw - 1;
+        } else if (MODE == 2) {
+          tx_bytes = 0;
+#pragma unroll
+          for (int j = 0; j < MT; ++j) {
+            const long long m = static_cast<long long>(mt_idx) * TM + j * 128;
+            cn[j] = -1;
+            if (m < total_pix) {  // sub-tiles beyond the batch are not loaded (their rows are never stored)
+              cn[j] = static_cast<int>(m / a.hw);
+              const int rem = static_cast<int>(m - static_cast<long long>(cn[j]) * a.hw);
+              const int pr = rem / a.wo;
+              cw[j] = (rem - pr * a.wo) * a.stride - a.pad;
+              chh[j] = pr * a.stride - a.pad;
+              tx_bytes += 128 * ROW_BYTES;
+            }
+          }
         }
+        int tap = 0, sl = 0;  // im2col: virtual slab -> (filter tap, channel slab)
         for (int s = 0; s < a.slabs; ++s) {
           mbar_wait(bar_a_empty + 8 * sa, pa);
           const uint32_t bar = bar_a_full + 8 * sa;
-          mbar_arrive_expect_tx(bar, a.box_bytes);
-          if (MODE == 0) tma_load_4d(a_ring + sa * a.patch_bytes, &tmap, bar, s * SLAB, x_start, y_start, n_img);
-          else tma_load_2d(a_ring + sa * a.patch_bytes, &tmap, bar, s * SLAB, mt_idx * TM);
+          const uint32_t dst = a_ring + sa * a.patch_bytes;
+          mbar_arrive_expect_tx(bar, tx_bytes);
+          if (MODE == 0) {
+            tma_load_4d(dst, &tmap, bar, s * SLAB, x_start, y_start, n_img);
+          } else if (MODE == 1) {
+            tma_load_2d(dst, &tmap, bar, s * SLAB, mt_idx * TM);
+          } else {
+            const int tr = tap / a.ksize, tc = tap - tr * a.ksize;
+#pragma unroll
+            for (int j = 0; j < MT; ++j)
+              if (cn[j] >= 0)
+                tma_load_im2col_4d(dst + j * (128 * ROW_BYTES), &tmap, bar, sl * SLAB, cw[j], chh[j], cn[j],
+                                   static_cast<uint16_t>(tc), static_cast<uint16_t>(tr));
+            if (++sl == a.slabs_per_tap) { sl = 0; ++tap; }
+          }
           if (++sa == n_sa) { sa = 0; pa ^= 1; }
         }
       }
@@ -509,24 +542,26 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
 
 typedef void (*WinKernelFn)(const WinArgs, const CUtensorMap);
 
-template <int SLAB, int TAPS, int MT>
+template <int SLAB, int AMODE, int MT>
 WinKernelFn pick_act(int act) {
-  if (act == 1) return conv_win_kernel<SLAB, TAPS, MT, 1>;
-  if (act == 2) return conv_win_kernel<SLAB, TAPS, MT, 2>;
-  return conv_win_kernel<SLAB, TAPS, MT, 0>;
+  if (act == 1) return conv_win_kernel<SLAB, AMODE, MT, 1>;
+  if (act == 2) return conv_win_kernel<SLAB, AMODE, MT, 2>;
+  return conv_win_kernel<SLAB, AMODE, MT, 0>;
 }
-template <int SLAB, int TAPS>
+template <int SLAB, int AMODE>
 WinKernelFn pick_mt(int mt, int act) {
-  return mt == 2 ? pick_act<SLAB, TAPS, 2>(act) : pick_act<SLAB, TAPS, 1>(act);
+  return mt == 2 ? pick_act<SLAB, AMODE, 2>(act) : pick_act<SLAB, AMODE, 1>(act);
 }
 template <int SLAB>
-WinKernelFn pick_taps(int taps, int mt, int act) {
-  return taps == 9 ? pick_mt<SLAB, 9>(mt, act) : pick_mt<SLAB, 1>(mt, act);
+WinKernelFn pick_mode(int mode, int mt, int act) {
+  if (mode == 0) return pick_mt<SLAB, 0>(mt, act);
+  if (mode == 1) return pick_mt<SLAB, 1>(mt, act);
+  return pick_mt<SLAB, 2>(mt, act);
 }
-WinKernelFn pick_kernel(int slab, int taps, int mt, int act) {
-  if (slab == 64) return pick_taps<64>(taps, mt, act);
-  if (slab == 32) return pick_taps<32>(taps, mt, act);
-  return pick_taps<16>(taps, mt, act);
+WinKernelFn pick_kernel(int slab, int mode, int mt, int act) {
+  if (slab == 64) return pick_mode<64>(mode, mt, act);
+  if (slab == 32) return pick_mode<32>(mode, mt, act);
+  return pick_mode<16>(mode, mt, act);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -543,6 +578,24 @@ EncodeTiledFn get_encode_tiled() {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
       fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
   }
   return fn;
 }
@@ -565,8 +618,9 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   static const bool disabled = getenv("AICAM_NO_WIN") != nullptr;
   static const int force_mt = getenv("AICAM_WIN_MT") ? atoi(getenv("AICAM_WIN_MT")) : 0;
   if (disabled || get_encode_tiled() == nullptr) return 0;
-  if (pc.stride != 1 || (pc.ksize != 1 && pc.ksize != 3) || pc.cin_pad % 16 != 0 || pc.cin_pad == 4) return 0;
-  if (L.ho != L.h || L.wo != L.w || L.batch <= 0) return 0;
+  static const bool no_im2col = getenv("AICAM_WIN_NO_IM2COL") != nullptr;
+  if ((pc.stride != 1 && pc.stride != 2) || (pc.ksize != 1 && pc.ksize != 3) || pc.cin_pad % 16 != 0 || pc.cin_pad == 4) return 0;
+  if (L.batch <= 0 || get_encode_im2col() == nullptr) return 0;
   const int es = L.out_f32 ? 4 : 2;
   const int cout_pad = (pc.cout + 15) / 16 * 16;
   if ((pc.cout * es) % 16 != 0 || (static_cast<long long>(L.out_cstride) * es) % 16 != 0 ||
@@ -579,10 +633,13 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
     return 0;
   if (L.in_cstride % 8 != 0 || L.in_coff % 8 != 0 || reinterpret_cast<uintptr_t>(L.in) % 16 != 0) return 0;
   if (L.in_img_stride != static_cast<long long>(L.h) * L.w * L.in_cstride) return 0;
-  const long long pixels = static_cast<long long>(L.batch) * L.h * L.w;
-  if (pixels >= (1ll << 31)) return 0;
+  const long long pixels = static_cast<long long>(L.batch) * L.ho * L.wo;  // output pixels
+  if (pixels >= (1ll << 31) || static_cast<long long>(L.batch) * L.h * L.w >= (1ll << 31)) return 0;
 
-  const int mode = pc.ksize == 3 ? 0 : 1;
+  // 0: window patches (3x3 stride 1), 1: flat (1x1 stride 1), 2: im2col TMA (stride 2, and 3x3 on maps too
+  // small for the window raster)
+  int mode = pc.stride == 1 ? (pc.ksize == 3 ? 0 : 1) : 2;
+  if (mode == 2 && no_im2col) return 0;
   const int taps = pc.ksize * pc.ksize;
   const int slab = pc.cin_pad % 64 == 0 ? 64 : (pc.cin_pad % 32 == 0 ? 32 : 16);
   const int slabs = pc.cin_pad / slab;
@@ -604,6 +661,8 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   // ---- choose the tiling: strips x (linear | row-aligned) x mt, cheapest estimated time
   WinPlan best;
   const int k16_total = taps * pc.cin_pad / 16;
+plan:
+  best = WinPlan();
   for (int mt = 1; mt <= 2; ++mt) {
     if (force_mt && mt != force_mt) continue;
     const int tm = 128 * mt;
@@ -644,11 +703,12 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
         if (fixed + 2 * static_cast<size_t>(p.patch_bytes) > SMEM_LIMIT) continue;
         p.sa = static_cast<int>(std::min<size_t>(MAX_RING, (SMEM_LIMIT - fixed) / p.patch_bytes));
         // enough patches in flight to cover the HBM latency of a tile, no more
-        p.sa = std::min(p.sa, std::max(4, 2 * slabs));
+        p.sa = std::min(p.sa, mode == 0 ? std::max(4, 2 * slabs) : 6);
         p.smem = fixed + static_cast<size_t>(p.sa) * p.patch_bytes;
         // estimated cycles per tile: tensor pipe vs L2->SM traffic vs epilogue, plus a fixed hand-off cost
         const double mma = static_cast<double>(mt) * k16_total * std::max(n_tile / 2.0, 16.0);
-        const double l2 = (static_cast<double>(p.box_bytes) * slabs + (resident ? 0.0 : static_cast<double>(wbytes) / n_tiles)) / 48.0;
+        const double l2 = (static_cast<double>(p.box_bytes) * slabs * (mode == 2 ? taps : 1) +
+                           (resident ? 0.0 : static_cast<double>(wbytes) / n_tiles)) / 48.0;
         const int groups = (n_tile + 15) / 16;
         const int active = mt == 2 ? 2 * std::min(2, groups) : std::min(4, groups);
         const double epi = (static_cast<double>(mt) * groups / active) * 350.0 + 350.0;
@@ -659,20 +719,25 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
       }
     }
   }
-  if (!best.ok) return 0;
   if (mode == 0) {
-    // junk rows / columns must not eat the gain: fall back to the im2col kernel for tiny feature maps
-    const double eff = static_cast<double>(pixels) / (static_cast<double>(best.tiles) * 128 * best.mt);
-    if (eff < 0.6) return 0;
+    // junk raster positions must not eat the gain: tiny feature maps go through im2col loads instead
+    const double eff = best.ok ? static_cast<double>(pixels) / (static_cast<double>(best.tiles) * 128 * best.mt) : 0.0;
+    if (eff < 0.6) {
+      if (no_im2col) return 0;
+      mode = 2;
+      goto plan;
+    }
   }
+  if (!best.ok) return 0;
 
   WinArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.mode = mode; a.h = L.h; a.w = L.w; a.hw = L.h * L.w;
+  a.mode = mode; a.h = L.h; a.w = L.w; a.hw = L.ho * L.wo;
+  a.ksize = pc.ksize; a.stride = pc.stride; a.pad = pc.ksize / 2; a.wo = L.wo; a.slabs_per_tap = slabs;
   a.rw = best.rw; a.tw = best.tw; a.strips = best.strips; a.tstep = best.tstep;
   a.tiles_per_strip = best.tiles_per_strip; a.tiles_per_img = best.strips * best.tiles_per_strip;
   a.mt = best.mt; a.tm = 128 * best.mt;
-  a.slab = slab; a.slabs = slabs; a.taps = taps; a.cin_pad = pc.cin_pad;
+  a.slab = slab; a.slabs = mode == 2 ? taps * slabs : slabs; a.taps = taps; a.cin_pad = pc.cin_pad;
   a.resident = resident ? 1 : 0; a.sa = best.sa; a.sb = resident ? 1 : sb;
   a.patch_bytes = best.patch_bytes; a.box_bytes = best.box_bytes; a.bstage_bytes = bstage_bytes;
   a.wbytes = static_cast<uint32_t>(wbytes);
@@ -694,7 +759,7 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   a.res_pitch = res_pitch;
   a.off_res = a.off_stage + a.tm * stage_pitch;
   a.inv_rw = 1.0f / static_cast<float>(best.rw);
-  a.flat = (mode == 1 && L.out_img_stride == static_cast<long long>(a.hw) * L.out_cstride &&
+  a.flat = (mode != 0 && L.out_img_stride == static_cast<long long>(a.hw) * L.out_cstride &&
             (!res_mode || L.res_img_stride == static_cast<long long>(a.hw) * L.res_cstride)) ? 1 : 0;
   const size_t smem = a.off_stage + static_cast<size_t>(a.tm) * (stage_pitch + (res_mode ? res_pitch : 0));
   if (smem > SMEM_LIMIT) return 0;
@@ -713,6 +778,18 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (mode == 2) {
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(pc.cin_pad), static_cast<cuuint64_t>(L.w), static_cast<cuuint64_t>(L.h),
+                                static_cast<cuuint64_t>(L.batch)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.in_cstride) * 2, static_cast<cuuint64_t>(L.w) * L.in_cstride * 2,
+                                   static_cast<cuuint64_t>(L.h) * L.w * L.in_cstride * 2};
+    const int pad = pc.ksize / 2;
+    const int lower[2] = {-pad, -pad};
+    const int upper[2] = {pad - (pc.ksize - 1), pad - (pc.ksize - 1)};
+    const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(pc.stride), static_cast<cuuint32_t>(pc.stride), 1};
+    cr = get_encode_im2col()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, lower, upper, static_cast<cuuint32_t>(slab),
+                             128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(pc.cin_pad), static_cast<cuuint64_t>(pixels)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(L.in_cstride) * 2};
@@ -726,7 +803,7 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
     return 0;
   }
 
-  WinKernelFn kernel = pick_kernel(slab, taps, best.mt, L.act);
+  WinKernelFn kernel = pick_kernel(slab, mode, best.mt, L.act);
   {
     static std::vector<WinKernelFn> configured;  // opt in to > 48 KB of dynamic shared memory once per instantiation
     if (std::find(configured.begin(), configured.end(), kernel) == configured.end()) {

@@ -39,6 +39,13 @@ CASES = [
     ("win_1x1_64_dfl_f32", 1, 80, 80, 64, 64, 1, 1, 0, 0, True),
     ("win_odd_13x17", 2, 13, 17, 64, 64, 3, 1, 1, 0, False),
     ("win_tall_300x9", 1, 300, 9, 32, 48, 3, 1, 2, 0, False),
+    # im2col-TMA mode of the same kernel: stride 2, and 3x3 on maps too small for the window raster
+    ("i2c_s2_64_128", 5, 64, 32, 64, 128, 3, 2, 2, 0, False),
+    ("i2c_s2_odd_15x9", 3, 15, 9, 32, 32, 3, 2, 1, 0, False),
+    ("i2c_s2_16_32_320", 1, 320, 320, 16, 32, 3, 2, 1, 0, False),
+    ("i2c_1x1s2_256_512", 7, 16, 8, 256, 512, 1, 2, 0, 0, False),
+    ("i2c_deep_256_res2", 9, 16, 8, 256, 256, 3, 1, 2, 2, False),
+    ("i2c_deep_512_res2", 13, 8, 4, 512, 512, 3, 1, 2, 2, False),
 ]
 
 
