@@ -18,6 +18,7 @@
 
 #include "conv_tc.cuh"
 #include "layers.cuh"
+#include "stem_pool.cuh"
 
 namespace aicam {
 
@@ -41,7 +42,7 @@ struct View {
 };
 
 struct Op {
-  enum Type { CONV, MAXPOOL, UPSAMPLE, AVGL2 } type;
+  enum Type { CONV, MAXPOOL, UPSAMPLE, AVGL2, STEMPOOL } type;
   int conv = -1;
   View in, out, res;
   int h = 0, w = 0, c = 0;  // input spatial size / channels moved (pool, upsample)
@@ -57,6 +58,8 @@ struct aicam_engine {
   int kind = 0, device = 0, max_batch = 0;
   uint32_t params[8] = {0};
   std::vector<aicam::PackedConv> convs;
+  aicam::StemPool stem;            // reid: fused conv.0 + ReLU + maxpool
+  int stem_in8 = -1;               // reid: NHWC8 copy of the input crops
   std::map<std::string, int> conv_by_name;
   std::vector<aicam::Buffer> buffers;
   std::vector<aicam::Op> ops;
@@ -215,11 +218,24 @@ struct Builder {
   void build_reid() {
     const int H = AICAM_REID_H, W = AICAM_REID_W;
     e->in_h = H; e->in_w = W;
-    const int s0 = buf(H, W, 64);
-    conv("conv.0", V(-1), H, W, V(s0), 3, 64, 3, 1, 2);
     int h = H / 2, w = W / 2, c = 64;
     int cur = buf(h, w, c);
-    pool(V(s0), V(cur), H, W, 64, 3, 2);
+    static const bool unfused = getenv("AICAM_NO_STEM_FUSION") != nullptr;
+    auto wi = tensors->find("conv.0.weight");
+    auto bi = tensors->find("conv.0.bias");
+    if (!unfused && wi != tensors->end() && bi != tensors->end() && wi->second.dims.size() == 4 && wi->second.dims[0] == 64 &&
+        wi->second.dims[1] == 3 && wi->second.dims[2] == 3 && static_cast<int>(bi->second.count) == 64) {
+      // fused stem: crops NHWC4 -> NHWC8 -> conv3x3 + ReLU + maxpool 3x3 s2 in one kernel (stem_pool.cu)
+      if (int rc = pack_stem_pool(wi->second.data, bi->second.data, 64, 3, &e->stem)) { err = rc; return; }
+      e->stem_in8 = buf(H, W, 8);
+      Op op; op.type = Op::STEMPOOL; op.in = V(-1); op.out = V(cur); op.h = H; op.w = W;
+      e->ops.push_back(op);
+      e->macs_per_item += static_cast<double>(H) * W * 64 * 3 * 9;
+    } else {
+      const int s0 = buf(H, W, 64);
+      conv("conv.0", V(-1), H, W, V(s0), 3, 64, 3, 1, 2);
+      pool(V(s0), V(cur), H, W, 64, 3, 2);
+    }
     const int widths[4] = {64, 128, 256, 512};
     for (int li = 0; li < 4; ++li) {
       const int cout = widths[li];
@@ -300,6 +316,13 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
         rc = launch_upsample2x(ip, is, ic, op.in.coff, batch, op.h, op.w, op.c, const_cast<__nv_bfloat16*>(op_), os,
                                oc, op.out.coff, stream);
         break;
+      case Op::STEMPOOL: {
+        geom(op.out, 0, &op_, &os, &oc);
+        __nv_bfloat16* in8 = e->buffers[e->stem_in8].ptr;
+        rc = launch_nhwc4_to_nhwc8(ip, batch, op.h, op.w, in8, n_dev, stream);
+        if (!rc) rc = launch_stem_pool(e->stem, in8, batch, op.h, op.w, n_dev, const_cast<__nv_bfloat16*>(op_), stream);
+        break;
+      }
       case Op::AVGL2:
         rc = launch_avgpool_l2norm(ip, batch, op.h * op.w, op.c, static_cast<float*>(output), stream, n_dev);
         break;
@@ -383,6 +406,7 @@ void aicam_engine_destroy(aicam_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   for (auto& c : e->convs) free_packed_conv(&c);
+  free_stem_pool(&e->stem);
   for (auto& b : e->buffers)
     if (b.ptr) cudaFree(b.ptr);
   delete e;
@@ -474,6 +498,29 @@ int aicam_conv2d(const aicam_conv_desc* d, const void* in, const float* w, const
   free_packed_conv(&pc);
   if (rc) return rc;
   if (se != cudaSuccess) return fail(AICAM_ERR_CUDA, std::string("conv2d: ") + cudaGetErrorString(se));
+  return AICAM_OK;
+}
+
+int aicam_reid_stem_pool(const void* in_nhwc4, int n, int h, int w, const float* weights_oihw, const float* bias, void* out,
+                         void* stream) {
+  if (!in_nhwc4 || !weights_oihw || !out || n <= 0 || h <= 0 || w <= 0)
+    return fail(AICAM_ERR_INVALID_ARG, "reid_stem_pool: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StemPool sp;
+  if (int rc = pack_stem_pool(weights_oihw, bias, 64, 3, &sp)) return rc;
+  __nv_bfloat16* in8 = nullptr;
+  cudaError_t ce = cudaMalloc(&in8, static_cast<size_t>(n) * h * w * 16);
+  if (ce != cudaSuccess) {
+    free_stem_pool(&sp);
+    return fail(AICAM_ERR_CUDA, std::string("reid_stem_pool: ") + cudaGetErrorString(ce));
+  }
+  int rc = launch_nhwc4_to_nhwc8(static_cast<const __nv_bfloat16*>(in_nhwc4), n, h, w, in8, nullptr, st);
+  if (!rc) rc = launch_stem_pool(sp, in8, n, h, w, nullptr, static_cast<__nv_bfloat16*>(out), st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(in8);
+  free_stem_pool(&sp);
+  if (rc) return rc;
+  if (se != cudaSuccess) return fail(AICAM_ERR_CUDA, std::string("reid_stem_pool: ") + cudaGetErrorString(se));
   return AICAM_OK;
 }
 

@@ -105,6 +105,12 @@ int aicam_conv2d(const aicam_conv_desc* d, const void* in_nhwc, const float* wei
 /* Micro-benchmark of the same operator on device-resident random data: `iters` launches
  * bracketed by CUDA events on `stream`; returns the mean kernel time in milliseconds. */
 int aicam_conv2d_bench(const aicam_conv_desc* d, int iters, double* mean_ms, void* stream);
+/* The fused ReID stem on its own (test entry): Conv3x3(3->64, s1, p1) + bias + ReLU + MaxPool(3, s2, p1),
+ * the first two layers of the ReID engine (reid_model.py:115).
+ *   in_nhwc4 : bf16 [n][h][w][4] (h, w even)   weights_oihw : fp32 host [64][3][3][3]   bias : fp32 host [64]
+ *   out      : bf16 [n][h/2][w/2][64] */
+int aicam_reid_stem_pool(const void* in_nhwc4, int n, int h, int w, const float* weights_oihw,
+                         const float* bias, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Preprocessing: replaces image_processing.letterbox + preprocess_yolo_input

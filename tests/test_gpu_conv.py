@@ -82,3 +82,30 @@ def test_conv_matches_torch(case):
     assert not bad.any(), "%s: %d/%d elements off, max abs err %.4g at %s (got %.5g want %.5g)" % (
         name, bad.sum(), bad.size, err.max(), np.unravel_index(err.argmax(), err.shape),
         got.flat[err.argmax()], want.flat[err.argmax()])
+
+
+@pytest.mark.parametrize("shape", [(3, 128, 64), (2, 24, 40), (5, 6, 2)], ids=["reid_128x64", "odd_tiles_24x40", "tiny_6x2"])
+def test_fused_stem_pool_matches_torch(shape):
+    """stem_pool.cu: conv3x3(3->64) + bias + ReLU + maxpool(3, s2, p1) fused, vs torch fp32 on the same
+    bf16-rounded operands.  The conv output is rounded to bf16 before pooling; max commutes with rounding."""
+    import ctypes as C
+    import gpu_util as G
+    from ai_camera_b200._lib import check, ptr
+    n, H, W = shape
+    rng = np.random.default_rng(n * 1000 + H)
+    x = G.bf16_round_np(rng.normal(0, 1, (n, H, W, 3)))
+    xp = np.zeros((n, H, W, 4), np.float32)
+    xp[..., :3] = x
+    w = G.bf16_round_np(rng.normal(0, 1.0 / np.sqrt(27), (64, 3, 3, 3)))
+    b = rng.normal(0, 0.5, 64).astype(np.float32)
+    xd = torch.from_numpy(xp).to(G.DEV).to(torch.bfloat16)
+    out = torch.empty((n, H // 2, W // 2, 64), dtype=torch.bfloat16, device=G.DEV)
+    check(G.lib().aicam_reid_stem_pool(ptr(xd), n, H, W, ptr(np.ascontiguousarray(w)), ptr(b), ptr(out), None))
+    got = out.float().cpu().numpy()
+    y = F.relu(F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(w), torch.from_numpy(b), padding=1))
+    want = F.max_pool2d(y, 3, 2, 1).permute(0, 2, 3, 1).numpy()
+    assert got.shape == want.shape
+    err = np.abs(got - want)
+    bad = err > 2e-2 + 1e-2 * np.abs(want)
+    assert not bad.any(), "%d/%d elements off, max abs err %.4g at %s" % (
+        bad.sum(), bad.size, err.max(), np.unravel_index(err.argmax(), err.shape))
