@@ -61,6 +61,8 @@ SIGNATURES = {
     "aicam_engine_set_bias": (_I, [_P, C.c_char_p, _P, _I]),
     "aicam_engine_get_bias": (_I, [_P, C.c_char_p, _P, _I]),
     "aicam_yolo_forward": (_I, [_P, _P, _I, _P, _P]),
+    "aicam_yolo_forward_s2d": (_I, [_P, _P, _I, _P, _P]),
+    "aicam_engine_accepts_s2d": (_I, [_P]),
     "aicam_reid_forward": (_I, [_P, _P, _I, _P, _P, _P]),
     "aicam_nchw_to_nhwc4": (_I, [_P, _I, _I, _I, _P, _P]),
     "aicam_conv2d": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),

@@ -653,6 +653,38 @@ int pack_conv_weights(const float* w, const float* bias, int cout, int cin, int 
   return AICAM_OK;
 }
 
+int pack_conv_weights_s2d(const float* w, const float* bias, int cout, int cin, int c0_pad, PackedConv* out) {
+  if (cout <= 0 || cin <= 0 || cin > c0_pad || (c0_pad != 4 && c0_pad != 16))
+    return fail(AICAM_ERR_INVALID_ARG, "pack_conv_weights_s2d: unsupported shape");
+  // output (oy, ox) reads input (2 oy - 1 + ky, 2 ox - 1 + kx): block row oy - 1 + ty, row parity sy with
+  // ky = 0 -> (ty 0, sy 1), ky = 1 -> (ty 1, sy 0), ky = 2 -> (ty 1, sy 1); same along x
+  const int cin_pad = 4 * c0_pad;
+  const int k_total = 4 * cin_pad;
+  const int q = k_total / 8;
+  const int cout_pad = (cout + 15) / 16 * 16;
+  std::vector<uint16_t> packed(static_cast<size_t>(q) * cout_pad * 8, 0);
+  const int t_of[3] = {0, 1, 1}, s_of[3] = {1, 0, 1};
+  for (int o = 0; o < cout; ++o)
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx)
+        for (int c = 0; c < cin; ++c) {
+          const int tap2 = t_of[ky] * 2 + t_of[kx];
+          const int k = tap2 * cin_pad + (s_of[ky] * 2 + s_of[kx]) * c0_pad + c;
+          const float v = w[(static_cast<size_t>(o) * cin + c) * 9 + ky * 3 + kx];
+          packed[(static_cast<size_t>(k / 8) * cout_pad + o) * 8 + (k % 8)] = f32_to_bf16_bits(v);
+        }
+  std::vector<float> b(cout_pad, 0.0f);
+  for (int o = 0; o < cout; ++o) b[o] = bias ? bias[o] : 0.0f;
+  PackedConv p;
+  p.cin = cin; p.cin_pad = cin_pad; p.cout = cout; p.ksize = 2; p.stride = 1; p.q = q; p.q_pad = q; p.s2d_c0 = c0_pad;
+  AICAM_CUDA_OK(cudaMalloc(&p.w, packed.size() * 2));
+  AICAM_CUDA_OK(cudaMalloc(&p.bias, b.size() * 4));
+  AICAM_CUDA_OK(cudaMemcpy(p.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+  AICAM_CUDA_OK(cudaMemcpy(p.bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  *out = p;
+  return AICAM_OK;
+}
+
 void free_packed_conv(PackedConv* p) {
   if (p->w) cudaFree(p->w);
   if (p->bias) cudaFree(p->bias);
@@ -661,6 +693,12 @@ void free_packed_conv(PackedConv* p) {
 }
 
 int launch_conv(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream) {
+  if (pc.s2d_c0) {  // space-to-depth layers exist only on the window kernel
+    if (L.batch <= 0) return AICAM_OK;
+    const int wrc = try_launch_conv_win(pc, L, stream);
+    if (wrc < 0) return wrc;
+    return wrc == 1 ? AICAM_OK : fail(AICAM_ERR_UNSUPPORTED, "launch_conv: space-to-depth layer not eligible for the window kernel");
+  }
   ConvKernelArgs a;
   a.in = L.in; a.in_img_stride = L.in_img_stride; a.in_cstride = L.in_cstride; a.in_coff = L.in_coff;
   a.h = L.h; a.w = L.w; a.ho = L.ho; a.wo = L.wo; a.howo = L.ho * L.wo;
@@ -714,6 +752,7 @@ int launch_conv(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream) 
     const int wrc = try_launch_conv_win(pc, L, stream);
     if (wrc < 0) return wrc;
     if (wrc == 1) return AICAM_OK;
+    if (L.out_s2d) return fail(AICAM_ERR_UNSUPPORTED, "launch_conv: space-to-depth output needs the window kernel");
   }
   // TMA im2col path: whole 128-pixel x slab-channel tiles per instruction (all layers but the stems)
   alignas(64) CUtensorMap tmap;

@@ -14,6 +14,7 @@ struct PackedConv {
   int cin_pad = 0;    // 4 (stem: 3 -> 4) or a multiple of 8
   int cout = 0, ksize = 1, stride = 1;
   int q = 0, q_pad = 0;
+  int s2d_c0 = 0;  // != 0: a 3x3 stride-2 layer packed as a 2x2 window over 2x2 input blocks of s2d_c0 channels (conv_win.cu)
 };
 
 struct ConvLaunch {
@@ -32,12 +33,16 @@ struct ConvLaunch {
   int res_mode;  // 0 none, 1 act(conv)+res, 2 act(conv+res)
   int act;       // 0 none, 1 SiLU, 2 ReLU
   const int* batch_dev = nullptr;  // optional device-side image count (<= batch)
+  int out_s2d = 0;                 // store the output space-to-depth: [ho/2][wo/2][2x2 sub-pixel][out_cstride] (window kernel only)
   long long* trace = nullptr;      // debug: clock64 stamps of CTA 0
 };
 
 // host: pack OIHW fp32 weights (host) into the device layout above
 int pack_conv_weights(const float* w_oihw, const float* bias, int cout, int cin, int ksize, int stride,
                       PackedConv* out);
+// 3x3 / stride 2 / pad 1 layer re-expressed over its space-to-depth input [h/2][w/2][2x2 sub-pixel][c0_pad]:
+// a 2x2 stride-1 window (pad 1 top / left) with K = tap2 * (4 c0_pad) + (sy * 2 + sx) * c0_pad + c; cin <= c0_pad in {4, 16}
+int pack_conv_weights_s2d(const float* w_oihw, const float* bias, int cout, int cin, int c0_pad, PackedConv* out);
 void free_packed_conv(PackedConv* p);
 int launch_conv(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream);
 

@@ -54,6 +54,7 @@ struct WinArgs {
   int h, w, hw;
   int rw, tw, strips, tstep, tiles_per_strip, tiles_per_img;
   float inv_rw;
+  int out_s2d;  // window modes: the output is stored space-to-depth: [h/2][w/2][2x2 sub-pixel][out_cstride]
   int flat;  // 1x1 mode: output and residual are dense, pixel p of the batch sits at p * cstride
   int mt, tm;
   int slab, slabs, taps, cin_pad;
@@ -192,8 +193,13 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
   constexpr uint32_t ROW_BYTES = SLAB * 2;
   constexpr int K16S = SLAB / 16;
   constexpr uint32_t LTYPE = SLAB == 64 ? 2u : (SLAB == 32 ? 4u : 6u);
-  constexpr int MODE = AMODE;             // 0: 3x3 window patches, 1: flat 1x1, 2: im2col TMA (any 1x1 / 3x3, stride 1 / 2)
-  constexpr int TAPS = AMODE == 0 ? 9 : 1;  // taps that share one A stage (im2col: every (tap, slab) is its own stage)
+  // 0: 3x3 window patches, 1: flat 1x1, 2: im2col TMA (any 1x1 / 3x3, stride 1 / 2),
+  // 3: 2x2 window, pad 1 on the top / left only: a 3x3 stride-2 layer over its space-to-depth input
+  //    (2x2 pixel blocks stored as one 4C-channel pixel; weights re-packed by pack_conv_weights_s2d)
+  constexpr bool WINDOW = AMODE == 0 || AMODE == 3;
+  constexpr int MODE = WINDOW ? 0 : AMODE;
+  constexpr int KW = AMODE == 3 ? 2 : 3;                        // window width in raster positions
+  constexpr int TAPS = AMODE == 0 ? 9 : (AMODE == 3 ? 4 : 1);   // taps that share one A stage
   constexpr int TM = 128 * MT;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
         const int x = tp.strip * a.tw + xp;
         valid = rel < a.tstep && y < a.h && xp < a.tw && x < a.w;
         img = tp.n_img;
-        pix = y * a.w + x;
+        pix = a.out_s2d ? (((y >> 1) * (a.w >> 1) + (x >> 1)) << 2) + ((y & 1) << 1) + (x & 1) : y * a.w + x;
       } else {
         const long long p = static_cast<long long>(mt_idx) * TM + my_j * 128 + row;
         valid = p < total_pix;
@@ -410,7 +416,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
           const uint32_t w_tap = static_cast<uint32_t>(a.cin_pad >> 3) * lbo;
 #pragma unroll
           for (int t = 0; t < TAPS; ++t) {
-            const int dy = t / 3, dx = t - dy * 3;  // TAPS == 1: (0, 0)
+            const int dy = t / KW, dx = t - dy * KW;  // TAPS == 1: (0, 0)
             const uint32_t a_lo = a_lo0 + dy * rw_units + dx * (ROW_BYTES >> 4);
             uint32_t b_lo;
             if (a.resident) {
@@ -556,6 +562,7 @@ template <int SLAB>
 WinKernelFn pick_mode(int mode, int mt, int act) {
   if (mode == 0) return pick_mt<SLAB, 0>(mt, act);
   if (mode == 1) return pick_mt<SLAB, 1>(mt, act);
+  if (mode == 3) return pick_mt<SLAB, 3>(mt, act);
   return pick_mt<SLAB, 2>(mt, act);
 }
 WinKernelFn pick_kernel(int slab, int mode, int mt, int act) {
@@ -619,7 +626,15 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   static const int force_mt = getenv("AICAM_WIN_MT") ? atoi(getenv("AICAM_WIN_MT")) : 0;
   if (disabled || get_encode_tiled() == nullptr) return 0;
   static const bool no_im2col = getenv("AICAM_WIN_NO_IM2COL") != nullptr;
-  if ((pc.stride != 1 && pc.stride != 2) || (pc.ksize != 1 && pc.ksize != 3) || pc.cin_pad % 16 != 0 || pc.cin_pad == 4) return 0;
+  const bool s2d = pc.s2d_c0 != 0;  // 3x3 stride-2 layer packed as a 2x2 window over 2x2 input blocks
+  if (s2d) {
+    // the launch describes the space-to-depth tensor: [batch][h][w][4 c0] dense, output h x w
+    if (pc.ksize != 2 || pc.stride != 1 || pc.cin_pad != 4 * pc.s2d_c0 || (pc.cin_pad != 16 && pc.cin_pad != 64) ||
+        L.in_cstride != pc.cin_pad || L.in_coff != 0 || L.ho != L.h || L.wo != L.w)
+      return fail(AICAM_ERR_INVALID_ARG, "conv_win: space-to-depth layer with an unsupported geometry");
+  } else if ((pc.stride != 1 && pc.stride != 2) || (pc.ksize != 1 && pc.ksize != 3) || pc.cin_pad % 16 != 0 || pc.cin_pad == 4) {
+    return 0;
+  }
   if (L.batch <= 0 || get_encode_im2col() == nullptr) return 0;
   const int es = L.out_f32 ? 4 : 2;
   const int cout_pad = (pc.cout + 15) / 16 * 16;
@@ -638,8 +653,12 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
 
   // 0: window patches (3x3 stride 1), 1: flat (1x1 stride 1), 2: im2col TMA (stride 2, and 3x3 on maps too
   // small for the window raster)
-  int mode = pc.stride == 1 ? (pc.ksize == 3 ? 0 : 1) : 2;
+  int mode = s2d ? 3 : (pc.stride == 1 ? (pc.ksize == 3 ? 0 : 1) : 2);
   if (mode == 2 && no_im2col) return 0;
+  if (L.out_s2d && mode != 0 && mode != 3) return 0;  // the caller reports the unsupported combination
+  bool window = mode == 0 || mode == 3;
+  const int kw1 = mode == 3 ? 1 : 2;  // window extent - 1 (both axes)
+  const int win_h = L.h, win_w = L.w;  // size of the raster the window slides over
   const int taps = pc.ksize * pc.ksize;
   const int slab = pc.cin_pad % 64 == 0 ? 64 : (pc.cin_pad % 32 == 0 ? 32 : 16);
   const int slabs = pc.cin_pad / slab;
@@ -663,35 +682,36 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   const int k16_total = taps * pc.cin_pad / 16;
 plan:
   best = WinPlan();
+  window = mode == 0 || mode == 3;
   for (int mt = 1; mt <= 2; ++mt) {
     if (force_mt && mt != force_mt) continue;
     const int tm = 128 * mt;
     if (2 * mt * n_tile > 512) continue;
     const size_t stage_bytes = static_cast<size_t>(tm) * (stage_pitch + (res_mode ? res_pitch : 0));
     const size_t fixed = fixed_base + stage_bytes;
-    for (int strips = 1; strips <= (mode == 0 ? 8 : 1); ++strips) {
-      for (int aligned = 0; aligned <= (mode == 0 ? 1 : 0); ++aligned) {
+    for (int strips = 1; strips <= (window ? 8 : 1); ++strips) {
+      for (int aligned = 0; aligned <= (window ? 1 : 0); ++aligned) {
         WinPlan p;
         p.mt = mt;
         p.strips = strips;
-        if (mode == 0) {
-          p.tw = (L.w + strips - 1) / strips;
-          p.rw = p.tw + 2;
+        if (window) {
+          p.tw = (win_w + strips - 1) / strips;
+          p.rw = p.tw + kw1;
           if (p.rw > 256 || (strips > 1 && p.tw < 8)) continue;
           if (aligned) {
             const int th = tm / p.rw;
             if (th < 1) continue;
             p.tstep = th * p.rw;
-            p.tiles_per_strip = (L.h + th - 1) / th;
+            p.tiles_per_strip = (win_h + th - 1) / th;
           } else {
             p.tstep = tm;
-            p.tiles_per_strip = (L.h * p.rw + tm - 1) / tm;
+            p.tiles_per_strip = (win_h * p.rw + tm - 1) / tm;
           }
           const int xp0max = aligned ? 0 : p.rw - 1;
-          p.bh = (xp0max + p.tstep - 1 + 2 * p.rw + 2) / p.rw + 1;
+          p.bh = (xp0max + p.tstep - 1 + kw1 * p.rw + kw1) / p.rw + 1;
           if (p.bh > 256) continue;
           p.box_bytes = static_cast<uint32_t>(p.bh) * p.rw * row_bytes;
-          const uint32_t reach = static_cast<uint32_t>(xp0max + tm + 2 * p.rw + 2) * row_bytes;  // junk rows stay inside the stage
+          const uint32_t reach = static_cast<uint32_t>(xp0max + tm + kw1 * p.rw + kw1 + 1) * row_bytes;  // junk rows stay inside the stage
           p.patch_bytes = (std::max(p.box_bytes, reach) + 1023) / 1024 * 1024;
           p.tiles = static_cast<long long>(L.batch) * strips * p.tiles_per_strip;
         } else {
@@ -703,7 +723,7 @@ plan:
         if (fixed + 2 * static_cast<size_t>(p.patch_bytes) > SMEM_LIMIT) continue;
         p.sa = static_cast<int>(std::min<size_t>(MAX_RING, (SMEM_LIMIT - fixed) / p.patch_bytes));
         // enough patches in flight to cover the HBM latency of a tile, no more
-        p.sa = std::min(p.sa, mode == 0 ? std::max(4, 2 * slabs) : 6);
+        p.sa = std::min(p.sa, window ? std::max(4, 2 * slabs) : 6);
         p.smem = fixed + static_cast<size_t>(p.sa) * p.patch_bytes;
         // estimated cycles per tile: tensor pipe vs L2->SM traffic vs epilogue, plus a fixed hand-off cost
         const double mma = static_cast<double>(mt) * k16_total * std::max(n_tile / 2.0, 16.0);
@@ -723,7 +743,7 @@ plan:
     // junk raster positions must not eat the gain: tiny feature maps go through im2col loads instead
     const double eff = best.ok ? static_cast<double>(pixels) / (static_cast<double>(best.tiles) * 128 * best.mt) : 0.0;
     if (eff < 0.6) {
-      if (no_im2col) return 0;
+      if (no_im2col || L.out_s2d) return 0;
       mode = 2;
       goto plan;
     }
@@ -732,7 +752,7 @@ plan:
 
   WinArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.mode = mode; a.h = L.h; a.w = L.w; a.hw = L.ho * L.wo;
+  a.mode = mode; a.h = win_h; a.w = win_w; a.hw = L.ho * L.wo;
   a.ksize = pc.ksize; a.stride = pc.stride; a.pad = pc.ksize / 2; a.wo = L.wo; a.slabs_per_tap = slabs;
   a.rw = best.rw; a.tw = best.tw; a.strips = best.strips; a.tstep = best.tstep;
   a.tiles_per_strip = best.tiles_per_strip; a.tiles_per_img = best.strips * best.tiles_per_strip;
@@ -746,6 +766,7 @@ plan:
   a.out = L.out; a.out_img_stride = L.out_img_stride; a.out_cstride = L.out_cstride; a.out_coff = L.out_coff; a.out_f32 = L.out_f32;
   a.res = L.res; a.res_img_stride = L.res_img_stride; a.res_cstride = L.res_cstride; a.res_coff = L.res_coff; a.res_mode = res_mode;
   a.act = L.act;
+  a.out_s2d = (window && L.out_s2d) ? 1 : 0;
   a.batch = L.batch; a.batch_dev = L.batch_dev;
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n_tile >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
   uint32_t cols = 32;
@@ -769,7 +790,7 @@ plan:
   const CUtensorMapSwizzle sw = slab == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (slab == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   void* base = const_cast<__nv_bfloat16*>(L.in) + L.in_coff;
   CUresult cr;
-  if (mode == 0) {
+  if (window) {
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(pc.cin_pad), static_cast<cuuint64_t>(L.w), static_cast<cuuint64_t>(L.h),
                                 static_cast<cuuint64_t>(L.batch)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.in_cstride) * 2, static_cast<cuuint64_t>(L.w) * L.in_cstride * 2,

@@ -48,6 +48,8 @@ struct Op {
   int h = 0, w = 0, c = 0;  // input spatial size / channels moved (pool, upsample)
   int k = 0, stride = 1;
   int act = 0, res_mode = 0, out_f32 = 0;
+  int s2d_c0 = 0;   // conv reads its input space-to-depth (h, w are the space-to-depth sizes), c0 channels per pixel
+  int out_s2d = 0;  // conv stores its output space-to-depth (for the next stride-2 layer)
 };
 
 }  // namespace
@@ -60,6 +62,7 @@ struct aicam_engine {
   std::vector<aicam::PackedConv> convs;
   aicam::StemPool stem;            // reid: fused conv.0 + ReLU + maxpool
   int stem_in8 = -1;               // reid: NHWC8 copy of the input crops
+  int s2d_in = -1;                 // yolov8: space-to-depth copy of an NHWC4 input (callers may pass it directly)
   std::map<std::string, int> conv_by_name;
   std::vector<aicam::Buffer> buffers;
   std::vector<aicam::Op> ops;
@@ -75,6 +78,15 @@ struct aicam_engine {
 namespace aicam {
 
 namespace {
+
+// channels per pixel of the dense input when a layer qualifies for the space-to-depth window path, else 0
+int s2d_channels(int k, int s, int cin, int in_cstride) {
+  static const bool off = getenv("AICAM_NO_S2D") != nullptr;
+  if (off || k != 3 || s != 2) return 0;
+  if (cin <= 4 && in_cstride == 4) return 4;
+  if (cin == 16 && in_cstride == 16) return 16;
+  return 0;
+}
 
 struct Builder {
   aicam_engine* e;
@@ -118,6 +130,32 @@ struct Builder {
     e->ops.push_back(op);
     const int ho = (h + 2 * (k / 2) - k) / s + 1, wo = (w + 2 * (k / 2) - k) / s + 1;
     e->macs_per_item += static_cast<double>(ho) * wo * cout * cin * k * k;
+    return AICAM_OK;
+  }
+
+  // 3x3 stride-2 layer over a space-to-depth input of (h2 x w2) 2x2 blocks with c0 channels per pixel
+  int conv_s2d(const std::string& name, View in, int h2, int w2, View out, int cin, int cout, int c0, int act, int out_s2d) {
+    if (err) return err;
+    auto wi = tensors->find(name + ".weight");
+    auto bi = tensors->find(name + ".bias");
+    if (wi == tensors->end() || bi == tensors->end())
+      return err = fail(AICAM_ERR_IO, "engine: blob has no tensor " + name + ".weight/.bias");
+    const BlobTensor& wt = wi->second;
+    if (wt.dims.size() != 4 || wt.dims[0] != cout || wt.dims[1] != cin || wt.dims[2] != 3 || wt.dims[3] != 3 ||
+        static_cast<int>(bi->second.count) != cout)
+      return err = fail(AICAM_ERR_IO, "engine: tensor " + name + " has an unexpected shape");
+    PackedConv pc;
+    if (int rc = pack_conv_weights_s2d(wt.data, bi->second.data, cout, cin, c0, &pc)) return err = rc;
+    e->convs.push_back(pc);
+    e->conv_by_name[name] = static_cast<int>(e->convs.size()) - 1;
+    Op op;
+    op.type = Op::CONV;
+    op.conv = static_cast<int>(e->convs.size()) - 1;
+    op.in = in; op.out = out;
+    op.h = h2; op.w = w2; op.k = 2; op.stride = 1;
+    op.act = act; op.s2d_c0 = c0; op.out_s2d = out_s2d;
+    e->ops.push_back(op);
+    e->macs_per_item += static_cast<double>(h2) * w2 * cout * cin * 9;
     return AICAM_OK;
   }
 
@@ -169,8 +207,18 @@ struct Builder {
     const int cat17 = buf(h16, h16, c3 + c4);  // [conv16(o3) | n12]
     const int o3 = buf(h8, h8, c3), o4 = buf(h16, h16, c4), o5 = buf(h32, h32, c5);
 
-    conv("model.0.conv", V(-1), S, S, V(a0), 3, c1, 3, 2, 1);
-    conv("model.1.conv", V(a0), h2, h2, V(a1), c1, c2, 3, 2, 1);
+    // The two stride-2 layers at full resolution run as 2x2 windows over space-to-depth tensors: the input
+    // arrives (or is repacked) as [S/2][S/2][2x2][RGB0], the stem stores its output as [S/4][S/4][2x2][c1].
+    const bool s2d0 = s2d_channels(3, 2, 3, 4) != 0;
+    const bool s2d1 = s2d0 && c1 == 16 && s2d_channels(3, 2, c1, c1) != 0;
+    if (s2d0) {
+      e->s2d_in = buf(h2, h2, 16);
+      conv_s2d("model.0.conv", V(-1), h2, h2, V(a0), 3, c1, 4, 1, s2d1 ? 1 : 0);
+    } else {
+      conv("model.0.conv", V(-1), S, S, V(a0), 3, c1, 3, 2, 1);
+    }
+    if (s2d1) conv_s2d("model.1.conv", V(a0), h4, h4, V(a1), c1, c2, 16, 1, 0);
+    else conv("model.1.conv", V(a0), h2, h2, V(a1), c1, c2, 3, 2, 1);
     c2f("model.2", V(a1), c2, V(a2), c2, ns, true, h4, h4);
     conv("model.3.conv", V(a2), h4, h4, V(a3), c2, c3, 3, 2, 1);
     c2f("model.4", V(a3), c3, V(cat14, c4), c3, nl, true, h8, h8);
@@ -262,7 +310,15 @@ struct Builder {
 };
 
 int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStream_t stream,
-            const int* n_dev = nullptr) {
+            const int* n_dev = nullptr, bool input_is_s2d = false) {
+  const void* input_s2d = input;
+  if (e->s2d_in >= 0 && !input_is_s2d) {
+    __nv_bfloat16* dst = e->buffers[e->s2d_in].ptr;
+    if (int rc = launch_space_to_depth(static_cast<const __nv_bfloat16*>(input), batch, e->in_h, e->in_w, 4, dst, stream)) return rc;
+    input_s2d = dst;
+  } else if (e->s2d_in < 0 && input_is_s2d) {
+    return fail(AICAM_ERR_UNSUPPORTED, "engine: this engine was built without the space-to-depth stem");
+  }
   for (const Op& op : e->ops) {
     auto geom = [&](const View& v, int fallback_c, const __nv_bfloat16** ptr, long long* img_stride, int* cstride) {
       if (v.buf >= 0) {
@@ -287,9 +343,16 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
         ConvLaunch L;
         const PackedConv& pc = e->convs[op.conv];
         L.in = ip; L.in_img_stride = is; L.in_cstride = ic; L.in_coff = op.in.coff;
+        if (op.s2d_c0) {  // the same bytes viewed as (h x w) blocks of 4 c0 channels
+          if (op.in.buf == -1) L.in = static_cast<const __nv_bfloat16*>(input_s2d);
+          L.in_cstride = 4 * op.s2d_c0;
+          L.in_img_stride = static_cast<long long>(op.h) * op.w * L.in_cstride;
+        }
+        L.out_s2d = op.out_s2d;
         L.batch = batch; L.h = op.h; L.w = op.w;
         L.ho = (op.h + 2 * (op.k / 2) - op.k) / op.stride + 1;
         L.wo = (op.w + 2 * (op.k / 2) - op.k) / op.stride + 1;
+        if (op.s2d_c0) { L.ho = op.h; L.wo = op.w; }
         if (op.out.buf == -2) {
           L.out = static_cast<float*>(output) + op.out.eoff;
         } else {
@@ -420,7 +483,12 @@ int aicam_engine_num_classes(const aicam_engine* e) {
 }
 int aicam_engine_num_anchors(const aicam_engine* e) { return e ? e->num_anchors : 0; }
 double aicam_engine_flops_per_item(const aicam_engine* e) { return e ? 2.0 * e->macs_per_item : 0.0; }
-int aicam_engine_num_launches(const aicam_engine* e) { return e ? static_cast<int>(e->ops.size()) : 0; }
+int aicam_engine_num_launches(const aicam_engine* e) {
+  if (!e) return 0;
+  int n = 0;
+  for (const auto& op : e->ops) n += op.type == aicam::Op::STEMPOOL ? 2 : 1;  // NHWC8 repack + fused stem
+  return n;
+}
 
 int aicam_engine_set_bias(aicam_engine* e, const char* name, const float* host, int n) {
   if (!e || !name || !host) return fail(AICAM_ERR_INVALID_ARG, "engine_set_bias: bad arguments");
@@ -451,6 +519,15 @@ int aicam_yolo_forward(aicam_engine* e, const void* in_nhwc4, int batch, float* 
   return run_ops(e, in_nhwc4, batch, head, static_cast<cudaStream_t>(stream));
 }
 
+int aicam_yolo_forward_s2d(aicam_engine* e, const void* in_s2d16, int batch, float* head, void* stream) {
+  if (!e || e->kind != AICAM_KIND_YOLOV8) return fail(AICAM_ERR_INVALID_ARG, "yolo_forward_s2d: not a yolov8 engine");
+  if (!in_s2d16 || !head) return fail(AICAM_ERR_INVALID_ARG, "yolo_forward_s2d: null tensor");
+  if (batch < 0 || batch > e->max_batch) return fail(AICAM_ERR_CAPACITY, "yolo_forward_s2d: batch exceeds max_batch");
+  return run_ops(e, in_s2d16, batch, head, static_cast<cudaStream_t>(stream), nullptr, true);
+}
+
+int aicam_engine_accepts_s2d(const aicam_engine* e) { return e && e->s2d_in >= 0 ? 1 : 0; }
+
 int aicam_reid_forward(aicam_engine* e, const void* crops_nhwc4, int n, const int32_t* n_dev, float* feats,
                        void* stream) {
   if (!e || e->kind != AICAM_KIND_REID) return fail(AICAM_ERR_INVALID_ARG, "reid_forward: not a reid engine");
@@ -480,6 +557,33 @@ int aicam_conv2d(const aicam_conv_desc* d, const void* in, const float* w, const
                  void* out, void* stream) {
   if (!d || !in || !w || !out) return fail(AICAM_ERR_INVALID_ARG, "conv2d: null argument");
   PackedConv pc;
+  const int c0 = (d->h % 2 == 0 && d->w % 2 == 0) ? s2d_channels(d->ksize, d->stride, d->cin, d->cin <= 4 ? 4 : d->cin) : 0;
+  if (c0) {  // 3x3 stride 2 over 3/4 or 16 dense channels: repack space-to-depth, 2x2 window kernel
+    if (int rc = pack_conv_weights_s2d(w, bias, d->cout, d->cin, c0, &pc)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    __nv_bfloat16* s2 = nullptr;
+    if (cudaMalloc(&s2, static_cast<size_t>(d->batch) * d->h * d->w * c0 * 2) != cudaSuccess) {
+      free_packed_conv(&pc);
+      return fail(AICAM_ERR_CUDA, "conv2d: cudaMalloc failed");
+    }
+    int rc = launch_space_to_depth(static_cast<const __nv_bfloat16*>(in), d->batch, d->h, d->w, c0, s2, st);
+    ConvLaunch L;
+    L.in = s2; L.in_cstride = 4 * c0; L.in_coff = 0;
+    L.batch = d->batch; L.h = d->h / 2; L.w = d->w / 2; L.ho = L.h; L.wo = L.w;
+    L.in_img_stride = static_cast<long long>(L.h) * L.w * L.in_cstride;
+    L.out = out; L.out_img_stride = static_cast<long long>(L.ho) * L.wo * d->cout; L.out_cstride = d->cout;
+    L.out_coff = 0; L.out_f32 = d->out_f32;
+    L.res = static_cast<const __nv_bfloat16*>(res); L.res_img_stride = L.out_img_stride; L.res_cstride = d->cout;
+    L.res_coff = 0; L.res_mode = res ? d->res_mode : 0;
+    L.act = d->act;
+    if (!rc) rc = launch_conv(pc, L, st);
+    cudaError_t se = cudaStreamSynchronize(st);
+    cudaFree(s2);
+    free_packed_conv(&pc);
+    if (rc) return rc;
+    if (se != cudaSuccess) return fail(AICAM_ERR_CUDA, std::string("conv2d: ") + cudaGetErrorString(se));
+    return AICAM_OK;
+  }
   if (int rc = pack_conv_weights(w, bias, d->cout, d->cin, d->ksize, d->stride, &pc)) return rc;
   ConvLaunch L;
   const int cs = pc.cin_pad;
@@ -530,9 +634,12 @@ int aicam_conv2d_bench(const aicam_conv_desc* d, int iters, double* mean_ms, voi
   uint32_t seed = 12345u;
   for (auto& v : w) { seed = seed * 1664525u + 1013904223u; v = (static_cast<int>(seed >> 16) % 2001 - 1000) * 1e-4f; }
   PackedConv pc;
-  if (int rc = pack_conv_weights(w.data(), b.data(), d->cout, d->cin, d->ksize, d->stride, &pc)) return rc;
+  const int c0 = (d->h % 2 == 0 && d->w % 2 == 0) ? s2d_channels(d->ksize, d->stride, d->cin, d->cin <= 4 ? 4 : d->cin) : 0;
+  if (int rc = c0 ? pack_conv_weights_s2d(w.data(), b.data(), d->cout, d->cin, c0, &pc)
+                  : pack_conv_weights(w.data(), b.data(), d->cout, d->cin, d->ksize, d->stride, &pc))
+    return rc;
   ConvLaunch L;
-  const int cs = pc.cin_pad;
+  const int cs = c0 ? c0 : pc.cin_pad;
   const int ho = (d->h + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
   const int wo = (d->w + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
   const size_t in_elems = static_cast<size_t>(d->batch) * d->h * d->w * cs;
@@ -549,6 +656,9 @@ int aicam_conv2d_bench(const aicam_conv_desc* d, int iters, double* mean_ms, voi
   }
   L.in = in; L.in_img_stride = static_cast<long long>(d->h) * d->w * cs; L.in_cstride = cs; L.in_coff = 0;
   L.batch = d->batch; L.h = d->h; L.w = d->w; L.ho = ho; L.wo = wo;
+  if (c0) {  // the timed launches read the same bytes as an already space-to-depth tensor
+    L.in_cstride = 4 * c0; L.h = d->h / 2; L.w = d->w / 2; L.ho = L.h; L.wo = L.w;
+  }
   L.out = out; L.out_img_stride = static_cast<long long>(ho) * wo * d->cout; L.out_cstride = d->cout; L.out_coff = 0;
   L.out_f32 = d->out_f32;
   L.res = res; L.res_img_stride = L.out_img_stride; L.res_cstride = d->cout; L.res_coff = 0; L.res_mode = d->res_mode;

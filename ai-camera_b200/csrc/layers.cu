@@ -104,7 +104,35 @@ __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ in, int hw, __nv_
   reinterpret_cast<uint2*>(out)[idx] = o;
 }
 
+// [n][h][w][c] -> [n][h/2][w/2][2x2 sub-pixel][c]: one thread per 16-byte (or, for 4 channels, 8-byte) piece
+template <typename V>
+__global__ void space_to_depth_kernel(const V* __restrict__ in, V* __restrict__ out, int h, int w, int pieces, long long total) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int pc = static_cast<int>(idx % pieces);
+  long long p = idx / pieces;
+  const int x = static_cast<int>(p % w); p /= w;
+  const int y = static_cast<int>(p % h);
+  const long long n = p / h;
+  const long long dst = (((n * (h >> 1) + (y >> 1)) * (w >> 1) + (x >> 1)) * 4 + ((y & 1) << 1) + (x & 1)) * pieces + pc;
+  out[dst] = __ldg(in + idx);
+}
+
 }  // namespace
+
+int launch_space_to_depth(const __nv_bfloat16* in, int batch, int h, int w, int c, __nv_bfloat16* out, cudaStream_t stream) {
+  if ((c != 4 && c % 8) || h % 2 || w % 2) return fail(AICAM_ERR_INVALID_ARG, "space_to_depth: 4 or a multiple of 8 channels, even sizes");
+  const int pieces = c == 4 ? 1 : c / 8;
+  const long long total = static_cast<long long>(batch) * h * w * pieces;
+  if (total == 0) return AICAM_OK;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (c == 4)
+    space_to_depth_kernel<uint2><<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint2*>(in), reinterpret_cast<uint2*>(out), h, w, 1, total);
+  else
+    space_to_depth_kernel<uint4><<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), h, w, pieces, total);
+  count_launch();
+  return last_launch("space_to_depth_kernel");
+}
 
 int launch_maxpool(const __nv_bfloat16* in, long long in_img_stride, int in_cstride, int in_coff, int batch, int h,
                    int w, int c, int k, int stride, __nv_bfloat16* out, long long out_img_stride, int out_cstride,

@@ -11,6 +11,8 @@ int launch_upsample2x(const __nv_bfloat16* in, long long in_img_stride, int in_c
                       cudaStream_t stream);
 int launch_avgpool_l2norm(const __nv_bfloat16* in, int batch, int hw, int c, float* out, cudaStream_t stream,
                           const int* n_dev = nullptr);
+// bf16 [n][h][w][c] -> [n][h/2][w/2][2x2 sub-pixel][c] (c = 4 or a multiple of 8)
+int launch_space_to_depth(const __nv_bfloat16* in, int batch, int h, int w, int c, __nv_bfloat16* out, cudaStream_t stream);
 int launch_nchw_to_nhwc4(const float* in, int n, int h, int w, __nv_bfloat16* out, cudaStream_t stream);
 
 }  // namespace aicam

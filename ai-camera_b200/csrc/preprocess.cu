@@ -187,15 +187,24 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
       *reinterpret_cast<float4*>(o + static_cast<long long>(c) * S * S) =
           make_float4(rgb[0][c], rgb[1][c], rgb[2][c], rgb[3][c]);
   } else {
-    uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) +
-                                        ((static_cast<long long>(n) * S + y) * S + xg * PIX) * 4);
     uint4 q0, q1;
     q0.x = pack_bf16x2(rgb[0][0], rgb[0][1]); q0.y = pack_bf16x2(rgb[0][2], 0.0f);
     q0.z = pack_bf16x2(rgb[1][0], rgb[1][1]); q0.w = pack_bf16x2(rgb[1][2], 0.0f);
     q1.x = pack_bf16x2(rgb[2][0], rgb[2][1]); q1.y = pack_bf16x2(rgb[2][2], 0.0f);
     q1.z = pack_bf16x2(rgb[3][0], rgb[3][1]); q1.w = pack_bf16x2(rgb[3][2], 0.0f);
-    o[0] = q0;
-    o[1] = q1;
+    if (FORMAT == 1) {
+      uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) +
+                                          ((static_cast<long long>(n) * S + y) * S + xg * PIX) * 4);
+      o[0] = q0;
+      o[1] = q1;
+    } else {
+      // space-to-depth: 2x2 pixel block (Y, X) = 16 channels [row parity][column parity][RGB0]; this thread
+      // holds columns 4 xg .. 4 xg + 3 of row y = blocks X = 2 xg, 2 xg + 1, row parity y & 1
+      uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) +
+                                          ((static_cast<long long>(n) * (S / 2) + (y >> 1)) * (S / 2) + 2 * xg) * 16 + (y & 1) * 8);
+      o[0] = q0;
+      o[2] = q1;
+    }
   }
 }
 
@@ -216,7 +225,7 @@ int aicam_letterbox_params(int h, int w, aicam_letterbox* meta) {
 
 int aicam_preprocess(const uint8_t* frames, int batch, int h, int w, int format, void* out, void* stream) {
   if (!frames || !out || batch < 0 || h <= 0 || w <= 0) return fail(AICAM_ERR_INVALID_ARG, "preprocess: bad arguments");
-  if (format != 0 && format != 1) return fail(AICAM_ERR_INVALID_ARG, "preprocess: format must be 0 or 1");
+  if (format < 0 || format > 2) return fail(AICAM_ERR_INVALID_ARG, "preprocess: format must be 0, 1 or 2");
   if (batch == 0) return AICAM_OK;
   Geometry g;
   if (int rc = get_geometry(h, w, &g)) return rc;
@@ -225,8 +234,10 @@ int aicam_preprocess(const uint8_t* frames, int batch, int h, int w, int format,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (format == 0)
     preprocess_kernel<0><<<blocks, 256, 0, st>>>(frames, h, w, g.mode, g.new_h, g.new_w, g.top, g.left, g.tab, out, total);
-  else
+  else if (format == 1)
     preprocess_kernel<1><<<blocks, 256, 0, st>>>(frames, h, w, g.mode, g.new_h, g.new_w, g.top, g.left, g.tab, out, total);
+  else
+    preprocess_kernel<2><<<blocks, 256, 0, st>>>(frames, h, w, g.mode, g.new_h, g.new_w, g.top, g.left, g.tab, out, total);
   count_launch();
   return last_launch("preprocess_kernel");
 }

@@ -67,6 +67,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tma
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 // im2col TMA load: base pixel (w, h, n) + filter offsets; writes pixelsPerColumn rows of channelsPerPixel elements
 __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c, int w, int h,
                                                    int n, uint16_t off_w, uint16_t off_h) {

@@ -38,6 +38,7 @@ class BatchDetector:
         self.scores = torch.zeros((batch, topk), dtype=torch.float32, device=dev)
         self.labels = torch.zeros((batch, topk), dtype=torch.int32, device=dev)
         self._nms = _lib.NmsParams(e.score_threshold, e.nms_threshold, topk, e.max_candidates, 0, 0)
+        self._s2d = bool(self.lib.aicam_engine_accepts_s2d(e.handle))
 
     def detect(self, frames: torch.Tensor):
         """frames: uint8 cuda [n<=batch, H, W, 3] BGR.  Returns device tensors (num_dets [n],
@@ -48,8 +49,12 @@ class BatchDetector:
             raise _lib.AicamError(-4, "detect: %d frames exceed the detector's batch %d" % (n, self.batch))
         e, st = self.engine, _lib.stream_ptr(self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.aicam_preprocess(_lib.ptr(frames), n, h, w, 1, _lib.ptr(e._nhwc), st))
-            _lib.check(self.lib.aicam_yolo_forward(e.handle, _lib.ptr(e._nhwc), n, _lib.ptr(e._head), st))
+            if self._s2d:  # same bytes, 2x2 pixel blocks: the stride-2 stem runs as a stride-1 window
+                _lib.check(self.lib.aicam_preprocess(_lib.ptr(frames), n, h, w, 2, _lib.ptr(e._nhwc), st))
+                _lib.check(self.lib.aicam_yolo_forward_s2d(e.handle, _lib.ptr(e._nhwc), n, _lib.ptr(e._head), st))
+            else:
+                _lib.check(self.lib.aicam_preprocess(_lib.ptr(frames), n, h, w, 1, _lib.ptr(e._nhwc), st))
+                _lib.check(self.lib.aicam_yolo_forward(e.handle, _lib.ptr(e._nhwc), n, _lib.ptr(e._head), st))
             self._nms.frame_h, self._nms.frame_w = h, w
             _lib.check(self.lib.aicam_decode_nms(
                 _lib.ptr(e._head), n, e.anchors, e.nc, C.byref(self._nms), _lib.ptr(self.num_dets),

@@ -77,6 +77,12 @@ int aicam_engine_get_bias(aicam_engine* e, const char* name, float* host, int n)
  *   head     : fp32 [batch][num_anchors][64 + nc]  raw DFL logits + class logits, anchors
  *              level-major (strides 8,16,32) then row-major */
 int aicam_yolo_forward(aicam_engine* e, const void* in_nhwc4, int batch, float* head, void* stream);
+/* Same network, input already space-to-depth as aicam_preprocess format 2 writes it:
+ * bf16 [batch][320][320][16] = 2x2 pixel blocks [row parity][column parity][R, G, B, 0].  The 3x3 stride-2
+ * stem runs as a 2x2 window over these blocks; aicam_yolo_forward repacks an NHWC4 input into this
+ * layout first.  aicam_engine_accepts_s2d: 1 when the engine was built with that stem. */
+int aicam_yolo_forward_s2d(aicam_engine* e, const void* in_s2d16, int batch, float* head, void* stream);
+int aicam_engine_accepts_s2d(const aicam_engine* e);
 
 /* ReID forward (the engine body behind reid_model.py:115).
  *   crops_nhwc4 : bf16 [n][128][64][4] ImageNet-normalised RGB (+ zero channel), from aicam_reid_crops
@@ -119,6 +125,8 @@ int aicam_reid_stem_pool(const void* in_nhwc4, int n, int h, int w, const float*
  *   frames : u8 [batch][h][w][3] BGR
  *   format 0: out = fp32 [batch][3][640][640] RGB/255 (the reference tensor, bit-exact)
  *   format 1: out = bf16 [batch][640][640][4] (what aicam_yolo_forward consumes)
+ *   format 2: out = bf16 [batch][320][320][16], the same values space-to-depth: 2x2 pixel blocks
+ *             [row parity][column parity][R, G, B, 0] (what aicam_yolo_forward_s2d consumes)
  * meta (host out, may be NULL): ratio, pad_w, pad_h as the reference returns them. */
 typedef struct {
   double ratio, pad_w, pad_h;

@@ -39,3 +39,15 @@ def test_preprocess_full_batch_checksum():
     want = torch.full((64, 3, 640, 640), 114.0 / 255.0)
     want[:, :, 140:500, :] = (frames[:, 1::3, 1::3, :].flip(-1).permute(0, 3, 1, 2).float() / 255.0)
     assert torch.equal(out, want)
+
+
+def test_space_to_depth_format_is_a_pure_permutation():
+    """Format 2 (what the 2x2-window stem consumes) holds exactly the NHWC4 values of format 1:
+    block (Y, X) channel (sy*2 + sx)*4 + c  ==  pixel (2Y + sy, 2X + sx) channel c."""
+    import gpu_util as G
+    rng = np.random.default_rng(7)
+    frames = torch.from_numpy(rng.integers(0, 256, (2, 540, 960, 3), dtype=np.uint8)).to(G.DEV)
+    a = G.preprocess(frames, 1).view(torch.int16).cpu().numpy()           # [B,640,640,4]
+    b = G.preprocess(frames, 2).view(torch.int16).cpu().numpy()           # [B,320,320,16]
+    want = a.reshape(2, 320, 2, 320, 2, 4).transpose(0, 1, 3, 2, 4, 5).reshape(2, 320, 320, 16)
+    assert np.array_equal(b, want)
