@@ -54,6 +54,7 @@ struct WinArgs {
   int h, w, hw;
   int rw, tw, strips, tstep, tiles_per_strip, tiles_per_img;
   float inv_rw;
+  int res_direct;  // residual read straight from global in the finish phase (no staging): deep, streamed layers
   int out_s2d;  // window modes: the output is stored space-to-depth: [h/2][w/2][2x2 sub-pixel][out_cstride]
   int flat;  // 1x1 mode: output and residual are dense, pixel p of the batch sits at p * cstride
   int mt, tm;
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
 
     // publish where the team's rows of `tile` live (part-0 warp, lane = row)
     auto publish_rows = [&](int tile, int slot) {
-      const int mt_idx = tile / a.n_tiles;
+      const int mt_idx = a.n_tiles == 1 ? tile : tile / a.n_tiles;
       const int n0 = (tile - mt_idx * a.n_tiles) * a.n_tile;
       bool valid;
       int img, pix;
@@ -301,54 +302,70 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       if (a.res_mode)
         ro[8 * 32 + lane] = valid ? img * a.res_img_stride + static_cast<long long>(pix) * a.res_cstride + a.res_coff + n0 : -1;
     };
+    // per-n-tile constants: column range of the TMEM phase, chunks per row of the copy phases.  With a
+    // single n-tile (most layers) they are computed once; otherwise again for every tile.
+    struct Cols { int n0, ncols, c_lo, c_hi, cpr, cpr_sh, rcpr, rcpr_sh; };
+    auto cols_of = [&](int nt) -> Cols {
+      Cols c;
+      c.n0 = nt * a.n_tile;
+      c.ncols = min(a.n_tile, a.cout - c.n0);
+      const int groups = (c.ncols + 15) >> 4;
+      c.c_lo = min(c.ncols, ((groups * part) / PARTS) << 4);
+      c.c_hi = min(c.ncols, ((groups * (part + 1)) / PARTS) << 4);
+      c.cpr = (c.ncols * esize) >> 4;
+      c.rcpr = (c.ncols * 2) >> 4;
+      c.cpr_sh = 0;
+      while ((1 << c.cpr_sh) < c.cpr) ++c.cpr_sh;
+      c.rcpr_sh = 0;
+      while ((1 << c.rcpr_sh) < c.rcpr) ++c.rcpr_sh;
+      return c;
+    };
+    const bool single_n = a.n_tiles == 1;
+    Cols cc = cols_of(single_n ? 0 : static_cast<int>(blockIdx.x) % a.n_tiles);
+    const bool res_staged = a.res_mode != 0 && a.res_direct == 0;
     // residual rows [ROWS_PER_WARP * part, +ROWS_PER_WARP) of the team's quarter -> residual staging:
     // 16-byte cp.async, lanes on consecutive chunks of a row (whole rows per instruction)
-    auto prefetch_res = [&](int tile, int slot) {
-      const int n0 = (tile % a.n_tiles) * a.n_tile;
-      const int rcpr = (min(a.n_tile, a.cout - n0) * 2) >> 4;
-      int sh = 0;
-      while ((1 << sh) < rcpr) ++sh;
-      const int ch = lane & ((1 << sh) - 1);
+    auto prefetch_res = [&](const Cols& c, int slot) {
+      const int ch = lane & ((1 << c.rcpr_sh) - 1);
       const long long* ro = rowoff_base + slot * (2 * 8 * 32) + 8 * 32;
-      for (int rr = lane >> sh; rr < ROWS_PER_WARP; rr += 32 >> sh) {
+      for (int rr = lane >> c.rcpr_sh; rr < ROWS_PER_WARP; rr += 32 >> c.rcpr_sh) {
         const int r = part * ROWS_PER_WARP + rr;
         const long long off = ro[r];
-        if (off >= 0 && ch < rcpr) cp_async_16(smem_u32(res_q + static_cast<size_t>(r) * rpitch + ch * 16), a.res + off + ch * 8);
+        if (off >= 0 && ch < c.rcpr) cp_async_16(smem_u32(res_q + static_cast<size_t>(r) * rpitch + ch * 16), a.res + off + ch * 8);
       }
     };
 
     if (part == 0) publish_rows(blockIdx.x, 0);
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
-    if (a.res_mode) prefetch_res(blockIdx.x, 0);
+    if (res_staged) prefetch_res(cc, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
-      const int n0 = (tile % a.n_tiles) * a.n_tile;
-      const int ncols = min(a.n_tile, a.cout - n0);
-      const int groups = (ncols + 15) >> 4;
-      const int c_lo = min(ncols, ((groups * part) / PARTS) << 4);  // my column range in the TMEM phase
-      const int c_hi = min(ncols, ((groups * (part + 1)) / PARTS) << 4);
+      const Cols c = cc;
       const long long* ro = rowoff_base + buf * (2 * 8 * 32);
       mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
-      if (a.res_mode) cp_async_wait_all();
+      if (res_staged) cp_async_wait_all();
       // B1: the team's residual rows have landed, its row offsets are published, and every warp of
       // the team is done copying the previous tile out of the staging rows
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
       const bool valid = ro[lane] >= 0;
+      // residual of my row: staged in shared memory, or (deep layers) read from global right here
+      const uint8_t* res_row = my_res;
+      if (a.res_direct && valid) res_row = reinterpret_cast<const uint8_t*>(a.res + ro[8 * 32 + lane]);
       // ---- TMEM -> registers -> bias / residual / activation -> my staging row (32 columns in flight)
       const uint32_t taddr = taddr_lane + buf * acc_cols + my_j * a.n_tile;
-      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+      for (int c0 = c.c_lo; c0 < c.c_hi; c0 += 32) {
         uint32_t v0[16], v1[16];
-        const bool two = c0 + 16 < c_hi;  // warp-uniform
+        const bool two = c0 + 16 < c.c_hi;  // warp-uniform
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-row predicated body
         tc_ld16_nowait(taddr + c0, v0);
         if (two) tc_ld16_nowait(taddr + c0 + 16, v1);
         tc_ld_wait();
         if (valid) {
-          finish_group<ACT>(v0, bias_s + n0 + c0, my_res + c0 * 2, a.res_mode, a.out_f32, my_stage + c0 * esize);
+          finish_group<ACT>(v0, bias_s + c.n0 + c0, res_row + c0 * 2, a.res_mode, a.out_f32, my_stage + c0 * esize);
           if (two)
-            finish_group<ACT>(v1, bias_s + n0 + c0 + 16, my_res + (c0 + 16) * 2, a.res_mode, a.out_f32,
+            finish_group<ACT>(v1, bias_s + c.n0 + c0 + 16, res_row + (c0 + 16) * 2, a.res_mode, a.out_f32,
                               my_stage + (c0 + 16) * esize);
         }
       }
@@ -356,20 +373,19 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       tc_fence_before();
       mbar_arrive(bar_acc_empty + 8 * buf);
       const int next = tile + static_cast<int>(gridDim.x);
-      if (part == 0 && next < total_tiles) publish_rows(next, buf ^ 1);
+      const bool more = next < total_tiles;
+      if (!single_n && more) cc = cols_of(next % a.n_tiles);
+      if (part == 0 && more) publish_rows(next, buf ^ 1);
       // B2: the team's staging rows are complete, the residual staging is free, next offsets are published
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
-      if (a.res_mode && next < total_tiles) prefetch_res(next, buf ^ 1);
+      if (res_staged && more) prefetch_res(cc, buf ^ 1);
       // ---- staging -> global, rows [ROWS_PER_WARP * part, +ROWS_PER_WARP): whole rows per instruction
-      {
-        const int cpr = (ncols * esize) >> 4;
-        int sh = 0;
-        while ((1 << sh) < cpr) ++sh;
-        const int ch = lane & ((1 << sh) - 1);
-        for (int rr = lane >> sh; rr < ROWS_PER_WARP; rr += 32 >> sh) {
+      if (c.cpr > 0) {
+        const int ch = lane & ((1 << c.cpr_sh) - 1);
+        for (int rr = lane >> c.cpr_sh; rr < ROWS_PER_WARP; rr += 32 >> c.cpr_sh) {
           const int r = part * ROWS_PER_WARP + rr;
           const long long oo = ro[r];
-          if (oo >= 0 && ch < cpr) {
+          if (oo >= 0 && ch < c.cpr) {
             const uint4 val = *reinterpret_cast<const uint4*>(stage_q + static_cast<size_t>(r) * pitch + ch * 16);
             *reinterpret_cast<uint4*>(out_bytes + oo * esize + ch * 16) = val;
           }
@@ -675,6 +691,9 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   const uint32_t stage_pitch = n_tile * es + 16;
   const uint32_t res_pitch = n_tile * 2 + 16;
   const int sb = resident ? 0 : 4;
+  // streamed (deep-K) layers: the epilogue is a small share of a tile, read the residual from global there
+  // instead of spending 70 KB of shared memory that the 256-row tiling needs
+  const bool res_staged = res_mode != 0 && resident;
   const size_t fixed_base = OFF_RING_A + (resident ? (wbytes + 1023) / 1024 * 1024 : static_cast<size_t>(sb) * bstage_bytes);
 
   // ---- choose the tiling: strips x (linear | row-aligned) x mt, cheapest estimated time
@@ -687,7 +706,7 @@ plan:
     if (force_mt && mt != force_mt) continue;
     const int tm = 128 * mt;
     if (2 * mt * n_tile > 512) continue;
-    const size_t stage_bytes = static_cast<size_t>(tm) * (stage_pitch + (res_mode ? res_pitch : 0));
+    const size_t stage_bytes = static_cast<size_t>(tm) * (stage_pitch + (res_staged ? res_pitch : 0));
     const size_t fixed = fixed_base + stage_bytes;
     for (int strips = 1; strips <= (window ? 8 : 1); ++strips) {
       for (int aligned = 0; aligned <= (window ? 1 : 0); ++aligned) {
@@ -782,7 +801,8 @@ plan:
   a.inv_rw = 1.0f / static_cast<float>(best.rw);
   a.flat = (mode != 0 && L.out_img_stride == static_cast<long long>(a.hw) * L.out_cstride &&
             (!res_mode || L.res_img_stride == static_cast<long long>(a.hw) * L.res_cstride)) ? 1 : 0;
-  const size_t smem = a.off_stage + static_cast<size_t>(a.tm) * (stage_pitch + (res_mode ? res_pitch : 0));
+  a.res_direct = (res_mode != 0 && !res_staged) ? 1 : 0;
+  const size_t smem = a.off_stage + static_cast<size_t>(a.tm) * (stage_pitch + (res_staged ? res_pitch : 0));
   if (smem > SMEM_LIMIT) return 0;
 
   alignas(64) CUtensorMap tmap;
