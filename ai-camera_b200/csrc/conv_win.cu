@@ -41,7 +41,7 @@ namespace {
 using namespace ptx;
 
 constexpr int NWG = 4;                          // epilogue warpgroups
-constexpr int WIN_THREADS = (4 * NWG + 3) * 32;  // + MMA issuer, patch producer, weight producer
+constexpr int WIN_THREADS = (4 * NWG + 4) * 32;  // + MMA issuer, patch producer, weight producer, epilogue I/O warp
 constexpr int MAX_RING = 8;
 constexpr uint32_t OFF_BIAS = 512;      // fp32 bias, <= 512 channels
 constexpr uint32_t OFF_ROWOFF = 2560;   // 2 tile parities x (output, residual) x 8 teams x 32 rows x int64 element offsets
@@ -49,11 +49,28 @@ constexpr uint32_t OFF_RING_A = 11264;   // 1024-byte aligned: swizzle patterns 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 constexpr size_t RESIDENT_LIMIT = 120 * 1024;
 
+// tensor maps of one launch: the input (patch / flat / im2col), and for the TMA epilogue the output and the
+// residual, one map per channel piece (<= 64 channels = one 128-byte swizzled row)
+struct WinMaps {
+  CUtensorMap in;
+  CUtensorMap out[2];
+  CUtensorMap res[2];
+};
+
 struct WinArgs {
   int mode;  // 0: 3x3 window over 4-D patches, 1: 1x1 over the flat [pixels][channels] matrix
   int h, w, hw;
   int rw, tw, strips, tstep, tiles_per_strip, tiles_per_img;
   float inv_rw;
+  // TMA epilogue (window modes, row-aligned tiles): compact staging tile [th * tw rows][piece channels], swizzled
+  int th;                 // raster rows per tile
+  int pieces;             // channel pieces of an n-tile (1 or 2)
+  int piece_ch[2];        // channels per piece: 64 / 32 / 16
+  uint32_t piece_off[2];  // byte offset of the piece inside a staging buffer (1024-aligned)
+  uint32_t stage_buf_bytes, res_tx_bytes;
+  int nres;               // residual staging buffers (TMA-loaded one or two tiles ahead)
+  int nstage;             // output staging buffers (2: the store of tile i overlaps the staging of tile i + 1)
+  long long* trace;       // debug: clock64 stamps of CTA 0 (AICAM_CONV_TRACE in aicam_conv2d_bench)
   int res_direct;  // residual read straight from global in the finish phase (no staging): deep, streamed layers
   int out_s2d;  // window modes: the output is stored space-to-depth: [h/2][w/2][2x2 sub-pixel][out_cstride]
   int flat;  // 1x1 mode: output and residual are dense, pixel p of the batch sits at p * cstride
@@ -129,7 +146,11 @@ __device__ __forceinline__ float activate(float x) {
 // One 16-column group of an accumulator row: + bias (+ residual), activation, pack into the staging row.
 template <int ACT>
 __device__ __forceinline__ void finish_group(const uint32_t (&v)[16], const float* bias, const uint8_t* res_row,
-                                             int res_mode, int out_f32, uint8_t* dst) {
+                                             int res_mode, int out_f32, uint8_t* dst, const uint8_t* res_hi = nullptr,
+                                             uint8_t* dst_hi = nullptr) {
+  // res_hi / dst_hi: address of the second 16-byte chunk when it is not adjacent (swizzled staging)
+  if (res_hi == nullptr) res_hi = res_row + 16;
+  if (dst_hi == nullptr) dst_hi = dst + 16;
   float x[16];
   const float4* bp = reinterpret_cast<const float4*>(bias);
 #pragma unroll
@@ -142,7 +163,7 @@ __device__ __forceinline__ void finish_group(const uint32_t (&v)[16], const floa
   }
   if (res_mode) {
     const uint4 q0v = *reinterpret_cast<const uint4*>(res_row);
-    const uint4 q1v = *reinterpret_cast<const uint4*>(res_row + 16);
+    const uint4 q1v = *reinterpret_cast<const uint4*>(res_hi);
     const uint32_t rw_[8] = {q0v.x, q0v.y, q0v.z, q0v.w, q1v.x, q1v.y, q1v.z, q1v.w};
     if (res_mode == 2) {
 #pragma unroll
@@ -172,7 +193,7 @@ __device__ __forceinline__ void finish_group(const uint32_t (&v)[16], const floa
     o1.x = pack_bf16x2(x[8], x[9]);   o1.y = pack_bf16x2(x[10], x[11]);
     o1.z = pack_bf16x2(x[12], x[13]); o1.w = pack_bf16x2(x[14], x[15]);
     *reinterpret_cast<uint4*>(dst) = o0;
-    *reinterpret_cast<uint4*>(dst + 16) = o1;
+    *reinterpret_cast<uint4*>(dst_hi) = o1;
   }
 }
 
@@ -189,8 +210,11 @@ __device__ __forceinline__ TilePos tile_pos(const WinArgs& a, int mt_idx) {
   return t;
 }
 
-template <int SLAB, int AMODE, int MT, int ACT>
-__global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs a, const __grid_constant__ CUtensorMap tmap) {
+// trace slot layout: [tile < 32][16 stamps]; who: 0-3 MMA warp, 4-5 producer, 8-13 epilogue thread 0
+#define WIN_TRACE(it, who) do { if (a.trace && blockIdx.x == 0 && (it) < 32) a.trace[(it) * 16 + (who)] = clock64(); } while (0)
+
+template <int SLAB, int AMODE, int MT, int ACT, int EPI>
+__global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs a, const __grid_constant__ WinMaps maps) {
   constexpr uint32_t ROW_BYTES = SLAB * 2;
   constexpr int K16S = SLAB / 16;
   constexpr uint32_t LTYPE = SLAB == 64 ? 2u : (SLAB == 32 ? 4u : 6u);
@@ -206,7 +230,9 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_a_full = sbase, bar_a_empty = sbase + 64, bar_b_full = sbase + 128, bar_b_empty = sbase + 192;
   const uint32_t bar_acc_full = sbase + 256, bar_acc_empty = sbase + 272, bar_w_full = sbase + 288;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 320);
+  const uint32_t bar_res_full = sbase + 296, bar_res_empty = sbase + 312;  // TMA epilogue: residual staging ring
+  const uint32_t bar_stage_free = sbase + 328;  // x2, TMA epilogue: the store that used the staging buffer has read it
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 352);
   float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
 
   const int warp = threadIdx.x >> 5;
@@ -231,10 +257,16 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       mbar_init(bar_acc_empty + 8 * s, 128 * NWG);
     }
     mbar_init(bar_w_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_res_full + 8 * s, 1);
+      mbar_init(bar_res_empty + 8 * s, 128 * NWG);
+    }
+    mbar_init(bar_stage_free, 1);
+    mbar_init(bar_stage_free + 8, 1);
     mbar_init_fence();
   }
   if (warp == 4 * NWG) tc_alloc(smem_u32(tmem_ptr_smem), a.tmem_cols);
-  if (warp == 4 * NWG + 1 && lane == 0) tma_prefetch_desc(&tmap);
+  if (warp == 4 * NWG + 1 && lane == 0) tma_prefetch_desc(&maps.in);
   for (int i = threadIdx.x; i < a.cout_pad; i += WIN_THREADS) bias_s[i] = __ldg(a.bias + i);
   tc_fence_before();
   __syncthreads();
@@ -242,7 +274,100 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t acc_cols = static_cast<uint32_t>(MT * a.n_tile);
 
-  if (warp < 4 * NWG) {
+  if (EPI == 1 && warp < 4 * NWG) {
+    // ================================================================== epilogue, TMA flavour (16 warps)
+    // Row-aligned window tiles: a tile is `th` whole raster rows, so its valid outputs are a th x tw box of
+    // the output image.  Each thread finishes its accumulator row (column split as below) into a COMPACT
+    // staging tile [y][x < tw][channels] written with the TMA swizzle; one thread then issues a tensor
+    // store per channel piece - the hardware drops the box rows / columns that fall outside the image.
+    // The residual arrives the same way (a box load issued by the patch producer one or two tiles ahead).
+    // No per-row addresses, no validity tables, no copy loops.
+    constexpr int PARTS = MT == 2 ? 2 : 4;
+    const int wg = warp >> 2, wq = warp & 3;
+    const int my_j = MT == 2 ? (wg >> 1) : 0;
+    const int part = MT == 2 ? (wg & 1) : wg;
+    const int r = my_j * 128 + wq * 32 + lane;  // my position inside the tile (tile-invariant)
+    bool valid = true;
+    int crow = r;                               // flat / im2col tiles: 128 MT consecutive pixels, already compact
+    if (WINDOW) {
+      const int y_l = r / a.rw, xp = r - y_l * a.rw;
+      valid = r < a.tstep && xp < a.tw;
+      crow = y_l * a.tw + xp;                   // my row of the compact tile
+    }
+    const uint32_t taddr_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+    // per piece: byte offset of my row and the swizzle XOR of its 16-byte chunks
+    uint32_t row_off[2], row_xor[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const uint32_t pb = static_cast<uint32_t>(a.piece_ch[p]) * 2;
+      const uint32_t ro = static_cast<uint32_t>(crow) * pb;
+      const uint32_t mask = pb == 128 ? 7u : (pb == 64 ? 3u : 1u);
+      row_off[p] = a.piece_off[p] + ro;
+      row_xor[p] = ((ro >> 7) & mask) << 4;
+    }
+    uint8_t* stage0 = smem + a.off_stage;
+    const uint8_t* res_base = smem + a.off_res;
+    uint32_t rslot = 0, rphase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int mt_idx = a.n_tiles == 1 ? tile : tile / a.n_tiles;
+      const int n0 = (tile - mt_idx * a.n_tiles) * a.n_tile;
+      const int ncols = min(a.n_tile, a.cout - n0);
+      const int groups = (ncols + 15) >> 4;
+      const int g_lo = (groups * part) / PARTS, g_hi = (groups * (part + 1)) / PARTS;
+      if (threadIdx.x == 0) WIN_TRACE(it, 8);
+      mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0) WIN_TRACE(it, 9);
+      const uint8_t* res_buf = res_base + rslot * a.stage_buf_bytes;
+      if (a.res_mode) mbar_wait(bar_res_full + 8 * rslot, rphase);
+      if (threadIdx.x == 0) WIN_TRACE(it, 10);
+      const uint32_t taddr = taddr_lane + buf * acc_cols + my_j * a.n_tile;
+      // staging buffer of this tile and the parity of "its previous store has been read"
+      const int sbuf = a.nstage == 2 ? (it & 1) : 0;
+      const uint32_t sfree_bar = bar_stage_free + 8 * sbuf;
+      const uint32_t sfree_par = (a.nstage == 2 ? ((it >> 1) & 1) : (it & 1)) ^ 1;
+      uint8_t* stage = stage0 + sbuf * a.stage_buf_bytes;
+      bool stage_ok = false;
+      for (int g = g_lo; g < g_hi; g += 2) {
+        uint32_t v0[16], v1[16];
+        const bool two = g + 1 < g_hi;  // warp-uniform
+        __syncwarp();
+        tc_ld16_nowait(taddr + g * 16, v0);
+        if (two) tc_ld16_nowait(taddr + g * 16 + 16, v1);
+        if (!stage_ok) {  // the I/O warp's store of the previous tile has finished reading the staging tile
+          mbar_wait(sfree_bar, sfree_par);
+          stage_ok = true;
+        }
+        tc_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const int c = (g + h) * 16;                      // first channel of the group inside the n-tile
+            const int p = c < a.piece_ch[0] ? 0 : 1;
+            const uint32_t ch0 = static_cast<uint32_t>(c - (p ? a.piece_ch[0] : 0)) * 2;  // byte offset inside the piece row
+            const uint32_t o0 = row_off[p] + (ch0 ^ row_xor[p]), o1 = row_off[p] + ((ch0 + 16) ^ row_xor[p]);
+            finish_group<ACT>(h ? v1 : v0, bias_s + n0 + c, res_buf + o0, a.res_mode, 0, stage + o0, res_buf + o1, stage + o1);
+          }
+        }
+      }
+      if (!stage_ok) mbar_wait(sfree_bar, sfree_par);  // (no column group: keep the phases in step)
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty + 8 * buf);
+      if (a.res_mode) {
+        mbar_arrive(bar_res_empty + 8 * rslot);
+        if (++rslot == static_cast<uint32_t>(a.nres)) { rslot = 0; rphase ^= 1; }
+      }
+      if (threadIdx.x == 0) WIN_TRACE(it, 12);
+      fence_proxy_async();  // my staging writes -> visible to the TMA unit
+      // hand the tile to the I/O warp: arrive without waiting (it syncs on the same barrier).  Two barrier ids
+      // alternate: a thread can be one tile ahead of the I/O warp, never two (the staging-buffer wait above)
+      asm volatile("bar.arrive %0, %1;" ::"r"(2 + (it & 1)), "n"(128 * NWG + 32) : "memory");
+      if (threadIdx.x == 0) WIN_TRACE(it, 13);
+    }
+  } else if (warp < 4 * NWG) {
     // ================================================================== epilogue (16 warps)
     // The PARTS warps {wq + 4 p} that share TMEM lane quarter wq (rows 32 wq .. 32 wq + 31 of a
     // 128-row accumulator) form a team.  TMEM -> staging is split by COLUMNS inside the team (a warp
@@ -343,12 +468,15 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       const int buf = it & 1;
       const Cols c = cc;
       const long long* ro = rowoff_base + buf * (2 * 8 * 32);
+      if (threadIdx.x == 0) WIN_TRACE(it, 8);
       mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) WIN_TRACE(it, 9);
       if (res_staged) cp_async_wait_all();
       // B1: the team's residual rows have landed, its row offsets are published, and every warp of
       // the team is done copying the previous tile out of the staging rows
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+      if (threadIdx.x == 0) WIN_TRACE(it, 10);
       const bool valid = ro[lane] >= 0;
       // residual of my row: staged in shared memory, or (deep layers) read from global right here
       const uint8_t* res_row = my_res;
@@ -372,12 +500,14 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       // my part of the accumulator buffer has been read: the MMA thread may reuse it for tile it + 2
       tc_fence_before();
       mbar_arrive(bar_acc_empty + 8 * buf);
+      if (threadIdx.x == 0) WIN_TRACE(it, 12);
       const int next = tile + static_cast<int>(gridDim.x);
       const bool more = next < total_tiles;
       if (!single_n && more) cc = cols_of(next % a.n_tiles);
       if (part == 0 && more) publish_rows(next, buf ^ 1);
       // B2: the team's staging rows are complete, the residual staging is free, next offsets are published
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+      if (threadIdx.x == 0) WIN_TRACE(it, 13);
       if (res_staged && more) prefetch_res(cc, buf ^ 1);
       // ---- staging -> global, rows [ROWS_PER_WARP * part, +ROWS_PER_WARP): whole rows per instruction
       if (c.cpr > 0) {
@@ -415,17 +545,20 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         uint32_t xp0 = 0;
-        if (MODE == 0) {
+        if (MODE == 0 && a.tstep % a.rw != 0) {  // row-aligned tiles start at raster column 0
           const int mt_idx = tile / a.n_tiles;
           const int r2 = mt_idx % a.tiles_per_img;
           xp0 = static_cast<uint32_t>(((r2 % a.tiles_per_strip) * a.tstep) % a.rw);
         }
+        if (leader) WIN_TRACE(it, 0);
         mbar_wait(bar_acc_empty + 8 * buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
+        if (leader) WIN_TRACE(it, 1);
         const uint32_t d_tmem = tmem0 + buf * acc_cols;
         for (int s = 0; s < a.slabs; ++s) {
           mbar_wait(bar_a_full + 8 * sa, pa);
           tc_fence_after();
+          if (leader && s == 0) WIN_TRACE(it, 2);
           // descriptor low word of the patch at raster position xp0: start >> 4 | LBO (unused, 1)
           const uint32_t a_lo0 = ((a_ring + sa * a.patch_bytes) >> 4) + xp0 * (ROW_BYTES >> 4) + (1u << 16);
           uint32_t w_lo = ((w_base >> 4) + static_cast<uint32_t>(s * SLAB >> 3) * lbo) | b_lo_flags;
@@ -459,6 +592,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
           if (++sa == n_sa) { sa = 0; pa ^= 1; }
         }
         tc_commit_if(leader, bar_acc_full + 8 * buf);
+        if (leader) WIN_TRACE(it, 3);
       }
       tc_fence_before();
     }
@@ -496,21 +630,24 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
           }
         }
         int tap = 0, sl = 0;  // im2col: virtual slab -> (filter tap, channel slab)
+        const int pit = (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
         for (int s = 0; s < a.slabs; ++s) {
+          if (s == 0) WIN_TRACE(pit, 4);
           mbar_wait(bar_a_empty + 8 * sa, pa);
+          if (s == 0) WIN_TRACE(pit, 5);
           const uint32_t bar = bar_a_full + 8 * sa;
           const uint32_t dst = a_ring + sa * a.patch_bytes;
           mbar_arrive_expect_tx(bar, tx_bytes);
           if (MODE == 0) {
-            tma_load_4d(dst, &tmap, bar, s * SLAB, x_start, y_start, n_img);
+            tma_load_4d(dst, &maps.in, bar, s * SLAB, x_start, y_start, n_img);
           } else if (MODE == 1) {
-            tma_load_2d(dst, &tmap, bar, s * SLAB, mt_idx * TM);
+            tma_load_2d(dst, &maps.in, bar, s * SLAB, mt_idx * TM);
           } else {
             const int tr = tap / a.ksize, tc = tap - tr * a.ksize;
 #pragma unroll
             for (int j = 0; j < MT; ++j)
               if (cn[j] >= 0)
-                tma_load_im2col_4d(dst + j * (128 * ROW_BYTES), &tmap, bar, sl * SLAB, cw[j], chh[j], cn[j],
+                tma_load_im2col_4d(dst + j * (128 * ROW_BYTES), &maps.in, bar, sl * SLAB, cw[j], chh[j], cn[j],
                                    static_cast<uint16_t>(tc), static_cast<uint16_t>(tr));
             if (++sl == a.slabs_per_tap) { sl = 0; ++tap; }
           }
@@ -518,7 +655,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
         }
       }
     }
-  } else {
+  } else if (warp == 4 * NWG + 2) {
     // ================================================================== weight (B) producer
     if (lane == 0) {
       if (a.resident) {
@@ -554,6 +691,76 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
         }
       }
     }
+  } else if (EPI == 1) {
+    // ================================================================== epilogue I/O warp (TMA flavour only)
+    // Residual boxes are fetched up to `nres` tiles ahead of the epilogue; finished tiles are stored with one
+    // tensor store per channel piece.  The epilogue warps never wait for either instruction to issue.
+    const long long total_pix_io = static_cast<long long>(batch) * a.hw;
+    (void)total_pix_io;
+    auto coords = [&](int tile, int& n0, int& cx, int& cy, int& cn) {
+      const int mt_idx = a.n_tiles == 1 ? tile : tile / a.n_tiles;
+      n0 = (tile - mt_idx * a.n_tiles) * a.n_tile;
+      if (WINDOW) {
+        const TilePos tp = tile_pos(a, mt_idx);
+        cx = tp.strip * a.tw; cy = tp.q0 / a.rw; cn = tp.n_img;
+      } else {
+        cx = mt_idx * TM; cy = 0; cn = 0;
+      }
+    };
+    auto load_res = [&](int tile, uint32_t slot, uint32_t phase) {
+      int n0, cx, cy, cn;
+      coords(tile, n0, cx, cy, cn);
+      mbar_wait(bar_res_empty + 8 * slot, phase ^ 1);
+      if (lane == 0) {
+        const uint32_t rbar = bar_res_full + 8 * slot;
+        const uint32_t rdst = sbase + a.off_res + slot * a.stage_buf_bytes;
+        mbar_arrive_expect_tx(rbar, a.res_tx_bytes);
+        if (WINDOW) {
+          tma_load_4d(rdst + a.piece_off[0], &maps.res[0], rbar, n0, cx, cy, cn);
+          if (a.pieces == 2) tma_load_4d(rdst + a.piece_off[1], &maps.res[1], rbar, n0 + a.piece_ch[0], cx, cy, cn);
+        } else {
+          tma_load_2d(rdst + a.piece_off[0], &maps.res[0], rbar, n0, cx);
+          if (a.pieces == 2) tma_load_2d(rdst + a.piece_off[1], &maps.res[1], rbar, n0 + a.piece_ch[0], cx);
+        }
+      }
+      __syncwarp();
+    };
+    uint32_t lslot = 0, lphase = 0;  // next residual slot to fill
+    int ahead = blockIdx.x;          // next tile whose residual is to be fetched
+    if (a.res_mode)
+      for (int k = 0; k < a.nres && ahead < total_tiles; ++k, ahead += gridDim.x) {
+        load_res(ahead, lslot, lphase);
+        if (++lslot == static_cast<uint32_t>(a.nres)) { lslot = 0; lphase ^= 1; }
+      }
+    int io_it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++io_it) {
+      int n0, cx, cy, cn;
+      coords(tile, n0, cx, cy, cn);
+      const int sbuf = a.nstage == 2 ? (io_it & 1) : 0;
+      const uint32_t src = sbase + a.off_stage + sbuf * a.stage_buf_bytes;
+      asm volatile("bar.sync %0, %1;" ::"r"(2 + (io_it & 1)), "n"(128 * NWG + 32) : "memory");  // every epilogue thread has staged its part
+      if (lane == 0) {
+        const bool two = a.pieces == 2 && n0 + a.piece_ch[0] < a.cout;
+        if (WINDOW) {
+          tma_store_4d(&maps.out[0], src + a.piece_off[0], n0, cx, cy, cn);
+          if (two) tma_store_4d(&maps.out[1], src + a.piece_off[1], n0 + a.piece_ch[0], cx, cy, cn);
+        } else {
+          tma_store_2d(&maps.out[0], src + a.piece_off[0], n0, cx);
+          if (two) tma_store_2d(&maps.out[1], src + a.piece_off[1], n0 + a.piece_ch[0], cx);
+        }
+        bulk_commit();
+        bulk_wait_read_all();
+        mbar_arrive(bar_stage_free + 8 * sbuf);  // that staging buffer may be overwritten
+      }
+      __syncwarp();
+      // the epilogue has consumed this tile's residual: refill that slot for the tile `nres` ahead
+      if (a.res_mode && ahead < total_tiles) {
+        load_res(ahead, lslot, lphase);
+        if (++lslot == static_cast<uint32_t>(a.nres)) { lslot = 0; lphase ^= 1; }
+        ahead += gridDim.x;
+      }
+    }
+    if (lane == 0) bulk_wait_all();
   }
   __syncthreads();
   if (warp == 4 * NWG) {
@@ -562,29 +769,29 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
   }
 }
 
-typedef void (*WinKernelFn)(const WinArgs, const CUtensorMap);
+typedef void (*WinKernelFn)(const WinArgs, const WinMaps);
 
-template <int SLAB, int AMODE, int MT>
+template <int SLAB, int AMODE, int MT, int EPI>
 WinKernelFn pick_act(int act) {
-  if (act == 1) return conv_win_kernel<SLAB, AMODE, MT, 1>;
-  if (act == 2) return conv_win_kernel<SLAB, AMODE, MT, 2>;
-  return conv_win_kernel<SLAB, AMODE, MT, 0>;
+  if (act == 1) return conv_win_kernel<SLAB, AMODE, MT, 1, EPI>;
+  if (act == 2) return conv_win_kernel<SLAB, AMODE, MT, 2, EPI>;
+  return conv_win_kernel<SLAB, AMODE, MT, 0, EPI>;
 }
-template <int SLAB, int AMODE>
+template <int SLAB, int AMODE, int EPI>
 WinKernelFn pick_mt(int mt, int act) {
-  return mt == 2 ? pick_act<SLAB, AMODE, 2>(act) : pick_act<SLAB, AMODE, 1>(act);
+  return mt == 2 ? pick_act<SLAB, AMODE, 2, EPI>(act) : pick_act<SLAB, AMODE, 1, EPI>(act);
 }
 template <int SLAB>
-WinKernelFn pick_mode(int mode, int mt, int act) {
-  if (mode == 0) return pick_mt<SLAB, 0>(mt, act);
-  if (mode == 1) return pick_mt<SLAB, 1>(mt, act);
-  if (mode == 3) return pick_mt<SLAB, 3>(mt, act);
-  return pick_mt<SLAB, 2>(mt, act);
+WinKernelFn pick_mode(int mode, int mt, int act, int epi) {
+  if (mode == 0) return epi ? pick_mt<SLAB, 0, 1>(mt, act) : pick_mt<SLAB, 0, 0>(mt, act);
+  if (mode == 3) return epi ? pick_mt<SLAB, 3, 1>(mt, act) : pick_mt<SLAB, 3, 0>(mt, act);
+  if (mode == 1) return epi ? pick_mt<SLAB, 1, 1>(mt, act) : pick_mt<SLAB, 1, 0>(mt, act);
+  return epi ? pick_mt<SLAB, 2, 1>(mt, act) : pick_mt<SLAB, 2, 0>(mt, act);
 }
-WinKernelFn pick_kernel(int slab, int mode, int mt, int act) {
-  if (slab == 64) return pick_mode<64>(mode, mt, act);
-  if (slab == 32) return pick_mode<32>(mode, mt, act);
-  return pick_mode<16>(mode, mt, act);
+WinKernelFn pick_kernel(int slab, int mode, int mt, int act, int epi) {
+  if (slab == 64) return pick_mode<64>(mode, mt, act, epi);
+  if (slab == 32) return pick_mode<32>(mode, mt, act, epi);
+  return pick_mode<16>(mode, mt, act, epi);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -631,6 +838,8 @@ struct WinPlan {
   uint32_t patch_bytes = 0, box_bytes = 0, off_w = 0, off_b = 0, off_stage = 0;
   size_t smem = 0;
   long long tiles = 0;
+  uint32_t stage_buf = 0;
+  int nres = 0, nstage = 1;
 };
 
 }  // namespace
@@ -696,23 +905,41 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   const bool res_staged = res_mode != 0 && resident;
   const size_t fixed_base = OFF_RING_A + (resident ? (wbytes + 1023) / 1024 * 1024 : static_cast<size_t>(sb) * bstage_bytes);
 
+  // ---- TMA epilogue (window modes, bf16, natural layout): the n-tile splits into one or two channel pieces
+  // of 64 / 32 / 16 channels, each a swizzled staging tile with its own output / residual tensor map
+  static const bool no_tma_epi = getenv("AICAM_WIN_NO_TMA_EPI") != nullptr;
+  int piece_ch[2] = {0, 0};
+  {
+    const int first = n_tile >= 64 ? 64 : (n_tile >= 32 ? 32 : 16);
+    const int rest = n_tile - first;
+    if (rest == 0 || rest == 64 || rest == 32 || rest == 16) { piece_ch[0] = first; piece_ch[1] = rest; }
+  }
+  bool epi = !no_tma_epi && piece_ch[0] != 0 && !L.out_f32 && !L.out_s2d && pc.cout % 8 == 0;
+
   // ---- choose the tiling: strips x (linear | row-aligned) x mt, cheapest estimated time
   WinPlan best;
   const int k16_total = taps * pc.cin_pad / 16;
 plan:
   best = WinPlan();
   window = mode == 0 || mode == 3;
+  // flat / im2col tiles are runs of consecutive output pixels: the store is a 2-D box when pixel p of the batch
+  // sits at p * cstride in the output (and residual) tensor
+  const bool flat_io = L.out_img_stride == static_cast<long long>(L.ho) * L.wo * L.out_cstride &&
+                       (!res_mode || L.res_img_stride == static_cast<long long>(L.ho) * L.wo * L.res_cstride);
+  // measured: the TMA epilogue pays off where the epilogue bounds the tile (window modes, small K); deep
+  // im2col / flat layers are L2-bound and need the shared memory for deeper operand rings instead
+  static const bool epi_everywhere = getenv("AICAM_WIN_TMA_EPI_ALL") != nullptr;
+  if (!window && !(epi_everywhere && flat_io)) epi = false;
   for (int mt = 1; mt <= 2; ++mt) {
     if (force_mt && mt != force_mt) continue;
     const int tm = 128 * mt;
     if (2 * mt * n_tile > 512) continue;
-    const size_t stage_bytes = static_cast<size_t>(tm) * (stage_pitch + (res_staged ? res_pitch : 0));
-    const size_t fixed = fixed_base + stage_bytes;
     for (int strips = 1; strips <= (window ? 8 : 1); ++strips) {
-      for (int aligned = 0; aligned <= (window ? 1 : 0); ++aligned) {
+      for (int aligned = epi ? 1 : 0; aligned <= (window ? 1 : 0); ++aligned) {
         WinPlan p;
         p.mt = mt;
         p.strips = strips;
+        size_t stage_bytes = static_cast<size_t>(tm) * (stage_pitch + (res_staged ? res_pitch : 0));
         if (window) {
           p.tw = (win_w + strips - 1) / strips;
           p.rw = p.tw + kw1;
@@ -727,7 +954,18 @@ plan:
             p.tiles_per_strip = (win_h * p.rw + tm - 1) / tm;
           }
           const int xp0max = aligned ? 0 : p.rw - 1;
-          p.bh = (xp0max + p.tstep - 1 + kw1 * p.rw + kw1) / p.rw + 1;
+          p.bh = aligned ? p.tstep / p.rw + kw1 : (xp0max + p.tstep - 1 + kw1 * p.rw + kw1) / p.rw + 1;
+          if (epi) {
+            // compact staging tile(s): output + residual ring, every piece 1024-byte aligned
+            const int rows_c = (p.tstep / p.rw) * p.tw;
+            size_t buf = 0;
+            for (int q = 0; q < 2; ++q)
+              if (piece_ch[q]) buf += (static_cast<size_t>(rows_c) * piece_ch[q] * 2 + 1023) / 1024 * 1024;
+            p.stage_buf = static_cast<uint32_t>(buf);
+            p.nres = res_mode ? 2 : 0;
+            p.nstage = 2;
+            stage_bytes = buf * (p.nstage + p.nres) + 1024;  // + alignment slack after the weight / B ring
+          }
           if (p.bh > 256) continue;
           p.box_bytes = static_cast<uint32_t>(p.bh) * p.rw * row_bytes;
           const uint32_t reach = static_cast<uint32_t>(xp0max + tm + kw1 * p.rw + kw1 + 1) * row_bytes;  // junk rows stay inside the stage
@@ -738,6 +976,26 @@ plan:
           p.box_bytes = static_cast<uint32_t>(tm) * row_bytes;
           p.patch_bytes = (p.box_bytes + 1023) / 1024 * 1024;
           p.tiles = (pixels + tm - 1) / tm;
+          if (epi) {
+            size_t buf = 0;
+            for (int q = 0; q < 2; ++q)
+              if (piece_ch[q]) buf += (static_cast<size_t>(tm) * piece_ch[q] * 2 + 1023) / 1024 * 1024;
+            p.stage_buf = static_cast<uint32_t>(buf);
+            p.nres = res_mode ? 2 : 0;
+            p.nstage = 2;
+            stage_bytes = buf * (p.nstage + p.nres) + 1024;
+          }
+        }
+        size_t fixed = fixed_base + stage_bytes;
+        if (epi && fixed + 3 * static_cast<size_t>(p.patch_bytes) > SMEM_LIMIT) {
+          p.nstage = 1;  // single output staging buffer rather than a shallow patch ring
+          stage_bytes = static_cast<size_t>(p.stage_buf) * (p.nstage + p.nres) + 1024;
+          fixed = fixed_base + stage_bytes;
+        }
+        if (epi && p.nres == 2 && fixed + 3 * static_cast<size_t>(p.patch_bytes) > SMEM_LIMIT) {
+          p.nres = 1;  // then one residual buffer
+          stage_bytes = static_cast<size_t>(p.stage_buf) * (p.nstage + p.nres) + 1024;
+          fixed = fixed_base + stage_bytes;
         }
         if (fixed + 2 * static_cast<size_t>(p.patch_bytes) > SMEM_LIMIT) continue;
         p.sa = static_cast<int>(std::min<size_t>(MAX_RING, (SMEM_LIMIT - fixed) / p.patch_bytes));
@@ -745,18 +1003,28 @@ plan:
         p.sa = std::min(p.sa, window ? std::max(4, 2 * slabs) : 6);
         p.smem = fixed + static_cast<size_t>(p.sa) * p.patch_bytes;
         // estimated cycles per tile: tensor pipe vs L2->SM traffic vs epilogue, plus a fixed hand-off cost
-        const double mma = static_cast<double>(mt) * k16_total * std::max(n_tile / 2.0, 16.0);
+        // one 128 x n_tile x 16 MMA: tensor pipe n_tile / 2 cycles, operand fetch (4 KB + n_tile * 32 B) at 128 B/clk
+        const double mma = static_cast<double>(mt) * k16_total * std::max(n_tile / 2.0, 32.0 + n_tile / 4.0);
         const double l2 = (static_cast<double>(p.box_bytes) * slabs * (mode == 2 ? taps : 1) +
                            (resident ? 0.0 : static_cast<double>(wbytes) / n_tiles)) / 48.0;
         const int groups = (n_tile + 15) / 16;
         const int active = mt == 2 ? 2 * std::min(2, groups) : std::min(4, groups);
-        const double epi = (static_cast<double>(mt) * groups / active) * 350.0 + 350.0;
-        const double per_tile = std::max(mma, std::max(l2, epi)) + 250.0;
+        // measured on B200 (clock64 traces): TMA epilogue ~35 cycles per column per thread + ~600, generic ~3x that
+        const double epi_cyc = epi ? (static_cast<double>(mt) * groups / active) * 550.0 + 600.0
+                                   : (static_cast<double>(mt) * groups / active) * 1000.0 + 1700.0;
+        double per_tile = std::max(mma, std::max(l2, epi_cyc)) + 250.0;
+        // shallow rings serialise producer, MMA and epilogue
+        if (window && p.sa < 3) per_tile *= 1.6;
+        if (epi && res_mode && p.nres < 2) per_tile *= 2.0;
         p.cost = static_cast<double>(p.tiles) * n_tiles * per_tile;
         p.ok = true;
         if (!best.ok || p.cost < best.cost) best = p;
       }
     }
+  }
+  if (epi && (!best.ok || static_cast<double>(pixels) / (static_cast<double>(best.tiles) * 128 * best.mt) < 0.6)) {
+    epi = false;  // row-aligned tiles waste too much here: generic epilogue, linear raster
+    goto plan;
   }
   if (mode == 0) {
     // junk raster positions must not eat the gain: tiny feature maps go through im2col loads instead
@@ -785,6 +1053,7 @@ plan:
   a.out = L.out; a.out_img_stride = L.out_img_stride; a.out_cstride = L.out_cstride; a.out_coff = L.out_coff; a.out_f32 = L.out_f32;
   a.res = L.res; a.res_img_stride = L.res_img_stride; a.res_cstride = L.res_cstride; a.res_coff = L.res_coff; a.res_mode = res_mode;
   a.act = L.act;
+  a.trace = L.trace;
   a.out_s2d = (window && L.out_s2d) ? 1 : 0;
   a.batch = L.batch; a.batch_dev = L.batch_dev;
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n_tile >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
@@ -798,15 +1067,35 @@ plan:
   a.stage_pitch = stage_pitch;
   a.res_pitch = res_pitch;
   a.off_res = a.off_stage + a.tm * stage_pitch;
+  a.th = window ? best.tstep / best.rw : 0;
+  if (epi) {
+    a.off_stage = (a.off_stage + 1023) / 1024 * 1024;
+    a.nstage = best.nstage;
+    a.off_res = a.off_stage + best.nstage * best.stage_buf;
+    a.stage_buf_bytes = best.stage_buf;
+    a.nres = best.nres;
+    a.pieces = piece_ch[1] ? 2 : 1;
+    const int rows_c = window ? a.th * best.tw : a.tm;
+    uint32_t off = 0;
+    a.res_tx_bytes = 0;
+    for (int q = 0; q < 2; ++q) {
+      a.piece_ch[q] = piece_ch[q];
+      a.piece_off[q] = off;
+      off += static_cast<uint32_t>((static_cast<size_t>(rows_c) * piece_ch[q] * 2 + 1023) / 1024 * 1024);
+      a.res_tx_bytes += static_cast<uint32_t>(rows_c) * piece_ch[q] * 2;
+    }
+  }
   a.inv_rw = 1.0f / static_cast<float>(best.rw);
   a.flat = (mode != 0 && L.out_img_stride == static_cast<long long>(a.hw) * L.out_cstride &&
             (!res_mode || L.res_img_stride == static_cast<long long>(a.hw) * L.res_cstride)) ? 1 : 0;
-  a.res_direct = (res_mode != 0 && !res_staged) ? 1 : 0;
-  const size_t smem = a.off_stage + static_cast<size_t>(a.tm) * (stage_pitch + (res_staged ? res_pitch : 0));
+  a.res_direct = (!epi && res_mode != 0 && !res_staged) ? 1 : 0;
+  const size_t smem = epi ? a.off_stage + static_cast<size_t>(best.stage_buf) * (best.nstage + best.nres)
+                          : a.off_stage + static_cast<size_t>(a.tm) * (stage_pitch + (res_staged ? res_pitch : 0));
   if (smem > SMEM_LIMIT) return 0;
 
-  alignas(64) CUtensorMap tmap;
-  std::memset(&tmap, 0, sizeof(tmap));
+  alignas(64) WinMaps maps;
+  std::memset(&maps, 0, sizeof(maps));
+  CUtensorMap& tmap = maps.in;
   const CUtensorMapSwizzle sw = slab == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (slab == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   void* base = const_cast<__nv_bfloat16*>(L.in) + L.in_coff;
   CUresult cr;
@@ -817,7 +1106,7 @@ plan:
                                    static_cast<cuuint64_t>(L.h) * L.w * L.in_cstride * 2};
     const cuuint32_t box[4] = {static_cast<cuuint32_t>(slab), static_cast<cuuint32_t>(best.rw), static_cast<cuuint32_t>(best.bh), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+    cr = get_encode_tiled()(&maps.in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else if (mode == 2) {
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(pc.cin_pad), static_cast<cuuint64_t>(L.w), static_cast<cuuint64_t>(L.h),
@@ -828,7 +1117,7 @@ plan:
     const int lower[2] = {-pad, -pad};
     const int upper[2] = {pad - (pc.ksize - 1), pad - (pc.ksize - 1)};
     const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(pc.stride), static_cast<cuuint32_t>(pc.stride), 1};
-    cr = get_encode_im2col()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, lower, upper, static_cast<cuuint32_t>(slab),
+    cr = get_encode_im2col()(&maps.in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, lower, upper, static_cast<cuuint32_t>(slab),
                              128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
@@ -836,7 +1125,7 @@ plan:
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(L.in_cstride) * 2};
     const cuuint32_t box[2] = {static_cast<cuuint32_t>(slab), static_cast<cuuint32_t>(a.tm)};
     const cuuint32_t estr[2] = {1, 1};
-    cr = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+    cr = get_encode_tiled()(&maps.in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (cr != CUDA_SUCCESS) {
@@ -844,7 +1133,48 @@ plan:
     return 0;
   }
 
-  WinKernelFn kernel = pick_kernel(slab, mode, best.mt, L.act);
+  if (epi) {
+    // output / residual boxes: [piece channels][tw columns][th rows][1 image] of the NHWC tensor (channel slice)
+    for (int q = 0; q < a.pieces && cr == CUDA_SUCCESS; ++q) {
+      const int pb = piece_ch[q] * 2;
+      const CUtensorMapSwizzle psw = pb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (pb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+      if (!window) {
+        // flat: [piece channels][128 MT pixels] of the [pixels][cstride] matrix
+        const cuuint64_t fd[2] = {static_cast<cuuint64_t>(pc.cout), static_cast<cuuint64_t>(pixels)};
+        const cuuint32_t fb[2] = {static_cast<cuuint32_t>(piece_ch[q]), static_cast<cuuint32_t>(a.tm)};
+        const cuuint32_t fe[2] = {1, 1};
+        const cuuint64_t fos[1] = {static_cast<cuuint64_t>(L.out_cstride) * 2};
+        cr = get_encode_tiled()(&maps.out[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, static_cast<__nv_bfloat16*>(L.out) + L.out_coff, fd, fos, fb, fe,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, psw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr == CUDA_SUCCESS && res_mode) {
+          const cuuint64_t frs[1] = {static_cast<cuuint64_t>(L.res_cstride) * 2};
+          cr = get_encode_tiled()(&maps.res[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(L.res) + L.res_coff, fd, frs, fb,
+                                  fe, CU_TENSOR_MAP_INTERLEAVE_NONE, psw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        continue;
+      }
+      const cuuint32_t box[4] = {static_cast<cuuint32_t>(piece_ch[q]), static_cast<cuuint32_t>(best.tw), static_cast<cuuint32_t>(a.th), 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      const cuuint64_t odims[4] = {static_cast<cuuint64_t>(pc.cout), static_cast<cuuint64_t>(L.wo), static_cast<cuuint64_t>(L.ho),
+                                   static_cast<cuuint64_t>(L.batch)};
+      const cuuint64_t ostr[3] = {static_cast<cuuint64_t>(L.out_cstride) * 2, static_cast<cuuint64_t>(L.wo) * L.out_cstride * 2,
+                                  static_cast<cuuint64_t>(L.out_img_stride) * 2};
+      cr = get_encode_tiled()(&maps.out[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, static_cast<__nv_bfloat16*>(L.out) + L.out_coff, odims, ostr,
+                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, psw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr == CUDA_SUCCESS && res_mode) {
+        const cuuint64_t rstr[3] = {static_cast<cuuint64_t>(L.res_cstride) * 2, static_cast<cuuint64_t>(L.wo) * L.res_cstride * 2,
+                                    static_cast<cuuint64_t>(L.res_img_stride) * 2};
+        cr = get_encode_tiled()(&maps.res[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(L.res) + L.res_coff, odims, rstr,
+                                box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, psw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+    }
+    if (cr != CUDA_SUCCESS)
+      return fail(AICAM_ERR_CUDA, "conv_win: cuTensorMapEncodeTiled (epilogue) failed with " + std::to_string(static_cast<int>(cr)));
+  }
+  WinKernelFn kernel = pick_kernel(slab, mode, best.mt, L.act, epi ? 1 : 0);
   {
     static std::vector<WinKernelFn> configured;  // opt in to > 48 KB of dynamic shared memory once per instantiation
     if (std::find(configured.begin(), configured.end(), kernel) == configured.end()) {
@@ -862,7 +1192,7 @@ plan:
   dim3 grid(static_cast<unsigned>(std::min<long long>(total_tiles, num_sms)));
   size_t slot = 0;
   const bool prof = profile_begin(stream, &slot);
-  kernel<<<grid, WIN_THREADS, smem, stream>>>(a, tmap);
+  kernel<<<grid, WIN_THREADS, smem, stream>>>(a, maps);
   if (prof) profile_end(stream, slot);
   count_launch();
   const int rc = last_launch("conv_win_kernel");

@@ -676,13 +676,18 @@ int aicam_conv2d_bench(const aicam_conv_desc* d, int iters, double* mean_ms, voi
     std::vector<long long> h(512);
     cudaMemcpy(h.data(), tr, 512 * 8, cudaMemcpyDeviceToHost);
     cudaFree(tr);
-    const long long t0 = h[0];
-    printf("trace (cycles since first gather): kb: gather_start gather_issued mma_ready mma_committed\n");
-    for (int k = 0; k < 30 && h[k * 4]; ++k)
-      printf("  kb %2d: %7lld %7lld %7lld %7lld\n", k, h[k * 4] - t0, h[k * 4 + 1] - t0, h[k * 4 + 2] - t0, h[k * 4 + 3] - t0);
-    for (int t = 0; t < 4 && h[240 + t * 4]; ++t)
-      printf("  tile %d epilogue: start %7lld tmem_read_done %7lld stores_done %7lld\n", t, h[240 + t * 4] - t0,
-             h[240 + t * 4 + 1] - t0, h[240 + t * 4 + 2] - t0);
+    long long t0 = 0;
+    for (int k = 0; k < 512 && !t0; ++k) t0 = h[k];
+    for (int k = 0; k < 512; ++k) if (h[k] && h[k] < t0) t0 = h[k];
+    printf("trace of CTA 0, cycles since its first stamp; per tile: MMA[wait_acc_empty acc_empty_ok a_full_ok issued] "
+           "PROD[wait_a_empty a_empty_ok] EPI[wait_acc_full acc_full_ok barA res_ok finished barB]\n");
+    for (int t = 0; t < 24; ++t) {
+      const long long* r = h.data() + t * 16;
+      if (!r[8] && !r[0]) break;
+      auto rel = [&](long long v) { return v ? v - t0 : -1ll; };
+      printf("  tile %2d  MMA %7lld %7lld %7lld %7lld  PROD %7lld %7lld  EPI %7lld %7lld %7lld %7lld %7lld %7lld\n", t, rel(r[0]),
+             rel(r[1]), rel(r[2]), rel(r[3]), rel(r[4]), rel(r[5]), rel(r[8]), rel(r[9]), rel(r[10]), rel(r[11]), rel(r[12]), rel(r[13]));
+    }
     fflush(stdout);
   }
   cudaEvent_t e0, e1;
