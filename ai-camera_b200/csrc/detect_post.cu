@@ -28,57 +28,76 @@ constexpr int NMS_THREADS = 1024;
 constexpr int MAX_CAND = 2048;
 constexpr int MAX_SORT = 16384;
 
-// ---- decode: one warp per anchor -------------------------------------------------------------
+// ---- decode: four threads per anchor ---------------------------------------------------------
+// Thread k of an anchor owns DFL side k (l, t, r, b: 16 logits = four 16-byte loads) and a quarter of the
+// class logits; a warp reads 8 consecutive head rows (8 x 576 B, every sector fully used).  The softmax
+// expectation is a register loop (no shuffles); two shuffle rounds merge the class argmax
+// (lowest index on ties) and gather the four distances.
 __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ head, int anchors, int nc, int total,
                                                      float* __restrict__ boxes, float* __restrict__ scores,
                                                      int* __restrict__ labels) {
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (gw >= total) return;
-  const int a = gw % anchors;
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int k = static_cast<int>(t & 3);
+  const int gw_raw = static_cast<int>(t >> 2);
+  const bool live = gw_raw < total;
+  const int gw = live ? gw_raw : total - 1;  // tail lanes recompute the last anchor (the shuffles need a full warp)
   const float* row = head + static_cast<long long>(gw) * (AICAM_HEAD_DFL + nc);
-  // DFL: lanes 0-15 / 16-31 hold one side each; two loads cover l,t then r,b
-  float dist[2];
+  float v[16];
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const float v = __ldg(row + 32 * k + lane);
-    float m = v;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    const float e = expf(v - m);
-    float s = e, ws = e * static_cast<float>(lane & 15);
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      ws += __shfl_xor_sync(0xffffffffu, ws, o);
-    }
-    dist[k] = ws / s;
+  for (int i = 0; i < 4; ++i) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(row + 16 * k) + i);
+    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
   }
-  const float l = __shfl_sync(0xffffffffu, dist[0], 0), t = __shfl_sync(0xffffffffu, dist[0], 16);
-  const float r = __shfl_sync(0xffffffffu, dist[1], 0), b = __shfl_sync(0xffffffffu, dist[1], 16);
-  // best class (lowest index on ties)
+  float m = v[0];
+#pragma unroll
+  for (int i = 1; i < 16; ++i) m = fmaxf(m, v[i]);
+  float s = 0.0f, ws = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float e = expf(v[i] - m);
+    s += e;
+    ws += e * static_cast<float>(i);
+  }
+  const float dist = ws / s;
+  // best class of my quarter (ascending scan with a strict compare keeps the lowest index on ties)
+  const int per = ((nc + 3) / 4 + 3) / 4 * 4;
+  const int c_lo = min(nc, k * per), c_hi = min(nc, c_lo + per);
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int c = lane; c < nc; c += 32) {
-    const float v = __ldg(row + AICAM_HEAD_DFL + c);
-    if (v > best) { best = v; bi = c; }
+  const float* cls = row + AICAM_HEAD_DFL;
+  if ((nc & 3) == 0) {
+    for (int c = c_lo; c < c_hi; c += 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(cls + c));
+      if (q.x > best) { best = q.x; bi = c; }
+      if (q.y > best) { best = q.y; bi = c + 1; }
+      if (q.z > best) { best = q.z; bi = c + 2; }
+      if (q.w > best) { best = q.w; bi = c + 3; }
+    }
+  } else {
+    for (int c = c_lo; c < c_hi; ++c) {
+      const float q = __ldg(cls + c);
+      if (q > best) { best = q; bi = c; }
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = 1; o <= 2; o <<= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, best, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
   }
-  if (lane == 0) {
+  const int base = threadIdx.x & 28;  // lane of side 0 of my anchor
+  const float l = __shfl_sync(0xffffffffu, dist, base), tt = __shfl_sync(0xffffffffu, dist, base + 1);
+  const float r = __shfl_sync(0xffffffffu, dist, base + 2), b = __shfl_sync(0xffffffffu, dist, base + 3);
+  if (k == 0 && live) {
     // anchor geometry for a 640x640 input: levels of 80^2, 40^2, 20^2 cells
-    int idx = a, gridw = AICAM_YOLO_INPUT / 8;
+    int idx = gw % anchors, gridw = AICAM_YOLO_INPUT / 8;
     float stride = 8.0f;
     if (idx >= gridw * gridw) {
       idx -= gridw * gridw; gridw = AICAM_YOLO_INPUT / 16; stride = 16.0f;
       if (idx >= gridw * gridw) { idx -= gridw * gridw; gridw = AICAM_YOLO_INPUT / 32; stride = 32.0f; }
     }
     const float ax = static_cast<float>(idx % gridw) + 0.5f, ay = static_cast<float>(idx / gridw) + 0.5f;
-    float4 box = make_float4((ax - l) * stride, (ay - t) * stride, (ax + r) * stride, (ay + b) * stride);
+    float4 box = make_float4((ax - l) * stride, (ay - tt) * stride, (ax + r) * stride, (ay + b) * stride);
     reinterpret_cast<float4*>(boxes)[gw] = box;
     scores[gw] = 1.0f / (1.0f + expf(-best));
     labels[gw] = bi;
@@ -285,7 +304,9 @@ int aicam_decode(const float* head, int batch, int anchors, int nc, float* boxes
   if (anchors != 8400) return fail(AICAM_ERR_UNSUPPORTED, "decode: only the 640x640 anchor grid (8400) is supported");
   if (batch == 0) return AICAM_OK;
   const int total = batch * anchors;
-  decode_kernel<<<cdiv(total * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(head, anchors, nc, total, boxes,
+  if ((AICAM_HEAD_DFL + nc) % 4 != 0 || reinterpret_cast<uintptr_t>(head) % 16 != 0)
+    return fail(AICAM_ERR_INVALID_ARG, "decode: head rows must be 16-byte aligned");
+  decode_kernel<<<cdiv(total * 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(head, anchors, nc, total, boxes,
                                                                                     scores, labels);
   count_launch();
   return last_launch("decode_kernel");
