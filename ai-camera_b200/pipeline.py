@@ -103,6 +103,10 @@ class BatchTracker:
         self.out_conf = torch.zeros((S, max_tracks), dtype=torch.float32, device=dev)
         self.out_count = torch.zeros(S, **i32)
         self._mask = config.tracked_class_mask()
+        # optional running totals (crops, reported tracks) kept on the device, for benchmarks: no host sync
+        self.count_stats = False
+        self.crop_total = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.track_total = torch.zeros(1, dtype=torch.int64, device=dev)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -133,6 +137,9 @@ class BatchTracker:
                 self._h, _lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(labels), self.K, _lib.ptr(self.det_index),
                 _lib.ptr(self.det_count), _lib.ptr(self.crop_slot), _lib.ptr(self.feats), _lib.ptr(self.out_tracks),
                 _lib.ptr(self.out_conf), _lib.ptr(self.out_count), st))
+            if self.count_stats:
+                self.crop_total += self.crop_count
+                self.track_total += self.out_count.sum()
         return self.out_tracks, self.out_conf, self.out_count
 
     def overflow(self):

@@ -17,6 +17,11 @@ import torch
 from . import config, weights
 
 
+def blob_dir():
+    """Cache directory of the synthetic weight blobs (outside gpurun_out/: ~57 MB that need not travel back)."""
+    return os.environ.get("AICAM_BLOB_DIR", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), ".blobs"))
+
+
 def make_blobs(directory, scale="n", yolo_seed=0, reid_seed=1):
     """Write the two synthetic weight blobs (if absent) and return their paths."""
     os.makedirs(directory, exist_ok=True)

@@ -114,7 +114,7 @@ def run_reference(args):
         return
     import torch  # noqa: F401
     from ai_camera_b200 import synth
-    yolo, reid = synth.make_blobs(os.path.join(ROOT, "gpurun_out", "blobs"))
+    yolo, reid = synth.make_blobs(synth.blob_dir())
     bias = synth.shifted_class_bias(yolo)
     n_sample = 2  # streams sampled per step (a bounded sample of the 64-stream batch)
     video = synth.SynthVideo(n_sample, FRAME_HW, n_frames=6, device="cpu")
@@ -164,7 +164,7 @@ def main():
     from ai_camera_b200.pipeline import TrackingPipeline
     lib = _lib.load()
     S = args.streams
-    blob_dir = os.path.join(ROOT, "gpurun_out", "blobs")
+    blob_dir = synth.blob_dir()
     if rank == 0:
         synth.make_blobs(blob_dir)
     if world > 1:
@@ -191,6 +191,7 @@ def main():
         step_no[0] += 1
         return out
 
+    pipe.tracker.count_stats = True  # device-side totals of crops / reported tracks (two tiny torch adds per step)
     for _ in range(args.warmup):
         one_step()
     torch.cuda.synchronize(dev)
@@ -226,6 +227,8 @@ def main():
         sampler.start()
     launches0 = lib.aicam_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    pipe.tracker.crop_total.zero_()
+    pipe.tracker.track_total.zero_()
     sync_all()
     ev[0].record()
     for k in range(args.steps):
@@ -238,8 +241,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches_eager = pipe.launches_per_step()
     gpu_launches = (lib.aicam_launch_count() - launches0) if graphs is None else launches_eager * args.steps
-    crops_per_step = float(pipe.tracker.crop_count.item())
-    tracks_out = int(pipe.tracker.out_count.sum().item())
+    crops_per_step = float(pipe.tracker.crop_total.item()) / args.steps      # mean over the timed steps
+    tracks_out = float(pipe.tracker.track_total.item()) / args.steps
     overflow = int(pipe.tracker.overflow().any())
 
     # ---- end to end: host frames in, track tables out, every step -------------------------
@@ -285,15 +288,24 @@ def main():
 
     # ---- roofline of the convolution kernel (separate, event-instrumented pass) -------------
     lib.aicam_profile_enable(1)
-    prof_steps = 3
+    prof_steps = 6
+    prof_crops = 0.0
     for _ in range(prof_steps):
         one_step()
+        prof_crops += float(pipe.tracker.crop_count.item())  # this step's crops (host sync: profiling pass only)
+    prof_crops /= prof_steps
     ms = _lib.C.c_double()
     nl = _lib.C.c_uint64()
     _lib.check(lib.aicam_profile_conv(_lib.C.byref(ms), _lib.C.byref(nl)))
     lib.aicam_profile_enable(0)
-    flops_step = S * pipe.detector.engine.flops_per_item() + float(pipe.tracker.crop_count.item()) * \
-        pipe.tracker.reid.flops_per_item()
+    flops_step = S * pipe.detector.engine.flops_per_item() + prof_crops * pipe.tracker.reid.flops_per_item()
+    # DRAM bytes of the same kernels for one step, from the committed ncu pass (profiles/r1_step_traffic.json)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_step_traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
     conv_ms_step = ms.value / prof_steps
     peaks = measured_peaks()
     achieved_tflops = flops_step / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step > 0 else 0.0
@@ -313,19 +325,25 @@ def main():
         "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "streams_per_gpu": S, "frame": "1080x1920x3 u8",
-                   "crops_per_step": float(allst[:, 2].mean()), "tracks_reported_last_step": float(allst[:, 3].sum()),
+                   "crops_per_step": float(allst[:, 2].mean()), "tracks_reported_per_step": float(allst[:, 3].mean()),
+                   "detections_per_frame": float(allst[:, 2].mean()) / S,
                    "tracker_overflow": bool(allst[:, 4].any()), "l2": "inputs larger than L2 (398 MB of frames per step)",
                    "cuda_graph": graphs is not None, "detector_logit_shift": delta,
                    "weights": "seeded synthetic (no checkpoints offline)"},
         "p50_latency_ms": statistics.median(per_step),
         "clocks": clocks,
         "e2e": {"value": world * S * e2e_steps / max_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "h2d_gbs": h2d * e2e_steps / max_e2e / 1e9,
+                "note": "raw 1080p frames from pinned host memory, copy double-buffered against compute; "
+                        "bounded by the PCIe host-to-device rate once compute is faster than the copy"},
         "gpu_launches": int(gpu_launches),
-        "roofline": {"kernel": "conv_tc_kernel (all %d launches of a step)" % (nl.value // prof_steps),
+        "roofline": {"kernel": "tcgen05 convolution kernels: conv_win_kernel + reid_stem_pool_kernel + conv_tc_kernel "
+                               "(all %d launches of a step)" % (nl.value // prof_steps),
                      "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16"], "unit": "TFLOP/s",
-                     "frac": achieved_tflops / peaks["bf16"], "traffic": None, "peak_source": peaks["source"],
-                     "kernel_ms_per_step": conv_ms_step, "flops_per_step": flops_step},
+                     "frac": achieved_tflops / peaks["bf16"], "traffic": traffic, "peak_source": peaks["source"],
+                     "kernel_ms_per_step": conv_ms_step, "flops_per_step": flops_step,
+                     "crops_per_profiled_step": prof_crops, "profiled_steps": prof_steps},
     }
     if world == 1 and not args.no_cpu_baseline:
         n_sample, cpu_steps = 2, 3

@@ -16,7 +16,7 @@ from ai_camera_b200.pipeline import TrackingPipeline  # noqa: E402
 
 S = int(os.environ.get("STREAMS", "64"))
 shift = float(os.environ.get("LOGIT_SHIFT", "-0.93"))
-yolo, reid = synth.make_blobs(os.path.join(ROOT, "gpurun_out", "blobs"))
+yolo, reid = synth.make_blobs(synth.blob_dir())
 video = synth.SynthVideo(S, (1080, 1920), n_frames=4, device="cuda:0")
 pipe = TrackingPipeline(yolo, reid, S, "cuda:0", max_tracks=128, max_crops=S * 40)
 for n in synth.CLS_LAYERS:
