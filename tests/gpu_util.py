@@ -182,7 +182,8 @@ class Tracker:
 def run_gpu_tracker(frames, frame_hw=(1080, 1920), feature_dim=512, **kw):
     """Single-stream scenario through the device tracker -> dict in the golden layout."""
     kmax = max(8, max(len(f["boxes"]) for f in frames))
-    trk = Tracker(1, max_tracks=256, max_dets=max(kmax, 8), feature_dim=feature_dim, stride_k=kmax,
+    max_tracks = kw.pop("max_tracks", 256)
+    trk = Tracker(1, max_tracks=max_tracks, max_dets=max(kmax, 8), feature_dim=feature_dim, stride_k=kmax,
                   frame_hw=frame_hw, **kw)
     outs, out_conf, out_off = [], [], [0]
     trk_i, trk_f, trk_off = [], [], [0]

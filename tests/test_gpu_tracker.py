@@ -84,6 +84,16 @@ def test_tracker_matches_oracle_fresh_seeds(seed, n_objects, n_frames):
     assert_same_tracking(G.run_gpu_tracker(frames), run_oracle(frames), "seed %d" % seed)
 
 
+def test_tracker_crowded_scene_300_persons():
+    """BASELINE config 5: 300 persons per frame (ReID batch 300, 300 x 300 association per stream); ids,
+    lifecycle and Kalman state bit-exact against the oracle, gallery growing over the frames."""
+    import gpu_util as G
+    frames = make_scenario(seed=104, n_frames=10, n_objects=300, size_range=(20.0, 90.0))
+    got = G.run_gpu_tracker(frames, max_tracks=512)
+    assert_same_tracking(got, run_oracle(frames), "crowded 300")
+    assert got["trk_off"][-1] - got["trk_off"][-2] >= 300  # at least one live track per person
+
+
 def test_tracker_streams_are_independent():
     """Several streams in one handle give what separate single-stream trackers give."""
     import gpu_util as G
