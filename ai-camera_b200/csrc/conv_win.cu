@@ -551,14 +551,19 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
           xp0 = static_cast<uint32_t>(((r2 % a.tiles_per_strip) * a.tstep) % a.rw);
         }
         if (leader) WIN_TRACE(it, 0);
+        // the first operand stage usually lands long before the epilogue frees the accumulator: poll it first so
+        // that its barrier round trip is off the accumulator -> first MMA path
+        mbar_wait(bar_a_full + 8 * sa, pa);
+        if (leader) WIN_TRACE(it, 2);
         mbar_wait(bar_acc_empty + 8 * buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         if (leader) WIN_TRACE(it, 1);
         const uint32_t d_tmem = tmem0 + buf * acc_cols;
         for (int s = 0; s < a.slabs; ++s) {
-          mbar_wait(bar_a_full + 8 * sa, pa);
-          tc_fence_after();
-          if (leader && s == 0) WIN_TRACE(it, 2);
+          if (s > 0) {
+            mbar_wait(bar_a_full + 8 * sa, pa);
+            tc_fence_after();
+          }
           // descriptor low word of the patch at raster position xp0: start >> 4 | LBO (unused, 1)
           const uint32_t a_lo0 = ((a_ring + sa * a.patch_bytes) >> 4) + xp0 * (ROW_BYTES >> 4) + (1u << 16);
           uint32_t w_lo = ((w_base >> 4) + static_cast<uint32_t>(s * SLAB >> 3) * lbo) | b_lo_flags;

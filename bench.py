@@ -346,8 +346,8 @@ def main():
                      "crops_per_profiled_step": prof_crops, "profiled_steps": prof_steps},
     }
     if world == 1 and not args.no_cpu_baseline:
-        n_sample, cpu_steps = 2, 3
-        frames = [[video.ring[t, s].cpu().numpy() for t in range(4)] for s in range(n_sample)]
+        n_sample, cpu_steps = 8, 16  # ~10 s of host work: a bounded sample of the 64-stream workload
+        frames = [[video.ring[t, s].cpu().numpy() for t in range(min(RING, 8))] for s in range(n_sample)]
         fps, dt, cores = cpu_baseline_run(yolo, reid, bias, frames, cpu_steps, warmup=1)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": "%d streams x %d steps of the same 1080p frames (%.1f s)" % (n_sample, cpu_steps, dt)}
