@@ -64,6 +64,8 @@ SIGNATURES = {
     "aicam_yolo_forward_s2d": (_I, [_P, _P, _I, _P, _P]),
     "aicam_engine_accepts_s2d": (_I, [_P]),
     "aicam_reid_forward": (_I, [_P, _P, _I, _P, _P, _P]),
+    "aicam_reid_forward_nhwc8": (_I, [_P, _P, _I, _P, _P, _P]),
+    "aicam_engine_accepts_nhwc8": (_I, [_P]),
     "aicam_nchw_to_nhwc4": (_I, [_P, _I, _I, _I, _P, _P]),
     "aicam_conv2d": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "aicam_conv2d_bench": (_I, [C.POINTER(ConvDesc), _I, C.POINTER(C.c_double), _P]),

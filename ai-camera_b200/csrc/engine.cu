@@ -316,8 +316,10 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
     __nv_bfloat16* dst = e->buffers[e->s2d_in].ptr;
     if (int rc = launch_space_to_depth(static_cast<const __nv_bfloat16*>(input), batch, e->in_h, e->in_w, 4, dst, stream)) return rc;
     input_s2d = dst;
-  } else if (e->s2d_in < 0 && input_is_s2d) {
+  } else if (e->s2d_in < 0 && input_is_s2d && e->kind == AICAM_KIND_YOLOV8) {
     return fail(AICAM_ERR_UNSUPPORTED, "engine: this engine was built without the space-to-depth stem");
+  } else if (e->kind == AICAM_KIND_REID && input_is_s2d && e->stem_in8 < 0) {
+    return fail(AICAM_ERR_UNSUPPORTED, "engine: this engine was built without the fused NHWC8 stem");
   }
   for (const Op& op : e->ops) {
     auto geom = [&](const View& v, int fallback_c, const __nv_bfloat16** ptr, long long* img_stride, int* cstride) {
@@ -381,8 +383,12 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
         break;
       case Op::STEMPOOL: {
         geom(op.out, 0, &op_, &os, &oc);
-        __nv_bfloat16* in8 = e->buffers[e->stem_in8].ptr;
-        rc = launch_nhwc4_to_nhwc8(ip, batch, op.h, op.w, in8, n_dev, stream);
+        const __nv_bfloat16* in8 = ip;  // caller-provided NHWC8 crops ...
+        if (!input_is_s2d) {             // ... or an NHWC4 tensor repacked here
+          __nv_bfloat16* tmp = e->buffers[e->stem_in8].ptr;
+          rc = launch_nhwc4_to_nhwc8(ip, batch, op.h, op.w, tmp, n_dev, stream);
+          in8 = tmp;
+        }
         if (!rc) rc = launch_stem_pool(e->stem, in8, batch, op.h, op.w, n_dev, const_cast<__nv_bfloat16*>(op_), stream);
         break;
       }
@@ -527,6 +533,15 @@ int aicam_yolo_forward_s2d(aicam_engine* e, const void* in_s2d16, int batch, flo
 }
 
 int aicam_engine_accepts_s2d(const aicam_engine* e) { return e && e->s2d_in >= 0 ? 1 : 0; }
+
+int aicam_engine_accepts_nhwc8(const aicam_engine* e) { return e && e->kind == AICAM_KIND_REID && e->stem_in8 >= 0 ? 1 : 0; }
+
+int aicam_reid_forward_nhwc8(aicam_engine* e, const void* crops_nhwc8, int n, const int32_t* n_dev, float* feats, void* stream) {
+  if (!e || e->kind != AICAM_KIND_REID) return fail(AICAM_ERR_INVALID_ARG, "reid_forward_nhwc8: not a reid engine");
+  if (!crops_nhwc8 || !feats || !n_dev) return fail(AICAM_ERR_INVALID_ARG, "reid_forward_nhwc8: null tensor (a device-side count is required)");
+  if (n < 0 || n > e->max_batch) return fail(AICAM_ERR_CAPACITY, "reid_forward_nhwc8: capacity exceeds max_batch");
+  return run_ops(e, crops_nhwc8, n, feats, static_cast<cudaStream_t>(stream), n_dev, true);
+}
 
 int aicam_reid_forward(aicam_engine* e, const void* crops_nhwc4, int n, const int32_t* n_dev, float* feats,
                        void* stream) {

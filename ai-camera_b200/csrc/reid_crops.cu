@@ -12,7 +12,7 @@
 // the same double -> float -> 11-bit rounding steps (explicit _rn intrinsics; the file is also
 // compiled with --fmad=false), then every thread interpolates its pixels.  Result: the uint8
 // resized crop, and therefore the float tensor, equals the reference's bit for bit.
-// HBM-bound: reads ~crop bytes, writes 128*64*8 B (NHWC4 bf16) per crop.
+// HBM-bound: reads ~crop bytes, writes 128*64*8 B (NHWC4 bf16) or 128*64*16 B (NHWC8, what the fused ReID stem reads) per crop.
 #include "common.cuh"
 
 namespace aicam {
@@ -175,11 +175,14 @@ __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ f
     if (FORMAT == 0) {
       float* o = static_cast<float*>(out) + static_cast<long long>(slot) * 3 * RH * RW + p;
       o[0] = rgb[0]; o[RH * RW] = rgb[1]; o[2 * RH * RW] = rgb[2];
-    } else {
+    } else if (FORMAT == 1) {
       uint2 q;
       q.x = pack_bf16x2(rgb[0], rgb[1]);
       q.y = pack_bf16x2(rgb[2], 0.0f);
       reinterpret_cast<uint2*>(out)[static_cast<long long>(slot) * RH * RW + p] = q;
+    } else {  // NHWC8: one pixel = one 16-byte K chunk of the fused ReID stem (stem_pool.cu)
+      reinterpret_cast<uint4*>(out)[static_cast<long long>(slot) * RH * RW + p] =
+          make_uint4(pack_bf16x2(rgb[0], rgb[1]), pack_bf16x2(rgb[2], 0.0f), 0u, 0u);
     }
   }
 }
@@ -196,7 +199,7 @@ extern "C" int aicam_reid_crops(const uint8_t* frames, int batch, int h, int w, 
                                 void* crops, int32_t* crop_count, void* stream) {
   if (!boxes || !scores || !labels || !num_dets || !det_index || !det_count || !crop_slot || !crop_rect || !crop_count)
     return fail(AICAM_ERR_INVALID_ARG, "reid_crops: null argument");
-  if (batch < 0 || stride_k <= 0 || h <= 0 || w <= 0 || max_crops < 0 || (format != 0 && format != 1))
+  if (batch < 0 || stride_k <= 0 || h <= 0 || w <= 0 || max_crops < 0 || (format < 0 || format > 2))
     return fail(AICAM_ERR_INVALID_ARG, "reid_crops: bad shape arguments");
   if (reinterpret_cast<uintptr_t>(boxes) % 16) return fail(AICAM_ERR_INVALID_ARG, "reid_crops: boxes must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -208,8 +211,10 @@ extern "C" int aicam_reid_crops(const uint8_t* frames, int batch, int h, int w, 
   if (max_crops == 0 || !frames || !crops) return AICAM_OK;  // filter only
   if (format == 0)
     crop_kernel<0><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
-  else
+  else if (format == 1)
     crop_kernel<1><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
+  else
+    crop_kernel<2><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
   count_launch();
   return last_launch("crop_kernel");
 }

@@ -96,7 +96,10 @@ class BatchTracker:
         self.crop_slot = torch.zeros((S, K), **i32)
         self.crop_rect = torch.zeros((self.max_crops, 5), **i32)
         self.crop_count = torch.zeros(1, **i32)
-        self.crops = torch.zeros((self.max_crops, config.REID_INPUT_SHAPE[0], config.REID_INPUT_SHAPE[1], 4),
+        # crops go straight into the layout the engine's first kernel reads (NHWC8 for the fused stem)
+        self._nhwc8 = bool(self.lib.aicam_engine_accepts_nhwc8(self.reid.handle))
+        self.crops = torch.zeros((self.max_crops, config.REID_INPUT_SHAPE[0], config.REID_INPUT_SHAPE[1],
+                                  8 if self._nhwc8 else 4),
                                  dtype=torch.bfloat16, device=dev)
         self.feats = torch.zeros((self.max_crops, self.F), dtype=torch.float32, device=dev)
         self.out_tracks = torch.zeros((S, max_tracks, 6), **i32)
@@ -128,11 +131,13 @@ class BatchTracker:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.aicam_reid_crops(
                 _lib.ptr(frames), S, h, w, _lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(labels), _lib.ptr(num_dets),
-                self.K, self.min_conf, self._mask[0], self._mask[1], 1, self.max_crops, _lib.ptr(self.det_index),
+                self.K, self.min_conf, self._mask[0], self._mask[1], 2 if self._nhwc8 else 1, self.max_crops,
+                _lib.ptr(self.det_index),
                 _lib.ptr(self.det_count), _lib.ptr(self.crop_slot), _lib.ptr(self.crop_rect), _lib.ptr(self.crops),
                 _lib.ptr(self.crop_count), st))
-            _lib.check(self.lib.aicam_reid_forward(self.reid.handle, _lib.ptr(self.crops), self.max_crops,
-                                                   _lib.ptr(self.crop_count), _lib.ptr(self.feats), st))
+            fwd = self.lib.aicam_reid_forward_nhwc8 if self._nhwc8 else self.lib.aicam_reid_forward
+            _lib.check(fwd(self.reid.handle, _lib.ptr(self.crops), self.max_crops, _lib.ptr(self.crop_count),
+                           _lib.ptr(self.feats), st))
             _lib.check(self.lib.aicam_tracker_step(
                 self._h, _lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(labels), self.K, _lib.ptr(self.det_index),
                 _lib.ptr(self.det_count), _lib.ptr(self.crop_slot), _lib.ptr(self.feats), _lib.ptr(self.out_tracks),
@@ -158,7 +163,7 @@ class BatchTracker:
         return ints[:n], floats[:n]
 
     def launches_per_step(self):
-        return 2 + self.reid.launches_per_forward() + 3
+        return 2 + self.reid.launches_per_forward() - (1 if self._nhwc8 else 0) + 3  # no NHWC8 repack kernel
 
 
 class TrackingPipeline:

@@ -93,6 +93,12 @@ int aicam_engine_accepts_s2d(const aicam_engine* e);
  *                 reid_model.py:126) */
 int aicam_reid_forward(aicam_engine* e, const void* crops_nhwc4, int n, const int32_t* n_dev,
                        float* feats, void* stream);
+/* Same network, crops already NHWC8 (aicam_reid_crops format 2: bf16 [n][128][64][8] = R, G, B + five zero
+ * channels, one pixel = one 16-byte K chunk of the fused stem); n is the capacity, the count is read from n_dev.
+ * aicam_engine_accepts_nhwc8: 1 when the engine was built with the fused stem. */
+int aicam_reid_forward_nhwc8(aicam_engine* e, const void* crops_nhwc8, int n, const int32_t* n_dev,
+                             float* feats, void* stream);
+int aicam_engine_accepts_nhwc8(const aicam_engine* e);
 
 /* Reference-layout converters used by the TRTEngine-shaped facade:
  * fp32 NCHW [n][3][h][w] -> bf16 NHWC4 [n][h][w][4]. */
@@ -178,6 +184,7 @@ int aicam_nms(const float* boxes, const float* scores, const int32_t* labels, in
  *               or -1 when the crop rectangle is empty (feature None, :155-158)
  *   crops     : format 0: fp32 [max_crops][3][128][64] (reference tensor, bit-exact)
  *               format 1: bf16 [max_crops][128][64][4]
+ *               format 2: bf16 [max_crops][128][64][8] (what aicam_reid_forward_nhwc8 consumes)
  *   crop_rect : i32 [max_crops][5] out: frame index, x1, y1, x2, y2 (int()-truncated, clamped)
  *   crop_count: i32 [1] total crops written (<= max_crops; crops beyond capacity are dropped
  *               and their crop_slot is -1)

@@ -42,8 +42,9 @@ def test_crops_bit_exact_and_filter():
     crop_count = torch.zeros(1, dtype=torch.int32, device=G.DEV)
     crops0 = torch.zeros((cap, 3, 128, 64), dtype=torch.float32, device=G.DEV)
     crops1 = torch.zeros((cap, 128, 64, 4), dtype=torch.bfloat16, device=G.DEV)
+    crops2 = torch.full((cap, 128, 64, 8), 7.0, dtype=torch.bfloat16, device=G.DEV)  # NHWC8 for the fused stem
     lo, hi = tracked_class_mask()
-    for fmt, crops in ((0, crops0), (1, crops1)):
+    for fmt, crops in ((0, crops0), (1, crops1), (2, crops2)):
         G.check(G.lib().aicam_reid_crops(G.ptr(fd), B, H, W, G.ptr(bd), G.ptr(sd), G.ptr(ld), G.ptr(nd), K, 0.3, lo, hi,
                                          fmt, cap, G.ptr(det_index), G.ptr(det_count), G.ptr(crop_slot), G.ptr(crop_rect),
                                          G.ptr(crops), G.ptr(crop_count), None))
@@ -65,5 +66,7 @@ def test_crops_bit_exact_and_filter():
             assert np.array_equal(crops0[row].cpu().numpy().view(np.uint32), want.view(np.uint32)), (b, i, r)
             wb = torch.from_numpy(want).to(torch.bfloat16).float().numpy().transpose(1, 2, 0)
             assert np.array_equal(crops1[row].float().cpu().numpy()[..., :3], wb)
+            c2 = crops2[row].float().cpu().numpy()
+            assert np.array_equal(c2[..., :3], wb) and not c2[..., 3:].any()
             row += 1
     assert cc == row
