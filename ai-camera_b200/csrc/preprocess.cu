@@ -13,9 +13,13 @@
 // the reference's bit for bit.  Taps with a zero weight are not loaded: for 1080p (exact 3:1)
 // the kernel touches one source pixel per output pixel, 360 of the 1080 rows.
 //
+// Pure-decimation geometries (1080p -> 640 x 360 is exactly 3:1) take a row-staged path: 128-bit coalesced loads
+// of each touched source row into shared memory, byte picks from there (preprocess_rows_kernel).
+//
 // HBM-bound.  Algorithmic bytes per 1080p frame: 360 rows x 5760 B read + 640*640*8 B written
 // (NHWC4 bf16) = 5 350 400 B   (format 0, fp32 NCHW: 2 073 600 + 4 915 200 B).
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -31,6 +35,7 @@ namespace {
 constexpr int S = AICAM_YOLO_INPUT;
 
 struct Geometry {
+  int decimate;  // every output pixel is exactly ONE source pixel (integer-ratio resize or copy): row-staged fast path
   int mode;  // 0 bilinear, 1 exact 2x box average, 2 copy
   int new_h, new_w, top, left;
   // device tables: x: sx0, sx1, a0, a1 (new_w each); y: sy0, sy1, b0, b1 (new_h each)
@@ -105,6 +110,15 @@ int get_geometry(int h, int w, Geometry* out) {
       b1(g.new_h);
   axis_tables(w, g.new_w, true, x0, x1, a0, a1);
   axis_tables(h, g.new_h, false, y0, y1, b0, b1);
+  // pure decimation: all second taps have weight 0 (e.g. 1080p -> 640 x 360 is exactly 3:1, the bilinear sample
+  // point falls on a source pixel centre), so cv2's fixed-point formula returns the source byte itself
+  g.decimate = g.mode != 1;
+  for (int d = 0; d < g.new_w && g.decimate; ++d) g.decimate = (a1[d] == 0 && a0[d] == 2048) || g.mode == 2;
+  for (int d = 0; d < g.new_h && g.decimate; ++d) g.decimate = (b1[d] == 0 && b0[d] == 2048) || g.mode == 2;
+  if (g.mode == 2) {  // copy: identity tables
+    for (int d = 0; d < g.new_w; ++d) x0[d] = d;
+    for (int d = 0; d < g.new_h; ++d) y0[d] = d;
+  }
   std::vector<int> tab;
   for (auto* v : {&x0, &x1, &a0, &a1}) tab.insert(tab.end(), v->begin(), v->end());
   for (auto* v : {&y0, &y1, &b0, &b1}) tab.insert(tab.end(), v->begin(), v->end());
@@ -208,6 +222,67 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
   }
 }
 
+// Row-staged fast path for pure decimation (Geometry::decimate): one CTA per output row.  The source row is
+// brought into shared memory with coalesced 128-bit loads (every byte of the row is fetched, one in `ratio`
+// pixels is used: that is the algorithmic traffic counted in the header), then each thread picks the three
+// bytes of its four pixels from shared memory.  Rows of the letterbox border issue no loads.
+template <int FORMAT>
+__global__ void __launch_bounds__(S / PIX) preprocess_rows_kernel(const uint8_t* __restrict__ frames, int h, int w, int new_h,
+                                                                  int new_w, int top, int left, const int* __restrict__ tab,
+                                                                  void* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t srow[];
+  const int y = blockIdx.x % S, n = blockIdx.x / S;
+  const int dy = y - top;
+  const bool row_in = dy >= 0 && dy < new_h;
+  if (row_in) {
+    const int sy = __ldg(tab + 4 * new_w + dy);
+    const uint4* src = reinterpret_cast<const uint4*>(frames + (static_cast<long long>(n) * h + sy) * w * 3);
+    const int chunks = (w * 3) >> 4;
+    for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
+      uint4 v;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i));
+      reinterpret_cast<uint4*>(srow)[i] = v;
+    }
+  }
+  __syncthreads();
+  const int xg = threadIdx.x;
+  float rgb[PIX][3];
+#pragma unroll
+  for (int p = 0; p < PIX; ++p) {
+    const int dx = xg * PIX + p - left;
+    int v0 = 114, v1 = 114, v2 = 114;  // BGR pad colour (image_processing.py:10)
+    if (row_in && dx >= 0 && dx < new_w) {
+      const uint8_t* sp = srow + __ldg(tab + dx) * 3;
+      v0 = sp[0]; v1 = sp[1]; v2 = sp[2];
+    }
+    rgb[p][0] = __fdiv_rn(static_cast<float>(v2), 255.0f);
+    rgb[p][1] = __fdiv_rn(static_cast<float>(v1), 255.0f);
+    rgb[p][2] = __fdiv_rn(static_cast<float>(v0), 255.0f);
+  }
+  if (FORMAT == 0) {
+    float* o = static_cast<float*>(out) + static_cast<long long>(n) * 3 * S * S + static_cast<long long>(y) * S + xg * PIX;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      *reinterpret_cast<float4*>(o + static_cast<long long>(c) * S * S) = make_float4(rgb[0][c], rgb[1][c], rgb[2][c], rgb[3][c]);
+  } else {
+    uint4 q0, q1;
+    q0.x = pack_bf16x2(rgb[0][0], rgb[0][1]); q0.y = pack_bf16x2(rgb[0][2], 0.0f);
+    q0.z = pack_bf16x2(rgb[1][0], rgb[1][1]); q0.w = pack_bf16x2(rgb[1][2], 0.0f);
+    q1.x = pack_bf16x2(rgb[2][0], rgb[2][1]); q1.y = pack_bf16x2(rgb[2][2], 0.0f);
+    q1.z = pack_bf16x2(rgb[3][0], rgb[3][1]); q1.w = pack_bf16x2(rgb[3][2], 0.0f);
+    if (FORMAT == 1) {
+      uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + ((static_cast<long long>(n) * S + y) * S + xg * PIX) * 4);
+      o[0] = q0;
+      o[1] = q1;
+    } else {
+      uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) +
+                                          ((static_cast<long long>(n) * (S / 2) + (y >> 1)) * (S / 2) + 2 * xg) * 16 + (y & 1) * 8);
+      o[0] = q0;
+      o[2] = q1;
+    }
+  }
+}
+
 }  // namespace
 
 }  // namespace aicam
@@ -232,6 +307,25 @@ int aicam_preprocess(const uint8_t* frames, int batch, int h, int w, int format,
   const long long total = static_cast<long long>(batch) * S * (S / PIX);
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const bool no_fast = getenv("AICAM_PREPROCESS_GENERIC") != nullptr;
+  if (g.decimate && !no_fast && (w * 3) % 16 == 0 && reinterpret_cast<uintptr_t>(frames) % 16 == 0 &&
+      (static_cast<long long>(h) * w * 3) % 16 == 0 && w * 3 <= 96 * 1024) {
+    const unsigned rows = static_cast<unsigned>(batch) * S;
+    const size_t smem = static_cast<size_t>(w) * 3;
+    if (smem > 48 * 1024) {
+      AICAM_CUDA_OK(cudaFuncSetAttribute(preprocess_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      AICAM_CUDA_OK(cudaFuncSetAttribute(preprocess_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      AICAM_CUDA_OK(cudaFuncSetAttribute(preprocess_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    }
+    if (format == 0)
+      preprocess_rows_kernel<0><<<rows, S / PIX, smem, st>>>(frames, h, w, g.new_h, g.new_w, g.top, g.left, g.tab, out);
+    else if (format == 1)
+      preprocess_rows_kernel<1><<<rows, S / PIX, smem, st>>>(frames, h, w, g.new_h, g.new_w, g.top, g.left, g.tab, out);
+    else
+      preprocess_rows_kernel<2><<<rows, S / PIX, smem, st>>>(frames, h, w, g.new_h, g.new_w, g.top, g.left, g.tab, out);
+    count_launch();
+    return last_launch("preprocess_rows_kernel");
+  }
   if (format == 0)
     preprocess_kernel<0><<<blocks, 256, 0, st>>>(frames, h, w, g.mode, g.new_h, g.new_w, g.top, g.left, g.tab, out, total);
   else if (format == 1)
