@@ -15,10 +15,11 @@
 // MMA: the descriptor's leading-dimension byte offset is the distance between the two taps' pixels.
 // 9 taps + 1 zero chunk = 5 MMAs per accumulator.
 //
-// Epilogue (16 warps): TMEM -> +bias, ReLU, bf16 -> a shared-memory convolution tile indexed by raster
-// position (positions outside the crop are written as 0: post-ReLU values are >= 0 and every pooling
-// window holds at least one real pixel, so 0 is as good as -inf); block barrier; 48 x 8 threads each
-// reduce one pooled pixel x 8 channels (nine 16-byte reads) and store 16 bytes.
+// Epilogue (16 warps): TMEM -> bf16 -> a shared-memory convolution tile indexed by raster position
+// (positions outside the crop are written as -inf); block barrier; 48 x 8 threads each reduce one pooled
+// pixel x 8 channels (nine 16-byte reads), then add the bias and apply the ReLU - both commute with the
+// max, so they run on 48 pooled pixels instead of 231 convolution pixels - and store 16 bytes.  The
+// convolution tile is double-buffered: one block barrier per tile.
 #include <cstring>
 #include <vector>
 
@@ -50,7 +51,8 @@ constexpr uint32_t PITCH = COUT * 2 + 16;      // convolution tile row pitch (ba
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = (EPI_WARPS + 3) * 32;
 constexpr uint32_t OFF_BIAS = 256, OFF_W = 1024, OFF_A = OFF_W + W_BYTES, OFF_CONV = OFF_A + STAGES * STAGE_BYTES;
-constexpr uint32_t SMEM_BYTES = OFF_CONV + 256 * PITCH;
+constexpr uint32_t CONV_TILE_BYTES = 256 * PITCH;
+constexpr uint32_t SMEM_BYTES = OFF_CONV + 2 * CONV_TILE_BYTES;  // convolution tile double-buffered: one barrier per tile
 
 struct StemArgs {
   const __nv_bfloat16* wgt;
@@ -141,16 +143,19 @@ __global__ void __launch_bounds__(THREADS, 1) reid_stem_pool_kernel(const StemAr
     const int c_lo = (wg & 1) * 32;        // my 32 of its 64 columns
     const int q = j * 128 + wq * 32 + lane;  // my raster position
     const int ry = q / RW, rx = q - ry * RW;
-    uint8_t* conv_s = smem + OFF_CONV;
-    uint8_t* my_row = conv_s + static_cast<size_t>(q) * PITCH + c_lo * 2;
+    const uint32_t my_row_off = static_cast<uint32_t>(q) * PITCH + c_lo * 2;
     const uint32_t taddr_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + j * COUT + c_lo;
     // pooling role: thread t < 384 owns pooled pixel t / 8 of the tile and channels 8 (t % 8) .. + 7
     const int pt = threadIdx.x;
     const int pp = pt >> 3, pg = pt & 7;
     const int ppy = pp / PW, ppx = pp - ppy * PW;
+    float pbias[8];  // bias and ReLU commute with the max: applied to the 48 pooled pixels, not the 231 convolution pixels
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pbias[i] = bias_s[pg * 8 + i];
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
+      uint8_t* conv_s = smem + OFF_CONV + buf * CONV_TILE_BYTES;
       const int n = tile / tiles_per_img;
       const int r2 = tile - n * tiles_per_img;
       const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
@@ -164,26 +169,22 @@ __global__ void __launch_bounds__(THREADS, 1) reid_stem_pool_kernel(const StemAr
       tc_ld_wait();
       tc_fence_before();
       mbar_arrive(bar_acc_empty + 8 * buf);  // accumulator read: the MMA warp may reuse the buffer
-      uint32_t o[16];
-      const float4* bp = reinterpret_cast<const float4*>(bias_s + c_lo);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 b0 = bp[i], b1 = bp[4 + i];
-        o[2 * i] = pack_bf16x2(fmaxf(__uint_as_float(v0[4 * i]) + b0.x, 0.0f), fmaxf(__uint_as_float(v0[4 * i + 1]) + b0.y, 0.0f));
-        o[2 * i + 1] = pack_bf16x2(fmaxf(__uint_as_float(v0[4 * i + 2]) + b0.z, 0.0f), fmaxf(__uint_as_float(v0[4 * i + 3]) + b0.w, 0.0f));
-        o[8 + 2 * i] = pack_bf16x2(fmaxf(__uint_as_float(v1[4 * i]) + b1.x, 0.0f), fmaxf(__uint_as_float(v1[4 * i + 1]) + b1.y, 0.0f));
-        o[8 + 2 * i + 1] = pack_bf16x2(fmaxf(__uint_as_float(v1[4 * i + 2]) + b1.z, 0.0f), fmaxf(__uint_as_float(v1[4 * i + 3]) + b1.w, 0.0f));
-      }
-      if (!valid) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = 0u;
-      }
       if (q < NPOS) {
+        // raw accumulators as bf16; positions outside the crop lose every max (-inf)
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o[i] = valid ? pack_bf16x2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1])) : 0xFF80FF80u;
+          o[8 + i] = valid ? pack_bf16x2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1])) : 0xFF80FF80u;
+        }
+        uint8_t* my_row = conv_s + my_row_off;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           *reinterpret_cast<uint4*>(my_row + i * 16) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");  // convolution tile complete
+      // convolution tile complete (the other buffer is still being pooled by nobody: every thread passed this
+      // barrier for tile it - 1 only after its own pooling of tile it - 2)
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       if (pt < PH * PW * 8) {
         const int py = ty * PH + ppy, px = tx * PW + ppx;
         if (py < a.ph && px < a.pw) {
@@ -194,10 +195,15 @@ __global__ void __launch_bounds__(THREADS, 1) reid_stem_pool_kernel(const StemAr
             const uint4 u = *reinterpret_cast<const uint4*>(base + static_cast<size_t>((t / 3) * RW + (t % 3)) * PITCH);
             m.x = hmax2(m.x, u.x); m.y = hmax2(m.y, u.y); m.z = hmax2(m.z, u.z); m.w = hmax2(m.w, u.w);
           }
-          *reinterpret_cast<uint4*>(a.out + ((static_cast<long long>(n) * a.ph + py) * a.pw + px) * COUT + pg * 8) = m;
+          const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            ow[i] = pack_bf16x2(fmaxf(bf16_lo(mw[i]) + pbias[2 * i], 0.0f), fmaxf(bf16_hi(mw[i]) + pbias[2 * i + 1], 0.0f));
+          *reinterpret_cast<uint4*>(a.out + ((static_cast<long long>(n) * a.ph + py) * a.pw + px) * COUT + pg * 8) =
+              make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");  // convolution tile free again
     }
   } else if (warp == EPI_WARPS) {
     // ================================================================== MMA issuer (converged warp, elected lane)
