@@ -68,6 +68,7 @@ SIGNATURES = {
     "aicam_engine_accepts_nhwc8": (_I, [_P]),
     "aicam_nchw_to_nhwc4": (_I, [_P, _I, _I, _I, _P, _P]),
     "aicam_conv2d": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "aicam_conv2d_padded": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _I, _I, _P]),
     "aicam_conv2d_bench": (_I, [C.POINTER(ConvDesc), _I, C.POINTER(C.c_double), _P]),
     "aicam_reid_stem_pool": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "aicam_letterbox_params": (_I, [_I, _I, C.POINTER(Letterbox)]),

@@ -649,6 +649,17 @@ int pack_conv_weights(const float* w, const float* bias, int cout, int cin, int 
   AICAM_CUDA_OK(cudaMalloc(&p.bias, b.size() * 4));
   AICAM_CUDA_OK(cudaMemcpy(p.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
   AICAM_CUDA_OK(cudaMemcpy(p.bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  const int nb = pick_n_tile(cout_pad, false);
+  if (nb < cout_pad) {  // n-tile-major copy for the streamed-weight window kernel
+    std::vector<uint16_t> nt(packed.size());
+    for (int qq = 0; qq < q_pad; ++qq)
+      for (int o = 0; o < cout_pad; ++o)
+        std::memcpy(&nt[((static_cast<size_t>(o / nb) * q_pad + qq) * nb + o % nb) * 8],
+                    &packed[(static_cast<size_t>(qq) * cout_pad + o) * 8], 16);
+    AICAM_CUDA_OK(cudaMalloc(&p.w_nt, nt.size() * 2));
+    AICAM_CUDA_OK(cudaMemcpy(p.w_nt, nt.data(), nt.size() * 2, cudaMemcpyHostToDevice));
+    p.nt_block = nb;
+  }
   *out = p;
   return AICAM_OK;
 }
@@ -688,6 +699,8 @@ int pack_conv_weights_s2d(const float* w, const float* bias, int cout, int cin, 
 void free_packed_conv(PackedConv* p) {
   if (p->w) cudaFree(p->w);
   if (p->bias) cudaFree(p->bias);
+  if (p->w_nt) cudaFree(p->w_nt);
+  p->w_nt = nullptr;
   p->w = nullptr;
   p->bias = nullptr;
 }
@@ -698,6 +711,12 @@ int launch_conv(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream) 
     const int wrc = try_launch_conv_win(pc, L, stream);
     if (wrc < 0) return wrc;
     return wrc == 1 ? AICAM_OK : fail(AICAM_ERR_UNSUPPORTED, "launch_conv: space-to-depth layer not eligible for the window kernel");
+  }
+  if (L.in_pad || L.out_pad) {  // zero-bordered tensors exist only on the window kernel
+    if (L.batch <= 0) return AICAM_OK;
+    const int wrc = try_launch_conv_win(pc, L, stream);
+    if (wrc < 0) return wrc;
+    return wrc == 1 ? AICAM_OK : fail(AICAM_ERR_UNSUPPORTED, "launch_conv: padded layer not eligible for the window kernel");
   }
   ConvKernelArgs a;
   a.in = L.in; a.in_img_stride = L.in_img_stride; a.in_cstride = L.in_cstride; a.in_coff = L.in_coff;

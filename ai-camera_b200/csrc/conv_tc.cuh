@@ -15,6 +15,10 @@ struct PackedConv {
   int cout = 0, ksize = 1, stride = 1;
   int q = 0, q_pad = 0;
   int s2d_c0 = 0;  // != 0: a 3x3 stride-2 layer packed as a 2x2 window over 2x2 input blocks of s2d_c0 channels (conv_win.cu)
+  // Layers wider than one n-tile keep a second copy [cout_pad / nt_block][q_pad][nt_block][8]: the weights one
+  // (K slab, n-tile) stage needs are then one contiguous run = one bulk copy instead of one per K chunk
+  __nv_bfloat16* w_nt = nullptr;
+  int nt_block = 0;
 };
 
 struct ConvLaunch {
@@ -35,6 +39,11 @@ struct ConvLaunch {
   const int* batch_dev = nullptr;  // optional device-side image count (<= batch)
   int out_s2d = 0;                 // store the output space-to-depth: [ho/2][wo/2][2x2 sub-pixel][out_cstride] (window kernel only)
   long long* trace = nullptr;      // debug: clock64 stamps of CTA 0
+  // "Padded" tensors carry a one-pixel zero border in memory: [batch][h + 2][w + 2][cstride], interior at (1, 1);
+  // h / w / ho / wo stay the logical sizes and the image strides describe the padded images.  The border is
+  // never written, so a 3x3 stride-1 layer can run over the flat raster of ALL padded pixels (window kernel,
+  // operand mode 4) without per-image halo handling.  The residual shares the output's layout.
+  int in_pad = 0, out_pad = 0;
 };
 
 // host: pack OIHW fp32 weights (host) into the device layout above

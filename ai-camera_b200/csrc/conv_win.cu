@@ -23,6 +23,7 @@
 // Warp roles (608 threads): 0-15 epilogue (four warpgroups split the accumulator columns; TMEM lane
 // quarter = warp % 4), 16 MMA issuer (one thread) + TMEM owner, 17 patch (A) producer, 18 weight (B) producer.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -74,6 +75,12 @@ struct WinArgs {
   int res_direct;  // residual read straight from global in the finish phase (no staging): deep, streamed layers
   int out_s2d;  // window modes: the output is stored space-to-depth: [h/2][w/2][2x2 sub-pixel][out_cstride]
   int flat;  // 1x1 mode: output and residual are dense, pixel p of the batch sits at p * cstride
+  int out_pad;   // flat / im2col modes: output (and residual) images carry a one-pixel zero border, interior at (1, 1)
+  int box_rows;  // mode 4: raster rows per TMA box (a patch is MT boxes)
+  int res_inplace;  // TMA epilogue: the residual tile is loaded INTO the output staging buffer and finished in place
+                    // (no residual ring): the store of tile i is followed by the residual load of tile i + nstage
+  int direct_out;  // generic epilogue: every thread stores its finished 32-byte groups straight to global (whole
+                   // sectors, no staging tile): deep streamed layers spend the shared memory on operand rings instead
   int mt, tm;
   int slab, slabs, taps, cin_pad;
   int ksize, stride, pad, wo, slabs_per_tap;  // im2col mode: filter geometry, output width, channel slabs per tap
@@ -81,6 +88,8 @@ struct WinArgs {
   uint32_t patch_bytes, box_bytes, bstage_bytes, wbytes;
   int n_tile, n_tiles, cout, cout_pad;
   const __nv_bfloat16* wgt;
+  const __nv_bfloat16* wgt_nt;  // n-tile-major copy ([n-tile][K chunk][n_tile][8]) or null
+  int q_pad;                    // K chunks per n-tile block of wgt_nt
   const float* bias;
   void* out;
   long long out_img_stride;
@@ -221,10 +230,16 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
   // 0: 3x3 window patches, 1: flat 1x1, 2: im2col TMA (any 1x1 / 3x3, stride 1 / 2),
   // 3: 2x2 window, pad 1 on the top / left only: a 3x3 stride-2 layer over its space-to-depth input
   //    (2x2 pixel blocks stored as one 4C-channel pixel; weights re-packed by pack_conv_weights_s2d)
+  // 4: 3x3 stride 1 over zero-bordered ("padded") tensors: input, output and residual are [batch][h+2][w+2][c] with a
+  //    zero border, so the WHOLE batch is one flat raster of padded pixels (row pitch RW = w + 2).  A tile is any TM
+  //    consecutive raster positions, its patch the TM + 2 RW + 2 positions around it (one 2-D box per 128 rows, no
+  //    per-image halo, no row alignment), tap (dy, dx) the patch shifted by dy RW + dx positions as in mode 0.
+  //    Border positions produce junk accumulator rows that are never stored, so the border stays zero.
   constexpr bool WINDOW = AMODE == 0 || AMODE == 3;
-  constexpr int MODE = WINDOW ? 0 : AMODE;
+  constexpr bool FLATWIN = AMODE == 4;
+  constexpr int MODE = WINDOW ? 0 : (FLATWIN ? 1 : AMODE);
   constexpr int KW = AMODE == 3 ? 2 : 3;                        // window width in raster positions
-  constexpr int TAPS = AMODE == 0 ? 9 : (AMODE == 3 ? 4 : 1);   // taps that share one A stage
+  constexpr int TAPS = (AMODE == 0 || AMODE == 4) ? 9 : (AMODE == 3 ? 4 : 1);   // taps that share one A stage
   constexpr int TM = 128 * MT;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -306,7 +321,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       row_xor[p] = ((ro >> 7) & mask) << 4;
     }
     uint8_t* stage0 = smem + a.off_stage;
-    const uint8_t* res_base = smem + a.off_res;
+    const uint8_t* res_base = smem + (a.res_inplace ? a.off_stage : a.off_res);
     uint32_t rslot = 0, rphase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -330,6 +345,13 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       const uint32_t sfree_par = (a.nstage == 2 ? ((it >> 1) & 1) : (it & 1)) ^ 1;
       uint8_t* stage = stage0 + sbuf * a.stage_buf_bytes;
       bool stage_ok = false;
+      bool zero_row = false;
+      if (FLATWIN) {  // my raster position of this tile: border positions are stored as zeros (the border stays zero)
+        const long long p = static_cast<long long>(mt_idx) * TM + r;
+        const int rem = static_cast<int>(p % a.hw);
+        const int yy = rem / a.rw, xx = rem - yy * a.rw;
+        zero_row = !(yy >= 1 && yy <= a.h && xx >= 1 && xx <= a.w);
+      }
       for (int g = g_lo; g < g_hi; g += 2) {
         uint32_t v0[16], v1[16];
         const bool two = g + 1 < g_hi;  // warp-uniform
@@ -349,7 +371,12 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
             const int p = c < a.piece_ch[0] ? 0 : 1;
             const uint32_t ch0 = static_cast<uint32_t>(c - (p ? a.piece_ch[0] : 0)) * 2;  // byte offset inside the piece row
             const uint32_t o0 = row_off[p] + (ch0 ^ row_xor[p]), o1 = row_off[p] + ((ch0 + 16) ^ row_xor[p]);
-            finish_group<ACT>(h ? v1 : v0, bias_s + n0 + c, res_buf + o0, a.res_mode, 0, stage + o0, res_buf + o1, stage + o1);
+            if (FLATWIN && zero_row) {
+              *reinterpret_cast<uint4*>(stage + o0) = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(stage + o1) = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+              finish_group<ACT>(h ? v1 : v0, bias_s + n0 + c, res_buf + o0, a.res_mode, 0, stage + o0, res_buf + o1, stage + o1);
+            }
           }
         }
       }
@@ -417,9 +444,18 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
         if (a.flat) {  // every tensor involved is dense: pixel p of the batch is at p * cstride
           img = 0;
           pix = static_cast<int>(p);
+          if (FLATWIN) {  // p runs over the padded raster: only interior positions are outputs
+            const int rem = pix - (pix / a.hw) * a.hw;
+            const int yy = rem / a.rw, xx = rem - yy * a.rw;
+            valid = valid && yy >= 1 && yy <= a.h && xx >= 1 && xx <= a.w;
+          }
         } else {
           img = static_cast<int>(p) / a.hw;
           pix = static_cast<int>(p) - img * a.hw;
+          if (a.out_pad) {  // zero-bordered output image: (y, x) -> (y + 1, x + 1) of a (wo + 2)-wide raster
+            const int y = pix / a.wo, x = pix - y * a.wo;
+            pix = (y + 1) * (a.wo + 2) + x + 1;
+          }
         }
       }
       long long* ro = rowoff_base + slot * (2 * 8 * 32);
@@ -491,10 +527,11 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
         if (two) tc_ld16_nowait(taddr + c0 + 16, v1);
         tc_ld_wait();
         if (valid) {
-          finish_group<ACT>(v0, bias_s + c.n0 + c0, res_row + c0 * 2, a.res_mode, a.out_f32, my_stage + c0 * esize);
+          uint8_t* dst = a.direct_out ? out_bytes + ro[lane] * esize : my_stage;
+          finish_group<ACT>(v0, bias_s + c.n0 + c0, res_row + c0 * 2, a.res_mode, a.out_f32, dst + c0 * esize);
           if (two)
             finish_group<ACT>(v1, bias_s + c.n0 + c0 + 16, res_row + (c0 + 16) * 2, a.res_mode, a.out_f32,
-                              my_stage + (c0 + 16) * esize);
+                              dst + (c0 + 16) * esize);
         }
       }
       // my part of the accumulator buffer has been read: the MMA thread may reuse it for tile it + 2
@@ -510,7 +547,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       if (threadIdx.x == 0) WIN_TRACE(it, 13);
       if (res_staged && more) prefetch_res(cc, buf ^ 1);
       // ---- staging -> global, rows [ROWS_PER_WARP * part, +ROWS_PER_WARP): whole rows per instruction
-      if (c.cpr > 0) {
+      if (c.cpr > 0 && !a.direct_out) {
         const int ch = lane & ((1 << c.cpr_sh) - 1);
         for (int rr = lane >> c.cpr_sh; rr < ROWS_PER_WARP; rr += 32 >> c.cpr_sh) {
           const int r = part * ROWS_PER_WARP + rr;
@@ -645,6 +682,11 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
           mbar_arrive_expect_tx(bar, tx_bytes);
           if (MODE == 0) {
             tma_load_4d(dst, &maps.in, bar, s * SLAB, x_start, y_start, n_img);
+          } else if (FLATWIN) {
+            const int row0 = mt_idx * TM - (a.rw + 1);  // negative / past-the-end rows are zero-filled
+#pragma unroll
+            for (int j = 0; j < MT; ++j)
+              tma_load_2d(dst + j * (a.box_rows * ROW_BYTES), &maps.in, bar, s * SLAB, row0 + j * a.box_rows);
           } else if (MODE == 1) {
             tma_load_2d(dst, &maps.in, bar, s * SLAB, mt_idx * TM);
           } else {
@@ -686,6 +728,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
               const __nv_bfloat16* src = a.wgt + (static_cast<long long>(chunk0) * a.cout_pad + n0) * 8;
               if (a.n_tile == a.cout_pad) {
                 bulk_g2s(dst, src, a.bstage_bytes, bar);
+              } else if (a.wgt_nt) {  // the stage is one contiguous run of the n-tile-major copy
+                bulk_g2s(dst, a.wgt_nt + (static_cast<long long>(n0 / a.n_tile) * a.q_pad + chunk0) * a.n_tile * 8, a.bstage_bytes, bar);
               } else {
                 for (int c = 0; c < nchunks; ++c)
                   bulk_g2s(dst + c * chunk_bytes, src + static_cast<long long>(c) * a.cout_pad * 8, chunk_bytes, bar);
@@ -718,7 +762,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       mbar_wait(bar_res_empty + 8 * slot, phase ^ 1);
       if (lane == 0) {
         const uint32_t rbar = bar_res_full + 8 * slot;
-        const uint32_t rdst = sbase + a.off_res + slot * a.stage_buf_bytes;
+        const uint32_t rdst = sbase + (a.res_inplace ? a.off_stage : a.off_res) + slot * a.stage_buf_bytes;
         mbar_arrive_expect_tx(rbar, a.res_tx_bytes);
         if (WINDOW) {
           tma_load_4d(rdst + a.piece_off[0], &maps.res[0], rbar, n0, cx, cy, cn);
@@ -790,6 +834,7 @@ template <int SLAB>
 WinKernelFn pick_mode(int mode, int mt, int act, int epi) {
   if (mode == 0) return epi ? pick_mt<SLAB, 0, 1>(mt, act) : pick_mt<SLAB, 0, 0>(mt, act);
   if (mode == 3) return epi ? pick_mt<SLAB, 3, 1>(mt, act) : pick_mt<SLAB, 3, 0>(mt, act);
+  if (mode == 4) return epi ? pick_mt<SLAB, 4, 1>(mt, act) : pick_mt<SLAB, 4, 0>(mt, act);
   if (mode == 1) return epi ? pick_mt<SLAB, 1, 1>(mt, act) : pick_mt<SLAB, 1, 0>(mt, act);
   return epi ? pick_mt<SLAB, 2, 1>(mt, act) : pick_mt<SLAB, 2, 0>(mt, act);
 }
@@ -835,6 +880,11 @@ EncodeIm2colFn get_encode_im2col() {
   return fn;
 }
 
+// 3x3 stride-1 layer over zero-bordered tensors: operand mode 4
+inline bool mode_is_flatwin(const PackedConv& pc, const ConvLaunch& L) {
+  return L.in_pad && L.out_pad && pc.stride == 1 && pc.ksize == 3 && pc.s2d_c0 == 0;
+}
+
 struct WinPlan {
   bool ok = false;
   double cost = 0.0;
@@ -877,13 +927,24 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
                    reinterpret_cast<uintptr_t>(L.res) % 16 != 0))
     return 0;
   if (L.in_cstride % 8 != 0 || L.in_coff % 8 != 0 || reinterpret_cast<uintptr_t>(L.in) % 16 != 0) return 0;
-  if (L.in_img_stride != static_cast<long long>(L.h) * L.w * L.in_cstride) return 0;
+  const int ip = L.in_pad ? 1 : 0, opd = L.out_pad ? 1 : 0;
+  const int hp = L.h + 2 * ip, wp = L.w + 2 * ip;  // input image as it lies in memory
+  if (L.in_img_stride != static_cast<long long>(hp) * wp * L.in_cstride) return 0;
+  if (opd && (L.out_img_stride != static_cast<long long>(L.ho + 2) * (L.wo + 2) * L.out_cstride ||
+              (res_mode && L.res_img_stride != static_cast<long long>(L.ho + 2) * (L.wo + 2) * L.res_cstride) || L.out_s2d || s2d))
+    return fail(AICAM_ERR_INVALID_ARG, "conv_win: padded output with an inconsistent image stride");
   const long long pixels = static_cast<long long>(L.batch) * L.ho * L.wo;  // output pixels
-  if (pixels >= (1ll << 31) || static_cast<long long>(L.batch) * L.h * L.w >= (1ll << 31)) return 0;
+  const long long padded_pixels = static_cast<long long>(L.batch) * hp * wp;
+  if (pixels >= (1ll << 31) || padded_pixels >= (1ll << 31)) return 0;
 
   // 0: window patches (3x3 stride 1), 1: flat (1x1 stride 1), 2: im2col TMA (stride 2, and 3x3 on maps too
   // small for the window raster)
   int mode = s2d ? 3 : (pc.stride == 1 ? (pc.ksize == 3 ? 0 : 1) : 2);
+  if (ip && pc.stride == 1) {
+    // stride 1 over a padded input: the flat padded raster (mode 4), output in the same padded geometry
+    if (pc.ksize != 3 || !opd || s2d) return fail(AICAM_ERR_UNSUPPORTED, "conv_win: padded input needs a 3x3 stride-1 layer with a padded output, or stride 2");
+    mode = 4;
+  }
   if (mode == 2 && no_im2col) return 0;
   if (L.out_s2d && mode != 0 && mode != 3) return 0;  // the caller reports the unsupported combination
   bool window = mode == 0 || mode == 3;
@@ -905,6 +966,13 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   const uint32_t stage_pitch = n_tile * es + 16;
   const uint32_t res_pitch = n_tile * 2 + 16;
   const int sb = resident ? 0 : 4;
+  // mode 4 fallback when the TMA epilogue is unavailable: no staging tile, every thread stores its own 32-byte groups
+  // (measured: ~15k cycles per 256 x 128 tile, LSU-bound - one sector per lane per instruction)
+  static const bool no_tma_epi4 = getenv("AICAM_WIN_NO_TMA_EPI") != nullptr;
+  const int nt_rest = n_tile - (n_tile >= 64 ? 64 : (n_tile >= 32 ? 32 : 16));  // the n-tile splits into <= 2 swizzled pieces
+  const bool epi4 = mode == 4 && !no_tma_epi4 && !L.out_f32 && pc.cout % 8 == 0 &&
+                    (nt_rest == 0 || nt_rest == 64 || nt_rest == 32 || nt_rest == 16);
+  const bool direct_out = mode == 4 && !resident && !L.out_f32 && !epi4;
   // streamed (deep-K) layers: the epilogue is a small share of a tile, read the residual from global there
   // instead of spending 70 KB of shared memory that the 256-row tiling needs
   const bool res_staged = res_mode != 0 && resident;
@@ -935,16 +1003,18 @@ plan:
   // im2col / flat layers are L2-bound and need the shared memory for deeper operand rings instead
   static const bool epi_everywhere = getenv("AICAM_WIN_TMA_EPI_ALL") != nullptr;
   if (!window && !(epi_everywhere && flat_io)) epi = false;
+  if (mode == 4) epi = epi4 && piece_ch[0] != 0;  // flat TMA epilogue: border positions are stored as zeros
+  else if (opd) epi = false;                        // (un-padded raster -> padded image: row-by-row offsets, generic epilogue)
   for (int mt = 1; mt <= 2; ++mt) {
     if (force_mt && mt != force_mt) continue;
     const int tm = 128 * mt;
     if (2 * mt * n_tile > 512) continue;
     for (int strips = 1; strips <= (window ? 8 : 1); ++strips) {
-      for (int aligned = epi ? 1 : 0; aligned <= (window ? 1 : 0); ++aligned) {
+      for (int aligned = (epi && window) ? 1 : 0; aligned <= (window ? 1 : 0); ++aligned) {
         WinPlan p;
         p.mt = mt;
         p.strips = strips;
-        size_t stage_bytes = static_cast<size_t>(tm) * (stage_pitch + (res_staged ? res_pitch : 0));
+        size_t stage_bytes = direct_out ? 0 : static_cast<size_t>(tm) * (stage_pitch + (res_staged ? res_pitch : 0));
         if (window) {
           p.tw = (win_w + strips - 1) / strips;
           p.rw = p.tw + kw1;
@@ -976,6 +1046,25 @@ plan:
           const uint32_t reach = static_cast<uint32_t>(xp0max + tm + kw1 * p.rw + kw1 + 1) * row_bytes;  // junk rows stay inside the stage
           p.patch_bytes = (std::max(p.box_bytes, reach) + 1023) / 1024 * 1024;
           p.tiles = static_cast<long long>(L.batch) * strips * p.tiles_per_strip;
+        } else if (mode == 4) {
+          // flat padded raster: MT boxes of `bh` rows cover the tile and the RW + 1 positions either side of it
+          p.tw = L.w; p.rw = wp; p.tstep = tm; p.tiles_per_strip = 0;
+          p.bh = ((tm + 2 * wp + 2 + mt - 1) / mt + 7) / 8 * 8;
+          if (p.bh > 256) continue;
+          p.box_bytes = static_cast<uint32_t>(mt) * p.bh * row_bytes;
+          p.patch_bytes = (p.box_bytes + 1023) / 1024 * 1024;
+          p.tiles = (padded_pixels + tm - 1) / tm;
+          if (epi) {
+            // the residual tile is loaded into the staging buffer and finished in place: no residual ring
+            size_t buf = 0;
+            for (int q = 0; q < 2; ++q)
+              if (piece_ch[q]) buf += (static_cast<size_t>(tm) * piece_ch[q] * 2 + 1023) / 1024 * 1024;
+            p.stage_buf = static_cast<uint32_t>(buf);
+            p.nstage = 2;
+            if (fixed_base + buf * 2 + 1024 + 2 * static_cast<size_t>(p.patch_bytes) > SMEM_LIMIT) p.nstage = 1;
+            p.nres = res_mode ? p.nstage : 0;
+            stage_bytes = buf * p.nstage + 1024;
+          }
         } else {
           p.tw = L.w; p.rw = L.w; p.tstep = tm; p.tiles_per_strip = 0; p.bh = 0;
           p.box_bytes = static_cast<uint32_t>(tm) * row_bytes;
@@ -992,12 +1081,12 @@ plan:
           }
         }
         size_t fixed = fixed_base + stage_bytes;
-        if (epi && fixed + 3 * static_cast<size_t>(p.patch_bytes) > SMEM_LIMIT) {
+        if (epi && mode != 4 && fixed + 3 * static_cast<size_t>(p.patch_bytes) > SMEM_LIMIT) {
           p.nstage = 1;  // single output staging buffer rather than a shallow patch ring
           stage_bytes = static_cast<size_t>(p.stage_buf) * (p.nstage + p.nres) + 1024;
           fixed = fixed_base + stage_bytes;
         }
-        if (epi && p.nres == 2 && fixed + 3 * static_cast<size_t>(p.patch_bytes) > SMEM_LIMIT) {
+        if (epi && mode != 4 && p.nres == 2 && fixed + 3 * static_cast<size_t>(p.patch_bytes) > SMEM_LIMIT) {
           p.nres = 1;  // then one residual buffer
           stage_bytes = static_cast<size_t>(p.stage_buf) * (p.nstage + p.nres) + 1024;
           fixed = fixed_base + stage_bytes;
@@ -1005,7 +1094,7 @@ plan:
         if (fixed + 2 * static_cast<size_t>(p.patch_bytes) > SMEM_LIMIT) continue;
         p.sa = static_cast<int>(std::min<size_t>(MAX_RING, (SMEM_LIMIT - fixed) / p.patch_bytes));
         // enough patches in flight to cover the HBM latency of a tile, no more
-        p.sa = std::min(p.sa, window ? std::max(4, 2 * slabs) : 6);
+        p.sa = std::min(p.sa, (window || mode == 4) ? std::max(4, 2 * slabs) : 6);
         p.smem = fixed + static_cast<size_t>(p.sa) * p.patch_bytes;
         // estimated cycles per tile: tensor pipe vs L2->SM traffic vs epilogue, plus a fixed hand-off cost
         // one 128 x n_tile x 16 MMA: tensor pipe n_tile / 2 cycles, operand fetch (4 KB + n_tile * 32 B) at 128 B/clk
@@ -1019,15 +1108,15 @@ plan:
                                    : (static_cast<double>(mt) * groups / active) * 1000.0 + 1700.0;
         double per_tile = std::max(mma, std::max(l2, epi_cyc)) + 250.0;
         // shallow rings serialise producer, MMA and epilogue
-        if (window && p.sa < 3) per_tile *= 1.6;
-        if (epi && res_mode && p.nres < 2) per_tile *= 2.0;
+        if ((window || (mode == 4 && slabs == 1)) && p.sa < 3) per_tile *= 1.6;
+        if (epi && mode != 4 && res_mode && p.nres < 2) per_tile *= 2.0;  // (mode 4 finishes the residual in place)
         p.cost = static_cast<double>(p.tiles) * n_tiles * per_tile;
         p.ok = true;
         if (!best.ok || p.cost < best.cost) best = p;
       }
     }
   }
-  if (epi && (!best.ok || static_cast<double>(pixels) / (static_cast<double>(best.tiles) * 128 * best.mt) < 0.6)) {
+  if (epi && mode != 4 && (!best.ok || static_cast<double>(pixels) / (static_cast<double>(best.tiles) * 128 * best.mt) < 0.6)) {
     epi = false;  // row-aligned tiles waste too much here: generic epilogue, linear raster
     goto plan;
   }
@@ -1044,8 +1133,9 @@ plan:
 
   WinArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.mode = mode; a.h = win_h; a.w = win_w; a.hw = L.ho * L.wo;
-  a.ksize = pc.ksize; a.stride = pc.stride; a.pad = pc.ksize / 2; a.wo = L.wo; a.slabs_per_tap = slabs;
+  a.mode = mode; a.h = win_h; a.w = win_w; a.hw = mode == 4 ? hp * wp : L.ho * L.wo;
+  a.ksize = pc.ksize; a.stride = pc.stride; a.pad = pc.ksize / 2 - ip; a.wo = L.wo; a.slabs_per_tap = slabs;
+  a.out_pad = opd; a.box_rows = best.bh; a.direct_out = direct_out ? 1 : 0;
   a.rw = best.rw; a.tw = best.tw; a.strips = best.strips; a.tstep = best.tstep;
   a.tiles_per_strip = best.tiles_per_strip; a.tiles_per_img = best.strips * best.tiles_per_strip;
   a.mt = best.mt; a.tm = 128 * best.mt;
@@ -1055,6 +1145,7 @@ plan:
   a.wbytes = static_cast<uint32_t>(wbytes);
   a.n_tile = n_tile; a.n_tiles = n_tiles; a.cout = pc.cout; a.cout_pad = cout_pad;
   a.wgt = pc.w; a.bias = pc.bias;
+  a.wgt_nt = (pc.w_nt && pc.nt_block == n_tile) ? pc.w_nt : nullptr; a.q_pad = pc.q_pad;
   a.out = L.out; a.out_img_stride = L.out_img_stride; a.out_cstride = L.out_cstride; a.out_coff = L.out_coff; a.out_f32 = L.out_f32;
   a.res = L.res; a.res_img_stride = L.res_img_stride; a.res_cstride = L.res_cstride; a.res_coff = L.res_coff; a.res_mode = res_mode;
   a.act = L.act;
@@ -1094,8 +1185,9 @@ plan:
   a.flat = (mode != 0 && L.out_img_stride == static_cast<long long>(a.hw) * L.out_cstride &&
             (!res_mode || L.res_img_stride == static_cast<long long>(a.hw) * L.res_cstride)) ? 1 : 0;
   a.res_direct = (!epi && res_mode != 0 && !res_staged) ? 1 : 0;
-  const size_t smem = epi ? a.off_stage + static_cast<size_t>(best.stage_buf) * (best.nstage + best.nres)
-                          : a.off_stage + static_cast<size_t>(a.tm) * (stage_pitch + (res_staged ? res_pitch : 0));
+  a.res_inplace = (epi && mode == 4) ? 1 : 0;
+  const size_t smem = epi ? a.off_stage + static_cast<size_t>(best.stage_buf) * (best.nstage + (a.res_inplace ? 0 : best.nres))
+                          : a.off_stage + (direct_out ? 0 : static_cast<size_t>(a.tm) * (stage_pitch + (res_staged ? res_pitch : 0)));
   if (smem > SMEM_LIMIT) return 0;
 
   alignas(64) WinMaps maps;
@@ -1114,21 +1206,22 @@ plan:
     cr = get_encode_tiled()(&maps.in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else if (mode == 2) {
-    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(pc.cin_pad), static_cast<cuuint64_t>(L.w), static_cast<cuuint64_t>(L.h),
+    // a padded input already holds its halo: the image is (h + 2) x (w + 2) and base pixels start at (ip - pad)
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(pc.cin_pad), static_cast<cuuint64_t>(wp), static_cast<cuuint64_t>(hp),
                                 static_cast<cuuint64_t>(L.batch)};
-    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.in_cstride) * 2, static_cast<cuuint64_t>(L.w) * L.in_cstride * 2,
-                                   static_cast<cuuint64_t>(L.h) * L.w * L.in_cstride * 2};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.in_cstride) * 2, static_cast<cuuint64_t>(wp) * L.in_cstride * 2,
+                                   static_cast<cuuint64_t>(hp) * wp * L.in_cstride * 2};
     const int pad = pc.ksize / 2;
-    const int lower[2] = {-pad, -pad};
-    const int upper[2] = {pad - (pc.ksize - 1), pad - (pc.ksize - 1)};
+    const int lower[2] = {ip - pad, ip - pad};
+    const int upper[2] = {pad - (pc.ksize - 1) - ip, pad - (pc.ksize - 1) - ip};
     const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(pc.stride), static_cast<cuuint32_t>(pc.stride), 1};
     cr = get_encode_im2col()(&maps.in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, lower, upper, static_cast<cuuint32_t>(slab),
                              128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
-    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(pc.cin_pad), static_cast<cuuint64_t>(pixels)};
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(pc.cin_pad), static_cast<cuuint64_t>(mode == 4 ? padded_pixels : pixels)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(L.in_cstride) * 2};
-    const cuuint32_t box[2] = {static_cast<cuuint32_t>(slab), static_cast<cuuint32_t>(a.tm)};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(slab), static_cast<cuuint32_t>(mode == 4 ? best.bh : a.tm)};
     const cuuint32_t estr[2] = {1, 1};
     cr = get_encode_tiled()(&maps.in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1145,7 +1238,7 @@ plan:
       const CUtensorMapSwizzle psw = pb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (pb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
       if (!window) {
         // flat: [piece channels][128 MT pixels] of the [pixels][cstride] matrix
-        const cuuint64_t fd[2] = {static_cast<cuuint64_t>(pc.cout), static_cast<cuuint64_t>(pixels)};
+        const cuuint64_t fd[2] = {static_cast<cuuint64_t>(pc.cout), static_cast<cuuint64_t>(mode == 4 ? padded_pixels : pixels)};
         const cuuint32_t fb[2] = {static_cast<cuuint32_t>(piece_ch[q]), static_cast<cuuint32_t>(a.tm)};
         const cuuint32_t fe[2] = {1, 1};
         const cuuint64_t fos[1] = {static_cast<cuuint64_t>(L.out_cstride) * 2};
@@ -1179,6 +1272,11 @@ plan:
     if (cr != CUDA_SUCCESS)
       return fail(AICAM_ERR_CUDA, "conv_win: cuTensorMapEncodeTiled (epilogue) failed with " + std::to_string(static_cast<int>(cr)));
   }
+  static const bool debug_plan = getenv("AICAM_WIN_DEBUG") != nullptr;
+  if (debug_plan)
+    fprintf(stderr, "conv_win: %dx%d c%d->%d k%d s%d mode %d mt %d n_tile %d x%d slab %d x%d resident %d sa %d sb %d patch %u bstage %u "
+            "epi %d direct %d tiles %lld smem %zu\n", L.h, L.w, pc.cin_pad, pc.cout, pc.ksize, pc.stride, mode, best.mt, n_tile, n_tiles,
+            slab, slabs, resident ? 1 : 0, a.sa, a.sb, a.patch_bytes, a.bstage_bytes, epi ? 1 : 0, a.direct_out, best.tiles * n_tiles, smem);
   WinKernelFn kernel = pick_kernel(slab, mode, best.mt, L.act, epi ? 1 : 0);
   {
     static std::vector<WinKernelFn> configured;  // opt in to > 48 KB of dynamic shared memory once per instantiation

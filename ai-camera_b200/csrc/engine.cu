@@ -33,6 +33,7 @@ struct BlobTensor {
 struct Buffer {
   __nv_bfloat16* ptr;
   int h, w, c;
+  int pad = 0;  // 1: stored [batch][h + 2][w + 2][c] with a zero border that no kernel ever writes (conv_tc.cuh)
 };
 
 struct View {
@@ -93,9 +94,9 @@ struct Builder {
   std::map<std::string, BlobTensor>* tensors;
   int err = AICAM_OK;
 
-  int buf(int h, int w, int c) {
-    Buffer b{nullptr, h, w, c};
-    const size_t bytes = static_cast<size_t>(e->max_batch) * h * w * c * sizeof(__nv_bfloat16);
+  int buf(int h, int w, int c, int pad = 0) {
+    Buffer b{nullptr, h, w, c, pad};
+    const size_t bytes = static_cast<size_t>(e->max_batch) * (h + 2 * pad) * (w + 2 * pad) * c * sizeof(__nv_bfloat16);
     if (cudaMalloc(&b.ptr, bytes) != cudaSuccess) {
       err = fail(AICAM_ERR_CUDA, "engine: cudaMalloc of an activation buffer failed");
       b.ptr = nullptr;
@@ -285,17 +286,21 @@ struct Builder {
       pool(V(s0), V(cur), H, W, 64, 3, 2);
     }
     const int widths[4] = {64, 128, 256, 512};
+    static const bool no_pad = getenv("AICAM_NO_PADDED_REID") != nullptr;
     for (int li = 0; li < 4; ++li) {
       const int cout = widths[li];
       for (int b = 0; b < 2; ++b) {
         const std::string name = "layer" + std::to_string(li + 1) + "." + std::to_string(b);
         const int s = (li > 0 && b == 0) ? 2 : 1;
         const int ho = h / s, wo = w / s;
-        const int t = buf(ho, wo, cout), o = buf(ho, wo, cout);
+        // layers 2-4 live in zero-bordered buffers: their 3x3 stride-1 convolutions run over the flat padded
+        // raster (conv_win.cu, operand mode 4) instead of nine im2col loads per tile on these small maps
+        const int pd = (li > 0 && !no_pad) ? 1 : 0;
+        const int t = buf(ho, wo, cout, pd), o = buf(ho, wo, cout, pd);
         conv(name + ".conv1", V(cur), h, w, V(t), c, cout, 3, s, 2);
         int resbuf = cur;
         if (tensors->count(name + ".downsample.0.weight")) {
-          resbuf = buf(ho, wo, cout);
+          resbuf = buf(ho, wo, cout, pd);
           conv(name + ".downsample.0", V(cur), h, w, V(resbuf), c, cout, 1, s, 0);
         }
         conv(name + ".conv2", V(t), ho, wo, V(o), cout, cout, 3, 1, 2, V(resbuf), 2);
@@ -325,7 +330,7 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
     auto geom = [&](const View& v, int fallback_c, const __nv_bfloat16** ptr, long long* img_stride, int* cstride) {
       if (v.buf >= 0) {
         const Buffer& b = e->buffers[v.buf];
-        *ptr = b.ptr; *cstride = b.c; *img_stride = static_cast<long long>(b.h) * b.w * b.c;
+        *ptr = b.ptr; *cstride = b.c; *img_stride = static_cast<long long>(b.h + 2 * b.pad) * (b.w + 2 * b.pad) * b.c;
       } else if (v.buf == -1) {
         *ptr = static_cast<const __nv_bfloat16*>(input); *cstride = 4;
         *img_stride = static_cast<long long>(e->in_h) * e->in_w * 4;
@@ -368,6 +373,10 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
         }
         L.act = op.act;
         L.batch_dev = n_dev;
+        L.in_pad = op.in.buf >= 0 ? e->buffers[op.in.buf].pad : 0;
+        L.out_pad = op.out.buf >= 0 ? e->buffers[op.out.buf].pad : 0;
+        if (op.res_mode && op.res.buf >= 0 && e->buffers[op.res.buf].pad != L.out_pad)
+          return fail(AICAM_ERR_INVALID_ARG, "engine: residual and output layouts differ");
         rc = launch_conv(pc, L, stream);
         break;
       }
@@ -392,9 +401,13 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
         if (!rc) rc = launch_stem_pool(e->stem, in8, batch, op.h, op.w, n_dev, const_cast<__nv_bfloat16*>(op_), stream);
         break;
       }
-      case Op::AVGL2:
-        rc = launch_avgpool_l2norm(ip, batch, op.h * op.w, op.c, static_cast<float*>(output), stream, n_dev);
+      case Op::AVGL2: {
+        // a padded buffer is summed border and all (the border is zero) and divided by the interior count
+        const int pd = op.in.buf >= 0 ? e->buffers[op.in.buf].pad : 0;
+        rc = launch_avgpool_l2norm(ip, batch, (op.h + 2 * pd) * (op.w + 2 * pd), op.h * op.w, op.c, static_cast<float*>(output),
+                                   stream, n_dev);
         break;
+      }
     }
     if (rc) return rc;
   }
@@ -599,19 +612,28 @@ int aicam_conv2d(const aicam_conv_desc* d, const void* in, const float* w, const
     if (se != cudaSuccess) return fail(AICAM_ERR_CUDA, std::string("conv2d: ") + cudaGetErrorString(se));
     return AICAM_OK;
   }
+  return aicam_conv2d_padded(d, in, w, bias, res, out, 0, 0, stream);
+}
+
+int aicam_conv2d_padded(const aicam_conv_desc* d, const void* in, const float* w, const float* bias, const void* res,
+                        void* out, int in_pad, int out_pad, void* stream) {
+  if (!d || !in || !w || !out) return fail(AICAM_ERR_INVALID_ARG, "conv2d: null argument");
+  PackedConv pc;
   if (int rc = pack_conv_weights(w, bias, d->cout, d->cin, d->ksize, d->stride, &pc)) return rc;
   ConvLaunch L;
   const int cs = pc.cin_pad;
+  const int ip = in_pad ? 1 : 0, opd = out_pad ? 1 : 0;
   L.in = static_cast<const __nv_bfloat16*>(in);
-  L.in_img_stride = static_cast<long long>(d->h) * d->w * cs; L.in_cstride = cs; L.in_coff = 0;
+  L.in_img_stride = static_cast<long long>(d->h + 2 * ip) * (d->w + 2 * ip) * cs; L.in_cstride = cs; L.in_coff = 0;
   L.batch = d->batch; L.h = d->h; L.w = d->w;
   L.ho = (d->h + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
   L.wo = (d->w + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
-  L.out = out; L.out_img_stride = static_cast<long long>(L.ho) * L.wo * d->cout; L.out_cstride = d->cout;
+  L.out = out; L.out_img_stride = static_cast<long long>(L.ho + 2 * opd) * (L.wo + 2 * opd) * d->cout; L.out_cstride = d->cout;
   L.out_coff = 0; L.out_f32 = d->out_f32;
   L.res = static_cast<const __nv_bfloat16*>(res); L.res_img_stride = L.out_img_stride; L.res_cstride = d->cout;
   L.res_coff = 0; L.res_mode = res ? d->res_mode : 0;
   L.act = d->act;
+  L.in_pad = ip; L.out_pad = opd;
   int rc = launch_conv(pc, L, static_cast<cudaStream_t>(stream));
   cudaError_t se = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
   free_packed_conv(&pc);
@@ -657,8 +679,10 @@ int aicam_conv2d_bench(const aicam_conv_desc* d, int iters, double* mean_ms, voi
   const int cs = c0 ? c0 : pc.cin_pad;
   const int ho = (d->h + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
   const int wo = (d->w + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
-  const size_t in_elems = static_cast<size_t>(d->batch) * d->h * d->w * cs;
-  const size_t out_elems = static_cast<size_t>(d->batch) * ho * wo * d->cout;
+  // AICAM_BENCH_PAD=1: 3x3 stride-1 layers are timed over zero-bordered tensors (operand mode 4)
+  const int bp = (getenv("AICAM_BENCH_PAD") && d->ksize == 3 && d->stride == 1 && !c0) ? 1 : 0;
+  const size_t in_elems = static_cast<size_t>(d->batch) * (d->h + 2 * bp) * (d->w + 2 * bp) * cs;
+  const size_t out_elems = static_cast<size_t>(d->batch) * (ho + 2 * bp) * (wo + 2 * bp) * d->cout;
   __nv_bfloat16 *in = nullptr, *res = nullptr;
   void* out = nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -669,12 +693,13 @@ int aicam_conv2d_bench(const aicam_conv_desc* d, int iters, double* mean_ms, voi
     AICAM_CUDA_OK(cudaMalloc(&res, out_elems * 2));
     AICAM_CUDA_OK(cudaMemset(res, 0x3c, out_elems * 2));
   }
-  L.in = in; L.in_img_stride = static_cast<long long>(d->h) * d->w * cs; L.in_cstride = cs; L.in_coff = 0;
+  L.in = in; L.in_img_stride = static_cast<long long>(d->h + 2 * bp) * (d->w + 2 * bp) * cs; L.in_cstride = cs; L.in_coff = 0;
   L.batch = d->batch; L.h = d->h; L.w = d->w; L.ho = ho; L.wo = wo;
+  L.in_pad = bp; L.out_pad = bp;
   if (c0) {  // the timed launches read the same bytes as an already space-to-depth tensor
     L.in_cstride = 4 * c0; L.h = d->h / 2; L.w = d->w / 2; L.ho = L.h; L.wo = L.w;
   }
-  L.out = out; L.out_img_stride = static_cast<long long>(ho) * wo * d->cout; L.out_cstride = d->cout; L.out_coff = 0;
+  L.out = out; L.out_img_stride = static_cast<long long>(ho + 2 * bp) * (wo + 2 * bp) * d->cout; L.out_cstride = d->cout; L.out_coff = 0;
   L.out_f32 = d->out_f32;
   L.res = res; L.res_img_stride = L.out_img_stride; L.res_cstride = d->cout; L.res_coff = 0; L.res_mode = d->res_mode;
   L.act = d->act;

@@ -67,7 +67,7 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, long lon
 }
 
 // One block per image: mean over hw pixels of each of c channels, then x / ||x||_2 (fp32).
-__global__ void avgpool_l2norm_kernel(const __nv_bfloat16* __restrict__ in, int hw, int c, float* __restrict__ out,
+__global__ void avgpool_l2norm_kernel(const __nv_bfloat16* __restrict__ in, int hw, int hw_div, int c, float* __restrict__ out,
                                       const int* __restrict__ n_dev) {
   extern __shared__ float red[];
   const int n = blockIdx.x;
@@ -77,7 +77,7 @@ __global__ void avgpool_l2norm_kernel(const __nv_bfloat16* __restrict__ in, int 
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     float s = 0.0f;
     for (int p = 0; p < hw; ++p) s += __bfloat162float(base[static_cast<long long>(p) * c + ch]);
-    s /= static_cast<float>(hw);
+    s /= static_cast<float>(hw_div);
     out[static_cast<long long>(n) * c + ch] = s;
     ss += s * s;
   }
@@ -163,10 +163,10 @@ int launch_upsample2x(const __nv_bfloat16* in, long long in_img_stride, int in_c
   return last_launch("upsample2x_kernel");
 }
 
-int launch_avgpool_l2norm(const __nv_bfloat16* in, int batch, int hw, int c, float* out, cudaStream_t stream,
+int launch_avgpool_l2norm(const __nv_bfloat16* in, int batch, int hw, int hw_div, int c, float* out, cudaStream_t stream,
                           const int* n_dev) {
   if (batch == 0) return AICAM_OK;
-  avgpool_l2norm_kernel<<<batch, 256, 256 * sizeof(float), stream>>>(in, hw, c, out, n_dev);
+  avgpool_l2norm_kernel<<<batch, 256, 256 * sizeof(float), stream>>>(in, hw, hw_div, c, out, n_dev);
   count_launch();
   return last_launch("avgpool_l2norm_kernel");
 }

@@ -114,6 +114,14 @@ typedef struct {
 } aicam_conv_desc;
 int aicam_conv2d(const aicam_conv_desc* d, const void* in_nhwc, const float* weights_oihw,
                  const float* bias, const void* res_nhwc, void* out_nhwc, void* stream);
+/* The same operator over zero-bordered ("padded") tensors: with in_pad / out_pad = 1 the input / the output and
+ * residual are [batch][h + 2][w + 2][c] with a one-pixel border of zeros, interior at (1, 1); the border of
+ * the output is never written (it must be zero already).  This is the layout the ReID engine keeps layers 2-4
+ * in, so that their 3x3 stride-1 layers run over one flat raster of padded pixels (csrc/conv_win.cu, mode 4).
+ * Supported: 3x3 stride 1 with in_pad = out_pad = 1; any stride-2 layer with either flag. */
+int aicam_conv2d_padded(const aicam_conv_desc* d, const void* in_nhwc, const float* weights_oihw,
+                        const float* bias, const void* res_nhwc, void* out_nhwc, int in_pad, int out_pad,
+                        void* stream);
 /* Micro-benchmark of the same operator on device-resident random data: `iters` launches
  * bracketed by CUDA events on `stream`; returns the mean kernel time in milliseconds. */
 int aicam_conv2d_bench(const aicam_conv_desc* d, int iters, double* mean_ms, void* stream);

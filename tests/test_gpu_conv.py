@@ -84,6 +84,70 @@ def test_conv_matches_torch(case):
         got.flat[err.argmax()], want.flat[err.argmax()])
 
 
+PADDED_CASES = [
+    # name, B, H, W, cin, cout, k, s, act, res_mode, in_pad, out_pad
+    # zero-bordered tensors (ReID layers 2-4): 3x3 stride 1 over the flat padded raster (conv_win.cu mode 4) ...
+    ("pad_l2_128", 5, 32, 16, 128, 128, 3, 1, 2, 2, 1, 1),
+    ("pad_l3_256", 9, 16, 8, 256, 256, 3, 1, 2, 2, 1, 1),
+    ("pad_l3_256_nores", 3, 16, 8, 256, 256, 3, 1, 2, 0, 1, 1),
+    ("pad_l4_512", 13, 8, 4, 512, 512, 3, 1, 2, 2, 1, 1),
+    ("pad_one_image", 1, 8, 4, 64, 64, 3, 1, 1, 1, 1, 1),
+    ("pad_odd_13x7_c64_96", 4, 13, 7, 64, 96, 3, 1, 0, 0, 1, 1),
+    # ... and the stride-2 layers that enter / leave the padded geometry (im2col mode)
+    ("pad_out_s2_64_128", 5, 64, 32, 64, 128, 3, 2, 2, 0, 0, 1),
+    ("pad_out_1x1s2_64_128", 5, 64, 32, 64, 128, 1, 2, 0, 0, 0, 1),
+    ("pad_inout_s2_128_256", 7, 32, 16, 128, 256, 3, 2, 2, 0, 1, 1),
+    ("pad_inout_1x1s2_256_512", 7, 16, 8, 256, 512, 1, 2, 0, 0, 1, 1),
+    ("pad_in_s2_odd_15x9", 3, 15, 9, 32, 32, 3, 2, 1, 0, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", PADDED_CASES, ids=[c[0] for c in PADDED_CASES])
+def test_padded_conv_matches_torch(case):
+    """Same operator over zero-bordered tensors; the output border must stay exactly zero."""
+    import ctypes as C
+    import gpu_util as G
+    from ai_camera_b200._lib import ConvDesc, check, ptr
+    name, B, H, W, cin, cout, k, s, act, res_mode, ipad, opad = case
+    rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
+    x = G.bf16_round_np(rng.normal(0, 1, (B, H, W, cin)))
+    w = G.bf16_round_np(rng.normal(0, 1.0 / np.sqrt(cin * k * k), (cout, cin, k, k)))
+    b = rng.normal(0, 0.5, cout).astype(np.float32)
+    ho, wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+    res = G.bf16_round_np(rng.normal(0, 1, (B, ho, wo, cout))) if res_mode else None
+
+    def padded(a, on):
+        return np.pad(a, ((0, 0), (1, 1), (1, 1), (0, 0))) if on else a
+
+    xd = torch.from_numpy(padded(x, ipad)).to(G.DEV).to(torch.bfloat16).contiguous()
+    rd = torch.from_numpy(padded(res, opad)).to(G.DEV).to(torch.bfloat16).contiguous() if res_mode else None
+    out = torch.zeros((B, ho + 2 * opad, wo + 2 * opad, cout), dtype=torch.bfloat16, device=G.DEV)
+    d = ConvDesc(B, H, W, cin, cout, k, s, act, res_mode, 0)
+    check(G.lib().aicam_conv2d_padded(C.byref(d), ptr(xd), ptr(np.ascontiguousarray(w)), ptr(b), ptr(rd), ptr(out),
+                                      ipad, opad, None))
+    got = out.float().cpu().numpy()
+    if opad:
+        border = got.copy()
+        border[:, 1:-1, 1:-1, :] = 0
+        assert not border.any(), "%s: the zero border was written" % name
+        got = got[:, 1:-1, 1:-1, :]
+    y = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(w), torch.from_numpy(b), stride=s,
+                 padding=k // 2)
+    r = torch.from_numpy(res).permute(0, 3, 1, 2) if res_mode else None
+    if res_mode == 2:
+        y = y + r
+    y = F.silu(y) if act == 1 else (F.relu(y) if act == 2 else y)
+    if res_mode == 1:
+        y = y + r
+    want = y.permute(0, 2, 3, 1).numpy()
+    assert got.shape == want.shape
+    err = np.abs(got - want)
+    bad = err > 2e-2 + 1e-2 * np.abs(want)
+    assert not bad.any(), "%s: %d/%d elements off, max abs err %.4g at %s (got %.5g want %.5g)" % (
+        name, bad.sum(), bad.size, err.max(), np.unravel_index(err.argmax(), err.shape),
+        got.flat[err.argmax()], want.flat[err.argmax()])
+
+
 @pytest.mark.parametrize("shape", [(3, 128, 64), (2, 24, 40), (5, 6, 2)], ids=["reid_128x64", "odd_tiles_24x40", "tiny_6x2"])
 def test_fused_stem_pool_matches_torch(shape):
     """stem_pool.cu: conv3x3(3->64) + bias + ReLU + maxpool(3, s2, p1) fused, vs torch fp32 on the same
