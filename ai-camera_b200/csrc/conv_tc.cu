@@ -649,7 +649,7 @@ int pack_conv_weights(const float* w, const float* bias, int cout, int cin, int 
   AICAM_CUDA_OK(cudaMalloc(&p.bias, b.size() * 4));
   AICAM_CUDA_OK(cudaMemcpy(p.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
   AICAM_CUDA_OK(cudaMemcpy(p.bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
-  const int nb = pick_n_tile(cout_pad, false);
+  const int nb = cout_pad % 256 == 0 ? 256 : pick_n_tile(cout_pad, false);  // (conv_win.cu takes 256-column tiles when it can)
   if (nb < cout_pad) {  // n-tile-major copy for the streamed-weight window kernel
     std::vector<uint16_t> nt(packed.size());
     for (int qq = 0; qq < q_pad; ++qq)

@@ -65,9 +65,9 @@ struct WinArgs {
   float inv_rw;
   // TMA epilogue (window modes, row-aligned tiles): compact staging tile [th * tw rows][piece channels], swizzled
   int th;                 // raster rows per tile
-  int pieces;             // channel pieces of an n-tile (1 or 2)
-  int piece_ch[2];        // channels per piece: 64 / 32 / 16
-  uint32_t piece_off[2];  // byte offset of the piece inside a staging buffer (1024-aligned)
+  int pieces;             // channel pieces of an n-tile: 1 or 2, or four 64-channel pieces (n_tile = 256)
+  int piece_ch[4];        // channels per piece: 64 / 32 / 16
+  uint32_t piece_off[4];  // byte offset of the piece inside a staging buffer (1024-aligned)
   uint32_t stage_buf_bytes, res_tx_bytes;
   int nres;               // residual staging buffers (TMA-loaded one or two tiles ahead)
   int nstage;             // output staging buffers (2: the store of tile i overlaps the staging of tile i + 1)
@@ -311,9 +311,9 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
     }
     const uint32_t taddr_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
     // per piece: byte offset of my row and the swizzle XOR of its 16-byte chunks
-    uint32_t row_off[2], row_xor[2];
+    uint32_t row_off[4], row_xor[4];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < 4; ++p) {
       const uint32_t pb = static_cast<uint32_t>(a.piece_ch[p]) * 2;
       const uint32_t ro = static_cast<uint32_t>(crow) * pb;
       const uint32_t mask = pb == 128 ? 7u : (pb == 64 ? 3u : 1u);
@@ -368,8 +368,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
           for (int h = 0; h < 2; ++h) {
             if (h == 1 && !two) break;
             const int c = (g + h) * 16;                      // first channel of the group inside the n-tile
-            const int p = c < a.piece_ch[0] ? 0 : 1;
-            const uint32_t ch0 = static_cast<uint32_t>(c - (p ? a.piece_ch[0] : 0)) * 2;  // byte offset inside the piece row
+            const int p = a.pieces > 2 ? (c >> 6) : (c < a.piece_ch[0] ? 0 : 1);  // (more than two pieces: all 64 wide)
+            const uint32_t ch0 = static_cast<uint32_t>(a.pieces > 2 ? (c & 63) : c - (p ? a.piece_ch[0] : 0)) * 2;  // byte offset inside the piece row
             const uint32_t o0 = row_off[p] + (ch0 ^ row_xor[p]), o1 = row_off[p] + ((ch0 + 16) ^ row_xor[p]);
             if (FLATWIN && zero_row) {
               *reinterpret_cast<uint4*>(stage + o0) = make_uint4(0u, 0u, 0u, 0u);
@@ -768,8 +768,11 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
           tma_load_4d(rdst + a.piece_off[0], &maps.res[0], rbar, n0, cx, cy, cn);
           if (a.pieces == 2) tma_load_4d(rdst + a.piece_off[1], &maps.res[1], rbar, n0 + a.piece_ch[0], cx, cy, cn);
         } else {
-          tma_load_2d(rdst + a.piece_off[0], &maps.res[0], rbar, n0, cx);
-          if (a.pieces == 2) tma_load_2d(rdst + a.piece_off[1], &maps.res[1], rbar, n0 + a.piece_ch[0], cx);
+          int pc0 = 0;  // first channel of the piece
+          for (int q = 0; q < a.pieces; ++q) {
+            tma_load_2d(rdst + a.piece_off[q], &maps.res[q ? 1 : 0], rbar, n0 + pc0, cx);
+            pc0 += a.piece_ch[q];
+          }
         }
       }
       __syncwarp();
@@ -794,8 +797,11 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
           tma_store_4d(&maps.out[0], src + a.piece_off[0], n0, cx, cy, cn);
           if (two) tma_store_4d(&maps.out[1], src + a.piece_off[1], n0 + a.piece_ch[0], cx, cy, cn);
         } else {
-          tma_store_2d(&maps.out[0], src + a.piece_off[0], n0, cx);
-          if (two) tma_store_2d(&maps.out[1], src + a.piece_off[1], n0 + a.piece_ch[0], cx);
+          int pc0 = 0;
+          for (int q = 0; q < a.pieces && n0 + pc0 < a.cout; ++q) {
+            tma_store_2d(&maps.out[q ? 1 : 0], src + a.piece_off[q], n0 + pc0, cx);
+            pc0 += a.piece_ch[q];
+          }
         }
         bulk_commit();
         bulk_wait_read_all();
@@ -957,6 +963,11 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   int n_tile = 16;
   for (int nt = L.out_f32 ? 80 : 128; nt >= 16; nt -= 16)
     if (cout_pad % nt == 0) { n_tile = nt; break; }
+  // 256-column tiles where the layer is wide enough: one 128 x 256 x 16 MMA reads 12 KB of operands in its 128
+  // tensor-pipe cycles (96 at 128 B/clk), a 128 x 128 one reads 8 KB in 64 - the narrower tile is bound by the
+  // shared-memory port (measured ~88 cycles per MMA), the wide one by the tensor pipe
+  static const bool no_n256 = getenv("AICAM_WIN_NO_N256") != nullptr;
+  if (!no_n256 && !L.out_f32 && cout_pad % 256 == 0 && (cout_pad == 256 || pc.nt_block == 256) && (mode == 4 || mode == 2 || mode == 1)) n_tile = 256;
   const int n_tiles = cout_pad / n_tile;
   const size_t wbytes = static_cast<size_t>(pc.q_pad) * cout_pad * 16;
   if (static_cast<size_t>(pc.q_pad) * 8 != static_cast<size_t>(taps) * pc.cin_pad) return 0;
@@ -965,13 +976,13 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   const uint32_t bstage_bytes = static_cast<uint32_t>(slab / 8) * n_tile * 16;
   const uint32_t stage_pitch = n_tile * es + 16;
   const uint32_t res_pitch = n_tile * 2 + 16;
-  const int sb = resident ? 0 : 4;
+  const int sb = resident ? 0 : (n_tile == 256 ? 3 : 4);  // 32 KB stages at 256 columns
   // mode 4 fallback when the TMA epilogue is unavailable: no staging tile, every thread stores its own 32-byte groups
   // (measured: ~15k cycles per 256 x 128 tile, LSU-bound - one sector per lane per instruction)
   static const bool no_tma_epi4 = getenv("AICAM_WIN_NO_TMA_EPI") != nullptr;
   const int nt_rest = n_tile - (n_tile >= 64 ? 64 : (n_tile >= 32 ? 32 : 16));  // the n-tile splits into <= 2 swizzled pieces
   const bool epi4 = mode == 4 && !no_tma_epi4 && !L.out_f32 && pc.cout % 8 == 0 &&
-                    (nt_rest == 0 || nt_rest == 64 || nt_rest == 32 || nt_rest == 16);
+                    (n_tile == 256 || nt_rest == 0 || nt_rest == 64 || nt_rest == 32 || nt_rest == 16);
   const bool direct_out = mode == 4 && !resident && !L.out_f32 && !epi4;
   // streamed (deep-K) layers: the epilogue is a small share of a tile, read the residual from global there
   // instead of spending 70 KB of shared memory that the 256-row tiling needs
@@ -981,8 +992,10 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   // ---- TMA epilogue (window modes, bf16, natural layout): the n-tile splits into one or two channel pieces
   // of 64 / 32 / 16 channels, each a swizzled staging tile with its own output / residual tensor map
   static const bool no_tma_epi = getenv("AICAM_WIN_NO_TMA_EPI") != nullptr;
-  int piece_ch[2] = {0, 0};
-  {
+  int piece_ch[4] = {0, 0, 0, 0};
+  if (n_tile == 256) {
+    piece_ch[0] = piece_ch[1] = piece_ch[2] = piece_ch[3] = 64;
+  } else {
     const int first = n_tile >= 64 ? 64 : (n_tile >= 32 ? 32 : 16);
     const int rest = n_tile - first;
     if (rest == 0 || rest == 64 || rest == 32 || rest == 16) { piece_ch[0] = first; piece_ch[1] = rest; }
@@ -1034,7 +1047,7 @@ plan:
             // compact staging tile(s): output + residual ring, every piece 1024-byte aligned
             const int rows_c = (p.tstep / p.rw) * p.tw;
             size_t buf = 0;
-            for (int q = 0; q < 2; ++q)
+            for (int q = 0; q < 4; ++q)
               if (piece_ch[q]) buf += (static_cast<size_t>(rows_c) * piece_ch[q] * 2 + 1023) / 1024 * 1024;
             p.stage_buf = static_cast<uint32_t>(buf);
             p.nres = res_mode ? 2 : 0;
@@ -1057,7 +1070,7 @@ plan:
           if (epi) {
             // the residual tile is loaded into the staging buffer and finished in place: no residual ring
             size_t buf = 0;
-            for (int q = 0; q < 2; ++q)
+            for (int q = 0; q < 4; ++q)
               if (piece_ch[q]) buf += (static_cast<size_t>(tm) * piece_ch[q] * 2 + 1023) / 1024 * 1024;
             p.stage_buf = static_cast<uint32_t>(buf);
             p.nstage = 2;
@@ -1072,7 +1085,7 @@ plan:
           p.tiles = (pixels + tm - 1) / tm;
           if (epi) {
             size_t buf = 0;
-            for (int q = 0; q < 2; ++q)
+            for (int q = 0; q < 4; ++q)
               if (piece_ch[q]) buf += (static_cast<size_t>(tm) * piece_ch[q] * 2 + 1023) / 1024 * 1024;
             p.stage_buf = static_cast<uint32_t>(buf);
             p.nres = res_mode ? 2 : 0;
@@ -1170,11 +1183,11 @@ plan:
     a.off_res = a.off_stage + best.nstage * best.stage_buf;
     a.stage_buf_bytes = best.stage_buf;
     a.nres = best.nres;
-    a.pieces = piece_ch[1] ? 2 : 1;
+    a.pieces = piece_ch[2] ? 4 : (piece_ch[1] ? 2 : 1);
     const int rows_c = window ? a.th * best.tw : a.tm;
     uint32_t off = 0;
     a.res_tx_bytes = 0;
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < 4; ++q) {
       a.piece_ch[q] = piece_ch[q];
       a.piece_off[q] = off;
       off += static_cast<uint32_t>((static_cast<size_t>(rows_c) * piece_ch[q] * 2 + 1023) / 1024 * 1024);
@@ -1233,7 +1246,7 @@ plan:
 
   if (epi) {
     // output / residual boxes: [piece channels][tw columns][th rows][1 image] of the NHWC tensor (channel slice)
-    for (int q = 0; q < a.pieces && cr == CUDA_SUCCESS; ++q) {
+    for (int q = 0; q < std::min(a.pieces, 2) && cr == CUDA_SUCCESS; ++q) {  // (pieces beyond the second reuse map 1)
       const int pb = piece_ch[q] * 2;
       const CUtensorMapSwizzle psw = pb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (pb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
       if (!window) {

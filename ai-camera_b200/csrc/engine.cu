@@ -268,12 +268,16 @@ struct Builder {
     const int H = AICAM_REID_H, W = AICAM_REID_W;
     e->in_h = H; e->in_w = W;
     int h = H / 2, w = W / 2, c = 64;
-    int cur = buf(h, w, c);
+    int cur = -1, pad1 = 0;
     static const bool unfused = getenv("AICAM_NO_STEM_FUSION") != nullptr;
+    static const bool no_pad = getenv("AICAM_NO_PADDED_REID") != nullptr;
+    static const bool no_pad1 = getenv("AICAM_NO_PADDED_L1") != nullptr;
     auto wi = tensors->find("conv.0.weight");
     auto bi = tensors->find("conv.0.bias");
     if (!unfused && wi != tensors->end() && bi != tensors->end() && wi->second.dims.size() == 4 && wi->second.dims[0] == 64 &&
         wi->second.dims[1] == 3 && wi->second.dims[2] == 3 && static_cast<int>(bi->second.count) == 64) {
+      pad1 = (no_pad || no_pad1) ? 0 : 1;  // the fused stem writes the zero-bordered layout directly
+      cur = buf(h, w, c, pad1);
       // fused stem: crops NHWC4 -> NHWC8 -> conv3x3 + ReLU + maxpool 3x3 s2 in one kernel (stem_pool.cu)
       if (int rc = pack_stem_pool(wi->second.data, bi->second.data, 64, 3, &e->stem)) { err = rc; return; }
       e->stem_in8 = buf(H, W, 8);
@@ -281,12 +285,12 @@ struct Builder {
       e->ops.push_back(op);
       e->macs_per_item += static_cast<double>(H) * W * 64 * 3 * 9;
     } else {
+      cur = buf(h, w, c);
       const int s0 = buf(H, W, 64);
       conv("conv.0", V(-1), H, W, V(s0), 3, 64, 3, 1, 2);
       pool(V(s0), V(cur), H, W, 64, 3, 2);
     }
     const int widths[4] = {64, 128, 256, 512};
-    static const bool no_pad = getenv("AICAM_NO_PADDED_REID") != nullptr;
     for (int li = 0; li < 4; ++li) {
       const int cout = widths[li];
       for (int b = 0; b < 2; ++b) {
@@ -295,7 +299,7 @@ struct Builder {
         const int ho = h / s, wo = w / s;
         // layers 2-4 live in zero-bordered buffers: their 3x3 stride-1 convolutions run over the flat padded
         // raster (conv_win.cu, operand mode 4) instead of nine im2col loads per tile on these small maps
-        const int pd = (li > 0 && !no_pad) ? 1 : 0;
+        const int pd = li > 0 ? (no_pad ? 0 : 1) : pad1;
         const int t = buf(ho, wo, cout, pd), o = buf(ho, wo, cout, pd);
         conv(name + ".conv1", V(cur), h, w, V(t), c, cout, 3, s, 2);
         int resbuf = cur;
@@ -398,7 +402,8 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
           rc = launch_nhwc4_to_nhwc8(ip, batch, op.h, op.w, tmp, n_dev, stream);
           in8 = tmp;
         }
-        if (!rc) rc = launch_stem_pool(e->stem, in8, batch, op.h, op.w, n_dev, const_cast<__nv_bfloat16*>(op_), stream);
+        if (!rc) rc = launch_stem_pool(e->stem, in8, batch, op.h, op.w, n_dev, const_cast<__nv_bfloat16*>(op_), stream,
+                                       op.out.buf >= 0 ? e->buffers[op.out.buf].pad : 0);
         break;
       }
       case Op::AVGL2: {

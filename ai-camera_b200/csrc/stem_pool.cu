@@ -59,6 +59,7 @@ struct StemArgs {
   const float* bias;
   __nv_bfloat16* out;
   int h, w, ph, pw;  // convolution size (= input size), pooled size
+  int out_pad;       // 1: the output images are zero-bordered, [ph + 2][pw + 2][64] with the interior at (1, 1)
   int tiles_y, tiles_x;
   int batch;
   const int* batch_dev;
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(THREADS, 1) reid_stem_pool_kernel(const StemAr
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             ow[i] = pack_bf16x2(fmaxf(bf16_lo(mw[i]) + pbias[2 * i], 0.0f), fmaxf(bf16_hi(mw[i]) + pbias[2 * i + 1], 0.0f));
-          *reinterpret_cast<uint4*>(a.out + ((static_cast<long long>(n) * a.ph + py) * a.pw + px) * COUT + pg * 8) =
+          *reinterpret_cast<uint4*>(a.out + ((static_cast<long long>(n) * (a.ph + 2 * a.out_pad) + py + a.out_pad) * (a.pw + 2 * a.out_pad) + px + a.out_pad) * COUT + pg * 8) =
               make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
       }
@@ -345,13 +346,13 @@ int launch_nhwc4_to_nhwc8(const __nv_bfloat16* in, int batch, int h, int w, __nv
 }
 
 int launch_stem_pool(const StemPool& sp, const __nv_bfloat16* in_nhwc8, int batch, int h, int w, const int* n_dev,
-                     __nv_bfloat16* out, cudaStream_t stream) {
+                     __nv_bfloat16* out, cudaStream_t stream, int out_pad) {
   if (batch <= 0) return AICAM_OK;
   if (encode_tiled() == nullptr) return fail(AICAM_ERR_CUDA, "stem_pool: cuTensorMapEncodeTiled is not available");
   if (h % 2 || w % 2) return fail(AICAM_ERR_INVALID_ARG, "stem_pool: even input sizes only");
   StemArgs a;
   a.wgt = sp.w; a.bias = sp.bias; a.out = out;
-  a.h = h; a.w = w; a.ph = h / 2; a.pw = w / 2;
+  a.h = h; a.w = w; a.ph = h / 2; a.pw = w / 2; a.out_pad = out_pad ? 1 : 0;
   a.tiles_y = cdiv(a.ph, PH); a.tiles_x = cdiv(a.pw, PW);
   a.batch = batch; a.batch_dev = n_dev;
   alignas(64) CUtensorMap tmap;

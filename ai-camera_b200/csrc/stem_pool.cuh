@@ -14,8 +14,9 @@ void free_stem_pool(StemPool* s);
 // in: bf16 [batch][h][w][4] -> out: bf16 [batch][h][w][8] (zero upper channels)
 int launch_nhwc4_to_nhwc8(const __nv_bfloat16* in, int batch, int h, int w, __nv_bfloat16* out, const int* n_dev,
                           cudaStream_t stream);
-// in: bf16 NHWC8 [batch][h][w][8]; out: bf16 [batch][h/2][w/2][64]
+// in: bf16 NHWC8 [batch][h][w][8]; out: bf16 [batch][h/2][w/2][64], or with out_pad the zero-bordered
+// [batch][h/2 + 2][w/2 + 2][64] (interior at (1, 1), border untouched)
 int launch_stem_pool(const StemPool& sp, const __nv_bfloat16* in_nhwc8, int batch, int h, int w, const int* n_dev,
-                     __nv_bfloat16* out, cudaStream_t stream);
+                     __nv_bfloat16* out, cudaStream_t stream, int out_pad = 0);
 
 }  // namespace aicam
