@@ -23,8 +23,8 @@ namespace {
 
 constexpr int RH = AICAM_REID_H, RW = AICAM_REID_W;
 
-// One block, one thread per frame: stable filter of the frame's detections, crop rectangles,
-// and (via a block-wide exclusive scan) deterministic crop rows.
+// One block, one WARP per frame: stable filter of the frame's detections (ballot compaction, lanes over
+// detections), crop rectangles, and (via a block-wide exclusive scan over frames) deterministic crop rows.
 __global__ void __launch_bounds__(1024) filter_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
                                                       const int* __restrict__ labels, const int* __restrict__ num_dets,
                                                       int batch, int stride_k, int h, int w, float min_conf,
@@ -32,67 +32,78 @@ __global__ void __launch_bounds__(1024) filter_kernel(const float* __restrict__ 
                                                       int max_crops, int* __restrict__ det_index,
                                                       int* __restrict__ det_count, int* __restrict__ crop_slot,
                                                       int* __restrict__ crop_rect, int* __restrict__ crop_count) {
-  __shared__ int s_scan[1024];
+  __shared__ int s_scan[32];  // valid crops per frame of the current group of 32 frames, then their exclusive scan
   __shared__ int s_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
   if (threadIdx.x == 0) s_base = 0;
   __syncthreads();
-  for (int b0 = 0; b0 < batch; b0 += blockDim.x) {
-    const int b = b0 + threadIdx.x;
+  for (int b0 = 0; b0 < batch; b0 += 32) {
+    const int b = b0 + warp;
     int nvalid = 0, nkeep = 0;
     if (b < batch) {
       const int n = min(num_dets[b], stride_k);
-      for (int i = 0; i < n; ++i) {
-        const long long o = static_cast<long long>(b) * stride_k + i;
-        const int cls = labels[o];
-        const bool tracked = cls >= 0 && cls < 128 && (((cls < 64 ? mask_lo >> cls : mask_hi >> (cls - 64)) & 1ull) != 0);
-        if (!(scores[o] >= min_conf && tracked)) continue;
-        const float4 bx = reinterpret_cast<const float4*>(boxes)[o];
-        const int x1 = max(0, static_cast<int>(bx.x)), y1 = max(0, static_cast<int>(bx.y));
-        const int x2 = min(w, static_cast<int>(bx.z)), y2 = min(h, static_cast<int>(bx.w));
-        det_index[static_cast<long long>(b) * stride_k + nkeep] = i;
-        // provisional: local crop ordinal or -1; rebased after the scan
-        crop_slot[static_cast<long long>(b) * stride_k + nkeep] = (x1 < x2 && y1 < y2) ? nvalid : -1;
-        if (x1 < x2 && y1 < y2) ++nvalid;
-        ++nkeep;
-      }
-      det_count[b] = nkeep;
-    }
-    // exclusive scan of nvalid over the block
-    s_scan[threadIdx.x] = nvalid;
-    __syncthreads();
-    for (int o = 1; o < static_cast<int>(blockDim.x); o <<= 1) {
-      const int v = threadIdx.x >= static_cast<unsigned>(o) ? s_scan[threadIdx.x - o] : 0;
-      __syncthreads();
-      s_scan[threadIdx.x] += v;
-      __syncthreads();
-    }
-    const int base = s_base + s_scan[threadIdx.x] - nvalid;
-    if (b < batch) {
-      const int n = min(num_dets[b], stride_k);
-      int k = 0;
-      for (int i = 0; i < n && k < nkeep; ++i) {
-        const long long o = static_cast<long long>(b) * stride_k + i;
-        if (det_index[static_cast<long long>(b) * stride_k + k] != i) continue;
-        const long long ko = static_cast<long long>(b) * stride_k + k;
-        if (crop_slot[ko] >= 0) {
-          const int slot = base + crop_slot[ko];
-          if (slot < max_crops) {
-            const float4 bx = reinterpret_cast<const float4*>(boxes)[o];
-            crop_slot[ko] = slot;
-            crop_rect[slot * 5 + 0] = b;
-            crop_rect[slot * 5 + 1] = max(0, static_cast<int>(bx.x));
-            crop_rect[slot * 5 + 2] = max(0, static_cast<int>(bx.y));
-            crop_rect[slot * 5 + 3] = min(w, static_cast<int>(bx.z));
-            crop_rect[slot * 5 + 4] = min(h, static_cast<int>(bx.w));
-          } else {
-            crop_slot[ko] = -1;
+      const long long fo = static_cast<long long>(b) * stride_k;
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        bool keep = false, ok = false;
+        if (i < n) {
+          const int cls = labels[fo + i];
+          const bool tracked = cls >= 0 && cls < 128 && (((cls < 64 ? mask_lo >> cls : mask_hi >> (cls - 64)) & 1ull) != 0);
+          keep = scores[fo + i] >= min_conf && tracked;
+          if (keep) {
+            const float4 bx = reinterpret_cast<const float4*>(boxes)[fo + i];
+            const int x1 = max(0, static_cast<int>(bx.x)), y1 = max(0, static_cast<int>(bx.y));
+            const int x2 = min(w, static_cast<int>(bx.z)), y2 = min(h, static_cast<int>(bx.w));
+            ok = x1 < x2 && y1 < y2;
           }
         }
-        ++k;
+        const unsigned km = __ballot_sync(0xffffffffu, keep), vm = __ballot_sync(0xffffffffu, ok);
+        if (keep) {
+          const int k = nkeep + __popc(km & lt);
+          det_index[fo + k] = i;
+          // provisional: local crop ordinal or -1; rebased after the scan
+          crop_slot[fo + k] = ok ? nvalid + __popc(vm & lt) : -1;
+        }
+        nkeep += __popc(km);
+        nvalid += __popc(vm);
       }
+      if (lane == 0) det_count[b] = nkeep;
+    }
+    if (lane == 0) s_scan[warp] = nvalid;
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the group's 32 counts
+      const int v = s_scan[lane];
+      int incl = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      s_scan[lane] = s_base + incl - v;
+      __syncwarp();
+      if (lane == 31) s_base += incl;
     }
     __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) s_base += s_scan[threadIdx.x];
+    if (b < batch) {
+      const int base = s_scan[warp];
+      const long long fo = static_cast<long long>(b) * stride_k;
+      for (int k = lane; k < nkeep; k += 32) {  // (my own writes of det_index / crop_slot: same warp, ordered by the barriers)
+        const int local = crop_slot[fo + k];
+        if (local < 0) continue;
+        const int slot = base + local;
+        if (slot < max_crops) {
+          const float4 bx = reinterpret_cast<const float4*>(boxes)[fo + det_index[fo + k]];
+          crop_slot[fo + k] = slot;
+          crop_rect[slot * 5 + 0] = b;
+          crop_rect[slot * 5 + 1] = max(0, static_cast<int>(bx.x));
+          crop_rect[slot * 5 + 2] = max(0, static_cast<int>(bx.y));
+          crop_rect[slot * 5 + 3] = min(w, static_cast<int>(bx.z));
+          crop_rect[slot * 5 + 4] = min(h, static_cast<int>(bx.w));
+        } else {
+          crop_slot[fo + k] = -1;
+        }
+      }
+    }
     __syncthreads();
   }
   if (threadIdx.x == 0) *crop_count = min(s_base, max_crops);

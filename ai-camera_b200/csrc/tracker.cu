@@ -346,6 +346,7 @@ struct StepIO {
   const float* boxes; const float* scores; const int* labels; int stride_k;
   const int* det_index; const int* det_count; const int* crop_slot;
   int* out_tracks; float* out_conf; int* out_count;
+  int cm_in_smem;  // the T x D cost matrix fits in shared memory (else the per-stream global workspace)
 };
 
 // K7 + K9-K12: predict, cascade, IoU stage, update, initiate, prune, output.  One CTA per stream.
@@ -365,9 +366,15 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
   int* match = reinterpret_cast<int*>(p); p += sizeof(int) * T;       // by order position: detection or -1
   int* cfr = reinterpret_cast<int*>(p); p += sizeof(int) * T;         // col_for_row of the current LSAP
   int* det_used = reinterpret_cast<int*>(p); p += sizeof(int) * Dm;
+  // per-position copies of the track list and of the two fields every serial phase keeps asking for: the
+  // single-thread loops below (lists, cascade levels, prune, output) then run on shared-memory latency
+  int* ord = reinterpret_cast<int*>(p); p += sizeof(int) * T;        // order[k]: slot of the k-th track
+  int* st_state = reinterpret_cast<int*>(p); p += sizeof(int) * T;
+  int* st_tsu = reinterpret_cast<int*>(p); p += sizeof(int) * T;
   p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~static_cast<uintptr_t>(15));
   const int nmax = max(T, Dm);
   LsapMem lm = lsap_carve(p, nmax);
+  p += lsap_bytes(nmax);
   __shared__ int s_nconf, s_ntent, s_nU, s_nL, s_levels[8], s_nt;
 
   const long long sb = static_cast<long long>(s) * T;
@@ -378,7 +385,8 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
 
   // -- K7 predict (tracker_core.py:44-49, track.py:76-80)
   for (int k = tid; k < nt; k += ASSOC_THREADS) {
-    const long long ts = sb + order[k];
+    const int slot = order[k];
+    const long long ts = sb + slot;
     float mean[8], cov[16];
     for (int i = 0; i < 8; ++i) mean[i] = t.mean[ts * 8 + i];
     for (int i = 0; i < 16; ++i) cov[i] = t.cov[ts * 16 + i];
@@ -386,7 +394,11 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
     for (int i = 0; i < 8; ++i) t.mean[ts * 8 + i] = mean[i];
     for (int i = 0; i < 16; ++i) t.cov[ts * 16 + i] = cov[i];
     t.age[ts] += 1;
-    t.tsu[ts] += 1;
+    const int tsu = t.tsu[ts] + 1;
+    t.tsu[ts] = tsu;
+    ord[k] = slot;
+    st_tsu[k] = tsu;
+    st_state[k] = t.state[ts];
     match[k] = -1;
   }
   // -- detections (deepsort_tracker.py:180-198, detection.py:15-47)
@@ -405,12 +417,11 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
   if (tid == 0) {
     int nc = 0, nn = 0;
     for (int k = 0; k < nt; ++k) {
-      const long long ts = sb + order[k];
-      if (t.state[ts] == CONFIRMED) {
+      if (st_state[k] == CONFIRMED) {
         conf_list[nc++] = k;
-        const int lv = t.tsu[ts];
+        const int lv = st_tsu[k];
         if (lv >= 1 && lv <= t.max_age && lv < 256) s_levels[lv >> 5] |= 1u << (lv & 31);
-      } else if (t.state[ts] == TENTATIVE) {
+      } else if (st_state[k] == TENTATIVE) {
         tent_list[nn++] = k;
       }
     }
@@ -418,13 +429,13 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
   }
   __syncthreads();
 
-  float* cm = t.cost_ws + static_cast<long long>(s) * T * Dm;
+  float* cm = io.cm_in_smem ? reinterpret_cast<float*>(p) : t.cost_ws + static_cast<long long>(s) * T * Dm;
   // One matching problem: rows L[0..nL), columns U[0..nU); metric 0 = gated appearance, 1 = IoU.
   auto solve = [&](int metric, float thr, float clamp) {
     const int nL = s_nL, nU = s_nU;
     for (int idx = tid; idx < nL * nU; idx += ASSOC_THREADS) {
       const int i = idx / nU, j = idx - i * nU;
-      const long long ts = sb + order[L[i]];
+      const long long ts = sb + ord[L[i]];
       const int d = U[j];
       float c;
       if (metric == 0) {
@@ -466,7 +477,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
     if (tid == 0) {
       int n = 0;
       for (int k = 0; k < s_nconf; ++k)
-        if (t.tsu[sb + order[conf_list[k]]] == level) L[n++] = conf_list[k];
+        if (st_tsu[conf_list[k]] == level) L[n++] = conf_list[k];
       s_nL = n;
     }
     __syncthreads();
@@ -479,7 +490,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
     for (int k = 0; k < s_ntent; ++k) L[n++] = tent_list[k];
     for (int k = 0; k < s_nconf; ++k) {
       const int pos = conf_list[k];
-      if (match[pos] < 0 && t.tsu[sb + order[pos]] == 1) L[n++] = pos;
+      if (match[pos] < 0 && st_tsu[pos] == 1) L[n++] = pos;
     }
     s_nL = n;
   }
@@ -488,7 +499,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
 
   // -- update matched tracks / mark missed (tracker_core.py:62-68, track.py:82-119)
   for (int k = warp; k < nt; k += ASSOC_THREADS / 32) {
-    const long long ts = sb + order[k];
+    const long long ts = sb + ord[k];
     const int d = match[k];
     if (d >= 0) {
       const int row = io.crop_slot[static_cast<long long>(s) * io.stride_k + d];
@@ -513,13 +524,16 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
         const int hits = t.hits[ts] + 1;
         t.hits[ts] = hits;
         t.tsu[ts] = 0;
+        st_tsu[k] = 0;
         t.conf[ts] = io.scores[o];
         t.cls[ts] = io.labels[o];
-        if (t.state[ts] == TENTATIVE && hits >= t.n_init) t.state[ts] = CONFIRMED;
+        if (st_state[k] == TENTATIVE && hits >= t.n_init) { t.state[ts] = CONFIRMED; st_state[k] = CONFIRMED; }
       }
     } else if (lane == 0) {
-      if (t.state[ts] == TENTATIVE) t.state[ts] = DELETED;
-      else if (t.state[ts] == CONFIRMED && t.tsu[ts] > t.max_age) t.state[ts] = DELETED;
+      if (st_state[k] == TENTATIVE || (st_state[k] == CONFIRMED && st_tsu[k] > t.max_age)) {
+        t.state[ts] = DELETED;
+        st_state[k] = DELETED;
+      }
     }
   }
   __syncthreads();
@@ -529,22 +543,30 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
     int n = 0;
     int nfree = t.n_free[s];
     for (int k = 0; k < nt; ++k) {
-      const int slot = order[k];
-      if (t.state[sb + slot] == DELETED) t.free_slots[sb + nfree++] = slot; else order[n++] = slot;
+      const int slot = ord[k];
+      if (st_state[k] == DELETED) {
+        t.free_slots[sb + nfree++] = slot;
+      } else {  // compaction in place (n <= k)
+        if (n != k) { order[n] = slot; ord[n] = slot; st_state[n] = st_state[k]; st_tsu[n] = st_tsu[k]; }
+        ++n;
+      }
     }
     const int nU = s_nU;
     int created = 0;
+    int next_id = t.next_id[s];
     for (int j = 0; j < nU; ++j) {
       if (nfree == 0) { atomicOr(&t.overflow[s], 1); break; }
       const int slot = t.free_slots[sb + --nfree];
-      order[n++] = slot;
+      order[n] = slot; ord[n] = slot; st_state[n] = TENTATIVE; st_tsu[n] = 0;
+      ++n;
       Utmp[created++] = slot;
       const long long ts = sb + slot;
-      t.track_id[ts] = t.next_id[s]++;
+      t.track_id[ts] = next_id++;
       t.state[ts] = TENTATIVE;
       t.hits[ts] = 1; t.age[ts] = 1; t.tsu[ts] = 0;
       t.gal_count[ts] = 0; t.gal_head[ts] = 0;
     }
+    t.next_id[s] = next_id;
     t.n_free[s] = nfree;
     t.n_tracks[s] = n;
     s_nt = n;
@@ -573,26 +595,28 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
   }
   __syncthreads();
   // -- output (deepsort_tracker.py:125-141): confirmed and updated this frame, track-list order
-  if (tid == 0) {
+  if (tid == 0) {  // which positions are reported (shared memory only) ...
     int n = 0;
     const int ntn = s_nt;
-    for (int k = 0; k < ntn; ++k) {
-      const long long ts = sb + order[k];
-      if (t.state[ts] != CONFIRMED || t.tsu[ts] != 0) continue;
-      float tl[4];
-      mean_to_tlwh(t.mean + ts * 8, tl);
-      const float w = tl[2] > 0.0f ? tl[2] : 0.0f, h = tl[3] > 0.0f ? tl[3] : 0.0f;
-      int* o = io.out_tracks + (sb + n) * 6;
-      o[0] = __float2int_rn(tl[0]);
-      o[1] = __float2int_rn(tl[1]);
-      o[2] = __float2int_rn(tl[0] + w);
-      o[3] = __float2int_rn(tl[1] + h);
-      o[4] = t.track_id[ts];
-      o[5] = t.cls[ts];
-      io.out_conf[sb + n] = t.conf[ts];
-      ++n;
-    }
+    for (int k = 0; k < ntn; ++k)
+      if (st_state[k] == CONFIRMED && st_tsu[k] == 0) L[n++] = k;
+    s_nL = n;
     io.out_count[s] = n;
+  }
+  __syncthreads();
+  for (int n = tid; n < s_nL; n += ASSOC_THREADS) {  // ... and their rows, one thread each
+    const long long ts = sb + ord[L[n]];
+    float tl[4];
+    mean_to_tlwh(t.mean + ts * 8, tl);
+    const float w = tl[2] > 0.0f ? tl[2] : 0.0f, h = tl[3] > 0.0f ? tl[3] : 0.0f;
+    int* o = io.out_tracks + (sb + n) * 6;
+    o[0] = __float2int_rn(tl[0]);
+    o[1] = __float2int_rn(tl[1]);
+    o[2] = __float2int_rn(tl[0] + w);
+    o[3] = __float2int_rn(tl[1] + h);
+    o[4] = t.track_id[ts];
+    o[5] = t.cls[ts];
+    io.out_conf[sb + n] = t.conf[ts];
   }
 }
 
@@ -624,8 +648,13 @@ __global__ void gating_kernel(const float* state, const float* meas, int n, int 
                       meas + static_cast<long long>(idx) * 4, m);
 }
 
-size_t assoc_smem(int T, int D) {
-  return sizeof(float) * 8 * D + sizeof(int) * (3 * D + 5 * T) + 16 + lsap_bytes(std::max(T, D));
+constexpr size_t CM_SMEM_LIMIT = 96 * 1024;  // cost matrices up to this size live in shared memory
+size_t assoc_smem(int T, int D, int* cm_in_smem = nullptr) {
+  const size_t base = sizeof(float) * 8 * D + sizeof(int) * (3 * D + 8 * T) + 16 + lsap_bytes(std::max(T, D));
+  const size_t cm = sizeof(float) * T * D;
+  const bool fits = cm <= CM_SMEM_LIMIT;
+  if (cm_in_smem) *cm_in_smem = fits ? 1 : 0;
+  return base + (fits ? cm : 0);
 }
 
 }  // namespace
@@ -730,8 +759,9 @@ int aicam_tracker_step(aicam_tracker* t, const float* boxes, const float* scores
     count_launch();
     if (int rc = last_launch("appearance_kernel")) return rc;
   }
-  StepIO io{boxes, scores, labels, stride_k, det_index, det_count, crop_slot, out_tracks, out_conf, out_count};
-  assoc_kernel<<<d.S, ASSOC_THREADS, assoc_smem(d.T, d.D), st>>>(d, io);
+  StepIO io{boxes, scores, labels, stride_k, det_index, det_count, crop_slot, out_tracks, out_conf, out_count, 0};
+  const size_t asm_bytes = assoc_smem(d.T, d.D, &io.cm_in_smem);
+  assoc_kernel<<<d.S, ASSOC_THREADS, asm_bytes, st>>>(d, io);
   count_launch();
   return last_launch("assoc_kernel");
 }

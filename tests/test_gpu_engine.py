@@ -19,6 +19,8 @@ def blobs(tmp_path_factory):
     d = tmp_path_factory.mktemp("blobs")
     paths = {}
     for name, gen in (("yolov8n", lambda: W.synth_yolov8_weights("n", seed=0)),
+                      ("yolov8s", lambda: W.synth_yolov8_weights("s", seed=0)),
+                      ("yolov8m", lambda: W.synth_yolov8_weights("m", seed=0)),
                       ("reid", lambda: W.synth_reid_weights(seed=1))):
         kind, params, tensors = gen()
         paths[name] = str(d / (name + ".aicw"))
@@ -64,6 +66,38 @@ def test_yolov8n_head_matches_oracle(blobs):
         size = np.maximum(wb[top, 2] - wb[top, 0], wb[top, 3] - wb[top, 1])[:, None]
         assert (np.abs(gb[top] - wb[top]) / size).max() < 1e-2
         assert np.abs(gs[top] - ws[top]).max() < 2e-2
+
+
+@pytest.mark.parametrize("scale,gflop", [("s", 28.6), ("m", 78.9)])
+def test_yolov8_s_m_head_matches_oracle(blobs, scale, gflop):
+    """BASELINE.json configs[3]: the larger YOLOv8 scales run on the same kernels (detection only)."""
+    import gpu_util as G
+    from oracle import detect_post, image_ops, nets
+    rng = np.random.default_rng(3)
+    frames = synth_image(rng, 540, 960)[None]
+    x = G.preprocess(torch.from_numpy(frames).to(G.DEV), 1)
+    path = blobs["yolov8" + scale]
+    e = _engine(path, 1)
+    try:
+        assert abs(G.lib().aicam_engine_flops_per_item(e) / 1e9 - gflop) < 0.02 * gflop
+        head = torch.empty((1, 8400, 144), dtype=torch.float32, device=G.DEV)
+        G.check(G.lib().aicam_yolo_forward(e, G.ptr(x), 1, G.ptr(head), None))
+        G.sync()
+    finally:
+        G.lib().aicam_engine_destroy(e)
+    net = nets.load_net(path)
+    xin = image_ops.preprocess_yolo_input(frames[0])[0]
+    want = net.head_flat(torch.from_numpy(xin)).numpy()
+    got = head.cpu().numpy()
+    err = np.abs(got - want)
+    print("yolov8%s head: max abs err %.4f (logit range %.2f), mean abs err %.5f" % (scale, err.max(), np.abs(want).max(), err.mean()))
+    assert err.mean() < 0.03 and err.max() < 0.5
+    gb, gs, gl = detect_post.decode(got[0])
+    wb, ws, wl = detect_post.decode(want[0])
+    top = np.argsort(-ws)[:200]
+    size = np.maximum(wb[top, 2] - wb[top, 0], wb[top, 3] - wb[top, 1])[:, None]
+    assert (np.abs(gb[top] - wb[top]) / size).max() < 1e-2
+    assert np.abs(gs[top] - ws[top]).max() < 3e-2
 
 
 def test_reid_embeddings_match_oracle(blobs):
