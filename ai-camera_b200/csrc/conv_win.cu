@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "conv_tc.cuh"
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
   if (MODE == 0) m_tiles = static_cast<long long>(batch) * a.tiles_per_img;
   else m_tiles = (static_cast<long long>(batch) * a.hw + TM - 1) / TM;
   const int total_tiles = static_cast<int>(m_tiles) * a.n_tiles;
+  pdl_trigger();  // the next layer's CTAs may take over each SM as soon as the CTA here exits
   if (static_cast<int>(blockIdx.x) >= total_tiles) return;
 
   if (threadIdx.x == 0) {
@@ -498,6 +500,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
 
     if (part == 0) publish_rows(blockIdx.x, 0);
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+    pdl_wait();  // residual reads and output stores: only after the previous layer has completed
     if (res_staged) prefetch_res(cc, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -641,6 +644,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
   } else if (warp == 4 * NWG + 1) {
     // ================================================================== patch (A) producer
     if (lane == 0) {
+      pdl_wait();  // the patches are the previous layer's output
       const uint32_t a_ring = sbase + OFF_RING_A;
       uint32_t sa = 0, pa = 1;
       const uint32_t n_sa = a.sa;
@@ -744,8 +748,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
     // ================================================================== epilogue I/O warp (TMA flavour only)
     // Residual boxes are fetched up to `nres` tiles ahead of the epilogue; finished tiles are stored with one
     // tensor store per channel piece.  The epilogue warps never wait for either instruction to issue.
-    const long long total_pix_io = static_cast<long long>(batch) * a.hw;
-    (void)total_pix_io;
+    pdl_wait();  // residual loads / output stores: only after the previous layer has completed
     auto coords = [&](int tile, int& n0, int& cx, int& cy, int& cn) {
       const int mt_idx = a.n_tiles == 1 ? tile : tile / a.n_tiles;
       n0 = (tile - mt_idx * a.n_tiles) * a.n_tile;
@@ -1308,7 +1311,20 @@ plan:
   dim3 grid(static_cast<unsigned>(std::min<long long>(total_tiles, num_sms)));
   size_t slot = 0;
   const bool prof = profile_begin(stream, &slot);
-  kernel<<<grid, WIN_THREADS, smem, stream>>>(a, maps);
+  {
+    // programmatic dependent launch: this layer's prologue (barriers, TMEM, bias, resident weights / first weight
+    // stages) overlaps the previous layer's tail; its activation traffic starts after griddepcontrol.wait
+    static const bool no_pdl = getenv("AICAM_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(WIN_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, a, maps);
+    if (le != cudaSuccess) return fail(AICAM_ERR_CUDA, std::string("conv_win: launch failed: ") + cudaGetErrorString(le));
+  }
   if (prof) profile_end(stream, slot);
   count_launch();
   const int rc = last_launch("conv_win_kernel");

@@ -95,6 +95,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t s
                    "l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// (prologue, constant loads) while its predecessor in the stream drains; pdl_wait() blocks until the predecessor grid
+// has completed and its memory is visible.  pdl_trigger() lets the successor's CTAs be scheduled as soon as every CTA
+// of this grid has called it (they still only fit on an SM once a CTA here has exited).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores have finished READING shared memory (the source may be overwritten)
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
