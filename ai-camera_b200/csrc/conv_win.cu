@@ -1018,7 +1018,10 @@ plan:
   // measured: the TMA epilogue pays off where the epilogue bounds the tile (window modes, small K); deep
   // im2col / flat layers are L2-bound and need the shared memory for deeper operand rings instead
   static const bool epi_everywhere = getenv("AICAM_WIN_TMA_EPI_ALL") != nullptr;
-  if (!window && !(epi_everywhere && flat_io)) epi = false;
+  // (1x1 layers with few input channels are all epilogue: measured 70 -> 50 us on 32 -> 32 @160x160)
+  static const int epi_flat_cin = getenv("AICAM_WIN_EPI_FLAT_CIN") ? atoi(getenv("AICAM_WIN_EPI_FLAT_CIN")) : 128;
+  const bool epi_flat = mode == 1 && flat_io && resident && pc.cin_pad <= epi_flat_cin;
+  if (!window && !(epi_everywhere && flat_io) && !epi_flat) epi = false;
   if (mode == 4) epi = epi4 && piece_ch[0] != 0;  // flat TMA epilogue: border positions are stored as zeros
   else if (opd) epi = false;                        // (un-padded raster -> padded image: row-by-row offsets, generic epilogue)
   for (int mt = 1; mt <= 2; ++mt) {

@@ -279,10 +279,16 @@ def main():
 
     e2e_run(3)
     sync_all()
-    t0 = time.perf_counter()
+    # timed on the device: the start event precedes the first copy's stream (the copy stream waits on it), the end
+    # event follows the last device-to-host copy on the compute stream
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    copy_stream.wait_event(ee0)
     e2e_run(e2e_steps)
+    ee1.record()
+    torch.cuda.synchronize(dev)
+    e2e_s = ee0.elapsed_time(ee1) * 1e-3
     sync_all()
-    e2e_s = time.perf_counter() - t0
     h2d = S * FRAME_HW[0] * FRAME_HW[1] * 3
     d2h = sum(t.numel() * t.element_size() for t in host_out)
 
@@ -302,13 +308,16 @@ def main():
     # DRAM bytes of the same kernels for one step, from the committed ncu pass (profiles/r1_step_traffic.json)
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_step_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_step_traffic_v4.json")) as f:
             traffic = json.load(f)
     except Exception:
         pass
     conv_ms_step = ms.value / prof_steps
     peaks = measured_peaks()
     achieved_tflops = flops_step / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step > 0 else 0.0
+    launches_step = max(1, nl.value // prof_steps)
+    # per launch, like `achieved`: DRAM bytes of the convolution launches of one step / their number
+    traffic_per_launch = (traffic["dram_bytes"] / traffic["launches"]) if traffic else None
 
     # ---- gather (the only collective: final stats) -------------------------------------------
     allst = np.asarray(sharding.gather_stats([total_ms, e2e_s, crops_per_step, float(tracks_out), float(overflow)], dev))
@@ -341,7 +350,10 @@ def main():
         "roofline": {"kernel": "tcgen05 convolution kernels: conv_win_kernel + reid_stem_pool_kernel + conv_tc_kernel "
                                "(all %d launches of a step)" % (nl.value // prof_steps),
                      "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16"], "unit": "TFLOP/s",
-                     "frac": achieved_tflops / peaks["bf16"], "traffic": traffic, "peak_source": peaks["source"],
+                     "frac": achieved_tflops / peaks["bf16"], "traffic": traffic_per_launch, "traffic_unit": "bytes/launch",
+                     "traffic_detail": traffic, "peak_source": peaks["source"],
+                     "launches_per_step": int(launches_step), "avg_launch_us": 1e3 * conv_ms_step / launches_step,
+                     "flops_per_launch": flops_step / launches_step,
                      "kernel_ms_per_step": conv_ms_step, "flops_per_step": flops_step,
                      "crops_per_profiled_step": prof_crops, "profiled_steps": prof_steps},
     }

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Turn ncu outputs brought back in gpurun_out/ into the small text summaries kept under profiles/.
   python scripts/summarize_ncu.py launches gpurun_out/launches.csv  > profiles/<name>.txt
-  python scripts/summarize_ncu.py report   gpurun_out/prof.ncu-rep  > profiles/<name>.txt"""
+  python scripts/summarize_ncu.py report   gpurun_out/prof.ncu-rep  > profiles/<name>.txt
+  python scripts/summarize_ncu.py traffic  gpurun_out/launches_dram.csv profiles/<name>.json > profiles/<name>.txt
+      (csv from: ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,
+       sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none --csv python scripts/profile_step.py)"""
 import collections
 import csv
 import re
@@ -40,6 +43,53 @@ def launches(path):
         print("%3d %-28s grid %-16s %9.1f us" % (i, k[:28], g, v))
 
 
+def traffic(path, json_out=None, crops=None):
+    """Launch list with DRAM bytes and tensor-pipe activity per launch + the per-step totals of the tcgen05
+    convolution kernels (what bench.py reports as roofline.traffic)."""
+    import json
+    lines = [l for l in open(path) if not l.startswith("==")]
+    by_id = collections.OrderedDict()
+    for r in csv.DictReader(lines):
+        k = r["ID"]
+        e = by_id.setdefault(k, {"name": re.search(r"(\w+_kernel)", r["Kernel Name"]).group(1) if re.search(r"(\w+_kernel)", r["Kernel Name"]) else r["Kernel Name"][:30],
+                                 "full": r["Kernel Name"], "grid": r["Grid Size"]})
+        v = float(r["Metric Value"].replace(",", ""))
+        u = r["Metric Unit"]
+        m = r["Metric Name"]
+        if m == "gpu__time_duration.sum":
+            e["us"] = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
+        elif m.startswith("dram__bytes"):
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            e["rd" if "read" in m else "wr"] = v * mult
+        elif m.startswith("sm__pipe_tensor"):
+            e["tensor"] = v
+    rows = list(by_id.values())
+    tot = sum(r.get("us", 0) for r in rows)
+    print("ncu launch list of ONE step (scripts/profile_step.py); serialised launches: compare shares")
+    print("metrics: gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum, sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active\n")
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+    for r in rows:
+        a = agg[r["name"][:34]]
+        a[0] += 1; a[1] += r.get("us", 0); a[2] += r.get("rd", 0); a[3] += r.get("wr", 0)
+    print("%-36s %3s %10s %6s %12s %12s" % ("kernel", "n", "time_us", "share", "dram_rd_MB", "dram_wr_MB"))
+    for k, (n, us, rd, wr) in sorted(agg.items(), key=lambda x: -x[1][1]):
+        print("%-36s %3d %10.1f %5.1f%% %12.1f %12.1f" % (k, n, us, 100 * us / tot, rd / 1e6, wr / 1e6))
+    print("total %.1f us\n\nper launch, in order:" % tot)
+    for i, r in enumerate(rows):
+        tp = re.search(r"<([^>]*)>", r["full"].replace("(int)", ""))
+        print("%3d %-24s %-18s grid %-14s %8.1f us  rd %8.1f MB  wr %8.1f MB  tensor %5.1f%%" % (
+            i, r["name"][:24], ("<" + tp.group(1).replace("unnamed", "").strip() + ">") if tp and "conv_win" in r["name"] else "", r["grid"], r.get("us", 0),
+            r.get("rd", 0) / 1e6, r.get("wr", 0) / 1e6, r.get("tensor", 0)))
+    conv = [r for r in rows if "conv_win" in r["name"] or "stem_pool" in r["name"] or "conv_tc" in r["name"]]
+    out = {"dram_read_bytes": sum(r.get("rd", 0) for r in conv), "dram_write_bytes": sum(r.get("wr", 0) for r in conv),
+           "launches": len(conv), "kernel_time_us": sum(r.get("us", 0) for r in conv), "crops_in_step": crops,
+           "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over scripts/profile_step.py (64 streams), summed over "
+                     "the tcgen05 convolution launches of one step"}
+    out["dram_bytes"] = out["dram_read_bytes"] + out["dram_write_bytes"]
+    if json_out:
+        json.dump(out, open(json_out, "w"))
+
+
 def report(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -66,4 +116,7 @@ def report(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None, int(sys.argv[4]) if len(sys.argv) > 4 else None)
+    else:
+        {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
