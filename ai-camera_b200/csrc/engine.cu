@@ -43,7 +43,7 @@ struct View {
 };
 
 struct Op {
-  enum Type { CONV, MAXPOOL, UPSAMPLE, AVGL2, STEMPOOL } type;
+  enum Type { CONV, MAXPOOL, UPSAMPLE, AVGL2, STEMPOOL, SPPF3 } type;
   int conv = -1;
   View in, out, res;
   int h = 0, w = 0, c = 0;  // input spatial size / channels moved (pool, upsample)
@@ -230,9 +230,10 @@ struct Builder {
     // SPPF
     const int hc = c5 / 2;
     conv("model.9.cv1.conv", V(a8), h32, h32, V(cats, 0), c5, hc, 1, 1, 1);
-    pool(V(cats, 0), V(cats, hc), h32, h32, hc, 5, 1);
-    pool(V(cats, hc), V(cats, 2 * hc), h32, h32, hc, 5, 1);
-    pool(V(cats, 2 * hc), V(cats, 3 * hc), h32, h32, hc, 5, 1);
+    {  // three chained 5x5 pools: one fused launch when eligible (layers.cu), else three max-pool launches
+      Op op; op.type = Op::SPPF3; op.in = V(cats, 0); op.out = V(cats, hc); op.h = h32; op.w = h32; op.c = hc; op.k = 5; op.stride = 1;
+      e->ops.push_back(op);
+    }
     conv("model.9.cv2.conv", V(cats, 0), h32, h32, V(cat20, c4), 4 * hc, c5, 1, 1, 1);
     // FPN top-down
     upsample(V(cat20, c4), V(cat11, 0), h32, h32, c5);
@@ -389,6 +390,16 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
         rc = launch_maxpool(ip, is, ic, op.in.coff, batch, op.h, op.w, op.c, op.k, op.stride,
                             const_cast<__nv_bfloat16*>(op_), os, oc, op.out.coff, stream, n_dev);
         break;
+      case Op::SPPF3: {
+        static const bool unfused = getenv("AICAM_NO_SPPF_FUSION") != nullptr;
+        rc = unfused ? 0 : try_launch_sppf_pool3(const_cast<__nv_bfloat16*>(ip), is, ic, op.in.coff, batch, op.h, op.w, op.c, stream, n_dev);
+        if (rc == 1) { rc = AICAM_OK; break; }
+        if (rc < 0) break;
+        for (int r = 0; r < 3 && !rc; ++r)
+          rc = launch_maxpool(ip, is, ic, op.in.coff + r * op.c, batch, op.h, op.w, op.c, op.k, op.stride, const_cast<__nv_bfloat16*>(ip), is, ic,
+                              op.in.coff + (r + 1) * op.c, stream, n_dev);
+        break;
+      }
       case Op::UPSAMPLE:
         geom(op.out, 0, &op_, &os, &oc);
         rc = launch_upsample2x(ip, is, ic, op.in.coff, batch, op.h, op.w, op.c, const_cast<__nv_bfloat16*>(op_), os,
@@ -510,7 +521,7 @@ double aicam_engine_flops_per_item(const aicam_engine* e) { return e ? 2.0 * e->
 int aicam_engine_num_launches(const aicam_engine* e) {
   if (!e) return 0;
   int n = 0;
-  for (const auto& op : e->ops) n += op.type == aicam::Op::STEMPOOL ? 2 : 1;  // NHWC8 repack + fused stem
+  for (const auto& op : e->ops) n += op.type == aicam::Op::STEMPOOL ? 2 : 1;  // NHWC8 repack + fused stem (upper bound)
   return n;
 }
 

@@ -50,6 +50,48 @@ __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ in, long long i
                             out_coff + g * 8) = m;
 }
 
+// SPPF: three chained 5x5 stride-1 max-pools (= windows 5, 9, 13 of the input) in ONE launch.  A block owns one image
+// x 32 channels (64-byte runs per pixel): the map lives in shared memory, each pool is a separable row / column max,
+// every pooled map is written to its channel slice of the concat buffer and feeds the next pool from shared memory.
+__global__ void __launch_bounds__(256) sppf_pool3_kernel(__nv_bfloat16* __restrict__ buf, long long img_stride, int cstride,
+                                                         int coff, int h, int w, int hc, const int* __restrict__ n_dev) {
+  extern __shared__ __align__(16) uint4 sp[];  // three [h * w][4] tiles
+  const int blocks_per_img = hc >> 5;
+  const int n = blockIdx.x / blocks_per_img, cb = blockIdx.x - n * blocks_per_img;
+  if (n_dev && n >= __ldg(n_dev)) return;
+  const int hw = h * w, items = hw * 4;
+  uint4* A = sp;
+  uint4* T = sp + items;
+  uint4* B = sp + 2 * items;
+  __nv_bfloat16* base = buf + n * img_stride + coff + cb * 32;
+  for (int i = threadIdx.x; i < items; i += blockDim.x)
+    A[i] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(i >> 2) * cstride + (i & 3) * 8);
+  __syncthreads();
+  auto mx = [](uint4 a, uint4 b) {
+    return make_uint4(bf16x2_max(a.x, b.x), bf16x2_max(a.y, b.y), bf16x2_max(a.z, b.z), bf16x2_max(a.w, b.w));
+  };
+  for (int r = 1; r <= 3; ++r) {
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {  // row max over x - 2 .. x + 2
+      const int px = i >> 2, g = i & 3, y = px / w, x = px - y * w;
+      uint4 m = A[i];
+      for (int dx = -2; dx <= 2; ++dx)
+        if (dx != 0 && x + dx >= 0 && x + dx < w) m = mx(m, A[((px + dx) << 2) + g]);
+      T[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {  // column max over y - 2 .. y + 2
+      const int px = i >> 2, g = i & 3, y = px / w;
+      uint4 m = T[i];
+      for (int dy = -2; dy <= 2; ++dy)
+        if (dy != 0 && y + dy >= 0 && y + dy < h) m = mx(m, T[((px + dy * w) << 2) + g]);
+      B[i] = m;
+      *reinterpret_cast<uint4*>(base + static_cast<long long>(r) * hc + static_cast<long long>(px) * cstride + g * 8) = m;
+    }
+    __syncthreads();
+    uint4* t2 = A; A = B; B = t2;
+  }
+}
+
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, long long in_img_stride, int in_cstride,
                                   int in_coff, int h, int w, int c8, __nv_bfloat16* __restrict__ out,
                                   long long out_img_stride, int out_cstride, int out_coff, long long total) {
@@ -66,21 +108,37 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, long lon
                             out_coff + g * 8) = v;
 }
 
-// One block per image: mean over hw pixels of each of c channels, then x / ||x||_2 (fp32).
-__global__ void avgpool_l2norm_kernel(const __nv_bfloat16* __restrict__ in, int hw, int hw_div, int c, float* __restrict__ out,
-                                      const int* __restrict__ n_dev) {
-  extern __shared__ float red[];
+// One block per image: mean over hw pixels of each of c channels, then x / ||x||_2 (fp32).  Thread t owns the
+// 8-channel group t % (c / 8) (16-byte loads) and every (256 / (c / 8))-th pixel; partial sums meet in shared memory.
+__global__ void __launch_bounds__(256) avgpool_l2norm_kernel(const __nv_bfloat16* __restrict__ in, int hw, int hw_div, int c,
+                                                             float* __restrict__ out, const int* __restrict__ n_dev) {
+  extern __shared__ float red[];  // [256][8] partial sums, then the block reduction of the squared norm
   const int n = blockIdx.x;
   if (n_dev && n >= __ldg(n_dev)) return;
-  const __nv_bfloat16* base = in + static_cast<long long>(n) * hw * c;
+  const int groups = c >> 3;                   // 8-channel groups (<= 256)
+  const int lanes = blockDim.x / groups;       // pixel phases per group
+  const int g = threadIdx.x % groups, ph = threadIdx.x / groups;
+  const __nv_bfloat16* base = in + static_cast<long long>(n) * hw * c + g * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ph < lanes)
+    for (int p = ph; p < hw; p += lanes) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p) * c));
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[2 * i] += bf16_lo(wv[i]); acc[2 * i + 1] += bf16_hi(wv[i]); }
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+  __syncthreads();
   float ss = 0.0f;
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {  // phases summed in a fixed order: deterministic
     float s = 0.0f;
-    for (int p = 0; p < hw; ++p) s += __bfloat162float(base[static_cast<long long>(p) * c + ch]);
+    for (int q = 0; q < lanes; ++q) s += red[(q * groups + (ch >> 3)) * 8 + (ch & 7)];
     s /= static_cast<float>(hw_div);
     out[static_cast<long long>(n) * c + ch] = s;
     ss += s * s;
   }
+  __syncthreads();
   red[threadIdx.x] = ss;
   __syncthreads();
   for (int o = blockDim.x / 2; o > 0; o >>= 1) {
@@ -150,6 +208,23 @@ int launch_maxpool(const __nv_bfloat16* in, long long in_img_stride, int in_cstr
   return last_launch("maxpool_kernel");
 }
 
+// pools 5 / 9 / 13 of channels [coff, coff + hc) of `buf` into [coff + hc, coff + 4 hc); returns 1 when launched,
+// 0 when the shape is not eligible (the caller chains three max-pools instead)
+int try_launch_sppf_pool3(__nv_bfloat16* buf, long long img_stride, int cstride, int coff, int batch, int h, int w, int hc,
+                          cudaStream_t stream, const int* n_dev) {
+  const size_t smem = static_cast<size_t>(3) * h * w * 64;
+  if (hc % 32 || cstride % 8 || coff % 8 || smem > 200 * 1024 || batch <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(sppf_pool3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 0;
+    configured = true;
+  }
+  sppf_pool3_kernel<<<static_cast<unsigned>(batch * (hc / 32)), 256, smem, stream>>>(buf, img_stride, cstride, coff, h, w, hc, n_dev);
+  count_launch();
+  const int rc = last_launch("sppf_pool3_kernel");
+  return rc ? rc : 1;
+}
+
 int launch_upsample2x(const __nv_bfloat16* in, long long in_img_stride, int in_cstride, int in_coff, int batch, int h,
                       int w, int c, __nv_bfloat16* out, long long out_img_stride, int out_cstride, int out_coff,
                       cudaStream_t stream) {
@@ -166,7 +241,10 @@ int launch_upsample2x(const __nv_bfloat16* in, long long in_img_stride, int in_c
 int launch_avgpool_l2norm(const __nv_bfloat16* in, int batch, int hw, int hw_div, int c, float* out, cudaStream_t stream,
                           const int* n_dev) {
   if (batch == 0) return AICAM_OK;
-  avgpool_l2norm_kernel<<<batch, 256, 256 * sizeof(float), stream>>>(in, hw, hw_div, c, out, n_dev);
+  if (c % 8 || c > 2048 || 256 % (c / 8 > 256 ? 256 : c / 8))
+    return fail(AICAM_ERR_INVALID_ARG, "avgpool_l2norm: channels must be 8 x a divisor of 256");
+  if (c / 8 > 256) return fail(AICAM_ERR_INVALID_ARG, "avgpool_l2norm: at most 2048 channels");
+  avgpool_l2norm_kernel<<<batch, 256, 256 * 8 * sizeof(float), stream>>>(in, hw, hw_div, c, out, n_dev);
   count_launch();
   return last_launch("avgpool_l2norm_kernel");
 }

@@ -6,6 +6,8 @@ namespace aicam {
 int launch_maxpool(const __nv_bfloat16* in, long long in_img_stride, int in_cstride, int in_coff, int batch, int h,
                    int w, int c, int k, int stride, __nv_bfloat16* out, long long out_img_stride, int out_cstride,
                    int out_coff, cudaStream_t stream, const int* n_dev = nullptr);
+int try_launch_sppf_pool3(__nv_bfloat16* buf, long long img_stride, int cstride, int coff, int batch, int h, int w, int hc,
+                          cudaStream_t stream, const int* n_dev = nullptr);
 int launch_upsample2x(const __nv_bfloat16* in, long long in_img_stride, int in_cstride, int in_coff, int batch, int h,
                       int w, int c, __nv_bfloat16* out, long long out_img_stride, int out_cstride, int out_coff,
                       cudaStream_t stream);

@@ -194,6 +194,9 @@ def main():
     pipe.tracker.count_stats = True  # device-side totals of crops / reported tracks (two tiny torch adds per step)
     for _ in range(args.warmup):
         one_step()
+    counted0 = lib.aicam_launch_count()
+    one_step()
+    launches_counted = lib.aicam_launch_count() - counted0  # kernels of ONE step, counted by the library itself
     torch.cuda.synchronize(dev)
     # CUDA graphs: one graph per ring position (the frame pointer is baked into the graph)
     graphs = None
@@ -239,7 +242,7 @@ def main():
     per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
-    launches_eager = pipe.launches_per_step()
+    launches_eager = launches_counted
     gpu_launches = (lib.aicam_launch_count() - launches0) if graphs is None else launches_eager * args.steps
     crops_per_step = float(pipe.tracker.crop_total.item()) / args.steps      # mean over the timed steps
     tracks_out = float(pipe.tracker.track_total.item()) / args.steps
