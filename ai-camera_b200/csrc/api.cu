@@ -33,6 +33,7 @@ bool profile_begin(cudaStream_t st, size_t* slot) {
   cudaEventRecord(g_events[*slot].first, st);
   return true;
 }
+bool profile_enabled() { return g_profile; }
 void profile_end(cudaStream_t st, size_t slot) { cudaEventRecord(g_events[slot].second, st); }
 
 }  // namespace aicam

@@ -22,6 +22,8 @@
 
 namespace aicam {
 
+bool profile_enabled();
+
 namespace {
 
 struct BlobTensor {
@@ -51,6 +53,7 @@ struct Op {
   int act = 0, res_mode = 0, out_f32 = 0;
   int s2d_c0 = 0;   // conv reads its input space-to-depth (h, w are the space-to-depth sizes), c0 channels per pixel
   int out_s2d = 0;  // conv stores its output space-to-depth (for the next stride-2 layer)
+  int lane = 0;     // 0: the caller's stream; 1, 2: the engine's side streams (independent tail chains, joined at the end)
 };
 
 }  // namespace
@@ -74,6 +77,11 @@ struct aicam_engine {
   long long out_img_stride = 0;
   int num_anchors = 0;
   int feat_buf = -1;           // reid: buffer feeding the average pool
+  // The six chains of the Detect head (3 levels x {box, class}) are independent of each other: they run on the
+  // caller's stream and two side streams, forked after the neck and joined before run_ops returns, so that the
+  // small late layers fill each other's launch gaps and idle SMs (also inside a CUDA-graph capture).
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 };
 
 namespace aicam {
@@ -250,17 +258,28 @@ struct Builder {
     const int lvl_c[3] = {c3, c4, c5};
     const int lvl_h[3] = {h8, h16, h32};
     long long anchor_base = 0;
+    // opt-in: measured on B200 the persistent one-CTA-per-SM kernels of different chains only delay each other
+    // (5.68 ms per step on one stream, 5.74 with three)
+    static const bool no_lanes = getenv("AICAM_HEAD_STREAMS") == nullptr;
+    int chain = 0;
+    auto set_lane = [&](size_t first_op, int lane) {
+      for (size_t i = first_op; i < e->ops.size(); ++i) e->ops[i].lane = no_lanes ? 0 : lane;
+    };
     for (int l = 0; l < 3; ++l) {
       const int hh = lvl_h[l];
       const int b1 = buf(hh, hh, cb), b2 = buf(hh, hh, cb), k1 = buf(hh, hh, cc), k2 = buf(hh, hh, cc);
       const std::string p2 = "model.22.cv2." + std::to_string(l), p3 = "model.22.cv3." + std::to_string(l);
       const long long eoff = anchor_base * e->out_cstride;
+      size_t first = e->ops.size();
       conv(p2 + ".0.conv", V(lvl_in[l]), hh, hh, V(b1), lvl_c[l], cb, 3, 1, 1);
       conv(p2 + ".1.conv", V(b1), hh, hh, V(b2), cb, cb, 3, 1, 1);
       conv(p2 + ".2", V(b2), hh, hh, V(-2, 0, eoff), cb, AICAM_HEAD_DFL, 1, 1, 0, View(), 0, 1);
+      set_lane(first, chain++ % 3);
+      first = e->ops.size();
       conv(p3 + ".0.conv", V(lvl_in[l]), hh, hh, V(k1), lvl_c[l], cc, 3, 1, 1);
       conv(p3 + ".1.conv", V(k1), hh, hh, V(k2), cc, cc, 3, 1, 1);
       conv(p3 + ".2", V(k2), hh, hh, V(-2, AICAM_HEAD_DFL, eoff), cc, nc, 1, 1, 0, View(), 0, 1);
+      set_lane(first, chain++ % 3);
       anchor_base += static_cast<long long>(hh) * hh;
     }
   }
@@ -331,7 +350,29 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
   } else if (e->kind == AICAM_KIND_REID && input_is_s2d && e->stem_in8 < 0) {
     return fail(AICAM_ERR_UNSUPPORTED, "engine: this engine was built without the fused NHWC8 stem");
   }
+  cudaStream_t main_stream = stream;
+  bool forked = false, used[2] = {false, false};
+  auto join = [&]() -> int {
+    for (int i = 0; i < 2; ++i)
+      if (used[i]) {
+        AICAM_CUDA_OK(cudaEventRecord(e->ev_join[i], e->side[i]));
+        AICAM_CUDA_OK(cudaStreamWaitEvent(main_stream, e->ev_join[i], 0));
+      }
+    return AICAM_OK;
+  };
   for (const Op& op : e->ops) {
+    stream = main_stream;
+    if (op.lane > 0 && e->side[op.lane - 1] && !profile_enabled()) {  // (per-launch timing: one kernel at a time)
+      if (!forked) {
+        AICAM_CUDA_OK(cudaEventRecord(e->ev_fork, main_stream));
+        forked = true;
+      }
+      if (!used[op.lane - 1]) {
+        AICAM_CUDA_OK(cudaStreamWaitEvent(e->side[op.lane - 1], e->ev_fork, 0));
+        used[op.lane - 1] = true;
+      }
+      stream = e->side[op.lane - 1];
+    }
     auto geom = [&](const View& v, int fallback_c, const __nv_bfloat16** ptr, long long* img_stride, int* cstride) {
       if (v.buf >= 0) {
         const Buffer& b = e->buffers[v.buf];
@@ -425,9 +466,12 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
         break;
       }
     }
-    if (rc) return rc;
+    if (rc) {
+      join();  // never leave a side stream un-joined (an open graph capture would be invalidated)
+      return rc;
+    }
   }
-  return AICAM_OK;
+  return join();
 }
 
 }  // namespace
@@ -495,6 +539,15 @@ int aicam_engine_create(const char* blob_path, int device, int max_batch, aicam_
     aicam_engine_destroy(e);
     return b.err;
   }
+  bool lanes = false;
+  for (const auto& op : e->ops) lanes = lanes || op.lane > 0;
+  if (lanes) {
+    for (int i = 0; i < 2; ++i) {
+      AICAM_CUDA_OK(cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking));
+      AICAM_CUDA_OK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
+    }
+    AICAM_CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  }
   AICAM_CUDA_OK(cudaDeviceSynchronize());
   *out = e;
   return AICAM_OK;
@@ -507,6 +560,11 @@ void aicam_engine_destroy(aicam_engine* e) {
   free_stem_pool(&e->stem);
   for (auto& b : e->buffers)
     if (b.ptr) cudaFree(b.ptr);
+  for (int i = 0; i < 2; ++i) {
+    if (e->side[i]) cudaStreamDestroy(e->side[i]);
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   delete e;
 }
 

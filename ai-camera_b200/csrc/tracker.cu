@@ -288,7 +288,11 @@ __global__ void __launch_bounds__(128) normalize_kernel(Dev t, const int* __rest
 }
 
 // K8: cost[slot][d] = min over the gallery of max(0, 1 - <g, f_d>)  (matching.py:109-217)
-constexpr int APP_DT = 16;  // detections per shared-memory tile
+// detections per shared-memory tile: the gallery is re-read once per tile, so the tile covers the usual frame (<= 32
+// tracked detections) in one pass.  Crowded scenes (configs[4], D = 300) still make ten passes - measured 17 GB of DRAM
+// reads against 1 GB of gallery (scripts/crowded_bench.py); the fix is a real GEMM tiling (L2-resident gallery tile
+// against all detections), listed as next in DESIGN.md.
+constexpr int APP_DT = 32;
 __global__ void __launch_bounds__(256) appearance_kernel(Dev t, const int* __restrict__ det_count,
                                                          const int* __restrict__ crop_slot, int stride_k) {
   extern __shared__ float sm_f[];  // [APP_DT][F] detection tile, then [8][APP_DT] per-warp minima
