@@ -20,6 +20,8 @@
 //   gallery[S][T][G][F] f32 (L2-normalised at insert; ring buffer: head, count)
 //   order[S][T]: slots of the live tracks in creation order (the reference's track list)
 //   free_slots[S][T] stack, next_id[S]
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -288,14 +290,13 @@ __global__ void __launch_bounds__(128) normalize_kernel(Dev t, const int* __rest
 }
 
 // K8: cost[slot][d] = min over the gallery of max(0, 1 - <g, f_d>)  (matching.py:109-217)
-// detections per shared-memory tile: the gallery is re-read once per tile, so the tile covers the usual frame (<= 32
-// tracked detections) in one pass.  Crowded scenes (configs[4], D = 300) still make ten passes - measured 17 GB of DRAM
-// reads against 1 GB of gallery (scripts/crowded_bench.py); the fix is a real GEMM tiling (L2-resident gallery tile
-// against all detections), listed as next in DESIGN.md.
+// detections per shared-memory tile of the row kernel: the gallery is re-read once per tile, so the tile covers the
+// usual frame (<= 32 tracked detections) in one pass; busier frames take the SGEMM tiling below (crowded scenes,
+// configs[4]: the row kernel measured 17 GB of DRAM reads against 1 GB of gallery and was shared-memory-load bound).
 constexpr int APP_DT = 32;
-__global__ void __launch_bounds__(256) appearance_kernel(Dev t, const int* __restrict__ det_count,
-                                                         const int* __restrict__ crop_slot, int stride_k) {
-  extern __shared__ float sm_f[];  // [APP_DT][F] detection tile, then [8][APP_DT] per-warp minima
+__device__ __forceinline__ void appearance_rows(const Dev& t, const int* __restrict__ det_count,
+                                                const int* __restrict__ crop_slot, int stride_k, float* sm_f) {
+  // sm_f: [APP_DT][F] detection tile, then [8][APP_DT] per-warp minima
   const int s = blockIdx.y, ti = blockIdx.x;
   if (ti >= t.n_tracks[s]) return;
   const int slot = t.order[static_cast<long long>(s) * t.T + ti];
@@ -344,6 +345,100 @@ __global__ void __launch_bounds__(256) appearance_kernel(Dev t, const int* __res
       out[d0 + threadIdx.x] = (has && ng > 0) ? v : INFTY_COST;
     }
   }
+}
+
+// K8 as a register-tiled SGEMM (feature dims that are multiples of 32): a block owns one track; its gallery (<= 128
+// rows per pass) meets 64 detections at a time, K in chunks of 32 staged k-major in shared memory; every thread
+// accumulates 8 gallery rows x 4 detections (32 FMAs per 12 shared-memory loads).  The gallery is read from DRAM
+// once per track (the passes over further detection tiles hit L2) - the one-warp-per-row kernel above re-read it per
+// tile and was shared-memory-load bound in crowded scenes (profiles/r1_crowded_scene_tracker.txt).
+constexpr int AG_ROWS = 128, AG_DT = 64, AG_KC = 32;
+__device__ __forceinline__ void appearance_gemm(const Dev& t, const int* __restrict__ det_count,
+                                                const int* __restrict__ crop_slot, int stride_k, float* sm_f) {
+  float (*Gs)[AG_ROWS + 4] = reinterpret_cast<float (*)[AG_ROWS + 4]>(sm_f);
+  float (*Fs)[AG_DT + 4] = reinterpret_cast<float (*)[AG_DT + 4]>(sm_f + AG_KC * (AG_ROWS + 4));
+  float (*wmin)[AG_DT] = reinterpret_cast<float (*)[AG_DT]>(sm_f + AG_KC * (AG_ROWS + 4) + AG_KC * (AG_DT + 4));
+  const int s = blockIdx.y, ti = blockIdx.x;
+  if (ti >= t.n_tracks[s]) return;
+  const int slot = t.order[static_cast<long long>(s) * t.T + ti];
+  const long long ts = static_cast<long long>(s) * t.T + slot;
+  if (t.state[ts] != CONFIRMED) return;  // only confirmed tracks enter the appearance cascade
+  const int nd = min(det_count[s], t.D);
+  const int ng = t.gal_count[ts];
+  const int F = t.F;
+  const float* gal = t.gallery + ts * t.G * F;
+  const float* fn = t.featn + static_cast<long long>(s) * t.D * F;
+  const int* cs = crop_slot + static_cast<long long>(s) * stride_k;
+  float* out = t.app_cost + ts * t.D;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int d0 = 0; d0 < nd; d0 += AG_DT) {
+    const int dn = min(AG_DT, nd - d0);
+    float best[4] = {INFTY_COST, INFTY_COST, INFTY_COST, INFTY_COST};
+    for (int r0 = 0; r0 < ng; r0 += AG_ROWS) {
+      const int rn = min(AG_ROWS, ng - r0);
+      float acc[8][4];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = 0.0f;
+      for (int k0 = 0; k0 < F; k0 += AG_KC) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // gallery chunk: 128 rows x 8 float4
+          const int idx = tid + 256 * i, row = idx >> 3, kq = (idx & 7) * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < rn) v = __ldg(reinterpret_cast<const float4*>(gal + static_cast<long long>(r0 + row) * F + k0 + kq));
+          Gs[kq][row] = v.x; Gs[kq + 1][row] = v.y; Gs[kq + 2][row] = v.z; Gs[kq + 3][row] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {  // detection chunk: 64 detections x 8 float4 (no feature: zeros)
+          const int idx = tid + 256 * i, dd = idx >> 3, kq = (idx & 7) * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (dd < dn && cs[d0 + dd] >= 0) v = *reinterpret_cast<const float4*>(fn + static_cast<long long>(d0 + dd) * F + k0 + kq);
+          Fs[kq][dd] = v.x; Fs[kq + 1][dd] = v.y; Fs[kq + 2][dd] = v.z; Fs[kq + 3][dd] = v.w;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < AG_KC; ++k) {
+          float g[8], f[4];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) g[r] = Gs[k][ty + 16 * r];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) f[j] = Fs[k][tx + 16 * j];
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[r][j] = fmaf(g[r], f[j], acc[r][j]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (ty + 16 * r < rn) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) best[j] = fminf(best[j], fmaxf(1.0f - acc[r][j], 0.0f));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wmin[ty][tx + 16 * j] = best[j];
+    __syncthreads();
+    if (tid < dn) {
+      float v = INFTY_COST;
+#pragma unroll
+      for (int w = 0; w < 16; ++w) v = fminf(v, wmin[w][tid]);
+      out[d0 + tid] = (cs[d0 + tid] >= 0 && ng > 0) ? v : INFTY_COST;
+    }
+    __syncthreads();
+  }
+}
+
+constexpr size_t AG_SMEM = (AG_KC * (AG_ROWS + 4) + AG_KC * (AG_DT + 4) + 16 * AG_DT) * sizeof(float);
+// One launch, two tilings: frames with at most APP_DT detections take the one-pass row kernel (gallery streamed once,
+// no padding work), busier frames the SGEMM tiling.  The choice is per block from the device-side count.
+__global__ void __launch_bounds__(256) appearance_kernel(Dev t, const int* __restrict__ det_count,
+                                                         const int* __restrict__ crop_slot, int stride_k, int gemm_ok) {
+  extern __shared__ __align__(16) float sm_f[];
+  if (gemm_ok && min(det_count[blockIdx.y], t.D) > APP_DT) appearance_gemm(t, det_count, crop_slot, stride_k, sm_f);
+  else appearance_rows(t, det_count, crop_slot, stride_k, sm_f);
 }
 
 struct StepIO {
@@ -724,7 +819,7 @@ int aicam_tracker_create(const aicam_tracker_config* cfg, aicam_tracker** out) {
   if (sm > 200 * 1024) { aicam_tracker_destroy(t); return fail(AICAM_ERR_CAPACITY, "tracker_create: max_tracks/max_dets need too much shared memory"); }
   cudaFuncSetAttribute(assoc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
   cudaFuncSetAttribute(appearance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       static_cast<int>((APP_DT * d.F + 8 * APP_DT) * sizeof(float)));
+                       static_cast<int>(std::max((APP_DT * d.F + 8 * APP_DT) * sizeof(float), AG_SMEM)));
   if (int r2 = aicam_tracker_reset(t, nullptr)) { aicam_tracker_destroy(t); return r2; }
   AICAM_CUDA_OK(cudaDeviceSynchronize());
   *out = t;
@@ -758,8 +853,10 @@ int aicam_tracker_step(aicam_tracker* t, const float* boxes, const float* scores
     normalize_kernel<<<dim3(d.D, d.S), 128, 0, st>>>(d, det_count, crop_slot, stride_k, feats);
     count_launch();
     if (int rc = last_launch("normalize_kernel")) return rc;
-    const size_t sm = (APP_DT * d.F + 8 * APP_DT) * sizeof(float);
-    appearance_kernel<<<dim3(d.T, d.S), 256, sm, st>>>(d, det_count, crop_slot, stride_k);
+    static const bool no_gemm = getenv("AICAM_APPEARANCE_ROWS") != nullptr;
+    const int gemm_ok = (d.F % AG_KC == 0 && !no_gemm) ? 1 : 0;
+    const size_t sm = std::max((APP_DT * d.F + 8 * APP_DT) * sizeof(float), gemm_ok ? AG_SMEM : size_t(0));
+    appearance_kernel<<<dim3(d.T, d.S), 256, sm, st>>>(d, det_count, crop_slot, stride_k, gemm_ok);
     count_launch();
     if (int rc = last_launch("appearance_kernel")) return rc;
   }
