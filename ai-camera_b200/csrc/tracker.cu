@@ -290,10 +290,12 @@ __global__ void __launch_bounds__(128) normalize_kernel(Dev t, const int* __rest
 }
 
 // K8: cost[slot][d] = min over the gallery of max(0, 1 - <g, f_d>)  (matching.py:109-217)
-// detections per shared-memory tile of the row kernel: the gallery is re-read once per tile, so the tile covers the
-// usual frame (<= 32 tracked detections) in one pass; busier frames take the SGEMM tiling below (crowded scenes,
-// configs[4]: the row kernel measured 17 GB of DRAM reads against 1 GB of gallery and was shared-memory-load bound).
-constexpr int APP_DT = 32;
+// detections per shared-memory tile of the row kernel.  The gallery is re-read (from L2) once per tile; frames with
+// more than APP_GEMM_MIN detections take the SGEMM tiling below (crowded scenes, configs[4]: the row kernel measured
+// 17 GB of DRAM reads against 1 GB of gallery and was shared-memory-load bound).  A 32-wide tile was measured slower
+// on the usual ~17-detection frames (97 vs 70 us per 64 streams: three times the shared memory, a third of the blocks).
+constexpr int APP_DT = 16;
+constexpr int APP_GEMM_MIN = 48;
 __device__ __forceinline__ void appearance_rows(const Dev& t, const int* __restrict__ det_count,
                                                 const int* __restrict__ crop_slot, int stride_k, float* sm_f) {
   // sm_f: [APP_DT][F] detection tile, then [8][APP_DT] per-warp minima
@@ -432,12 +434,12 @@ __device__ __forceinline__ void appearance_gemm(const Dev& t, const int* __restr
 }
 
 constexpr size_t AG_SMEM = (AG_KC * (AG_ROWS + 4) + AG_KC * (AG_DT + 4) + 16 * AG_DT) * sizeof(float);
-// One launch, two tilings: frames with at most APP_DT detections take the one-pass row kernel (gallery streamed once,
-// no padding work), busier frames the SGEMM tiling.  The choice is per block from the device-side count.
+// One launch, two tilings: frames with at most APP_GEMM_MIN detections take the row kernel (no padding work), busier
+// frames the SGEMM tiling.  The choice is per block from the device-side count.
 __global__ void __launch_bounds__(256) appearance_kernel(Dev t, const int* __restrict__ det_count,
                                                          const int* __restrict__ crop_slot, int stride_k, int gemm_ok) {
   extern __shared__ __align__(16) float sm_f[];
-  if (gemm_ok && min(det_count[blockIdx.y], t.D) > APP_DT) appearance_gemm(t, det_count, crop_slot, stride_k, sm_f);
+  if (gemm_ok && min(det_count[blockIdx.y], t.D) > APP_GEMM_MIN) appearance_gemm(t, det_count, crop_slot, stride_k, sm_f);
   else appearance_rows(t, det_count, crop_slot, stride_k, sm_f);
 }
 
