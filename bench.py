@@ -158,6 +158,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # stdout carries exactly one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     from ai_camera_b200 import _lib, sharding, synth
