@@ -700,7 +700,9 @@ void free_packed_conv(PackedConv* p) {
   if (p->w) cudaFree(p->w);
   if (p->bias) cudaFree(p->bias);
   if (p->w_nt) cudaFree(p->w_nt);
+  if (p->w_pair) cudaFree(p->w_pair);
   p->w_nt = nullptr;
+  p->w_pair = nullptr;
   p->w = nullptr;
   p->bias = nullptr;
 }

@@ -19,6 +19,9 @@ struct PackedConv {
   // (K slab, n-tile) stage needs are then one contiguous run = one bulk copy instead of one per K chunk
   __nv_bfloat16* w_nt = nullptr;
   int nt_block = 0;
+  // 3x3 stride-1 layers with 64 / 128 output channels: [rank][K / 8][cout / 2][8], the halves of the weight columns the
+  // two CTAs of a cta_group::2 pair keep (conv_pair.cu); made by pack_pair_weights for layers that run zero-bordered
+  __nv_bfloat16* w_pair = nullptr;
 };
 
 struct ConvLaunch {
@@ -52,6 +55,7 @@ int pack_conv_weights(const float* w_oihw, const float* bias, int cout, int cin,
 // 3x3 / stride 2 / pad 1 layer re-expressed over its space-to-depth input [h/2][w/2][2x2 sub-pixel][c0_pad]:
 // a 2x2 stride-1 window (pad 1 top / left) with K = tap2 * (4 c0_pad) + (sy * 2 + sx) * c0_pad + c; cin <= c0_pad in {4, 16}
 int pack_conv_weights_s2d(const float* w_oihw, const float* bias, int cout, int cin, int c0_pad, PackedConv* out);
+int pack_pair_weights(PackedConv* p);
 void free_packed_conv(PackedConv* p);
 int launch_conv(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream);
 

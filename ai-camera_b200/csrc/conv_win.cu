@@ -910,7 +910,13 @@ struct WinPlan {
 
 // Returns 1 when the layer was launched on the window kernel, 0 when the shape is not eligible
 // (the caller falls back to conv_tc_kernel), negative on error.
+int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream);
+
 int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream) {
+  if (mode_is_flatwin(pc, L) && pc.w_pair) {  // 64 / 128-channel 3x3 layers of a zero-bordered trunk: CTA pairs (conv_pair.cu)
+    const int prc = try_launch_conv_pair(pc, L, stream);
+    if (prc != 0) return prc;
+  }
   static const bool disabled = getenv("AICAM_NO_WIN") != nullptr;
   static const int force_mt = getenv("AICAM_WIN_MT") ? atoi(getenv("AICAM_WIN_MT")) : 0;
   if (disabled || get_encode_tiled() == nullptr) return 0;

@@ -328,6 +328,10 @@ struct Builder {
           conv(name + ".downsample.0", V(cur), h, w, V(resbuf), c, cout, 1, s, 0);
         }
         conv(name + ".conv2", V(t), ho, wo, V(o), cout, cout, 3, 1, 2, V(resbuf), 2);
+        if (pd && !err) {  // zero-bordered 3x3 stride-1 layers with 64 / 128 channels run on CTA pairs (conv_pair.cu)
+          if (s == 1) pack_pair_weights(&e->convs[e->conv_by_name[name + ".conv1"]]);
+          pack_pair_weights(&e->convs[e->conv_by_name[name + ".conv2"]]);
+        }
         cur = o; h = ho; w = wo; c = cout;
       }
     }
@@ -708,6 +712,7 @@ int aicam_conv2d_padded(const aicam_conv_desc* d, const void* in, const float* w
   L.res_coff = 0; L.res_mode = res ? d->res_mode : 0;
   L.act = d->act;
   L.in_pad = ip; L.out_pad = opd;
+  if (ip && opd) pack_pair_weights(&pc);
   int rc = launch_conv(pc, L, static_cast<cudaStream_t>(stream));
   cudaError_t se = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
   free_packed_conv(&pc);
@@ -770,6 +775,7 @@ int aicam_conv2d_bench(const aicam_conv_desc* d, int iters, double* mean_ms, voi
   L.in = in; L.in_img_stride = static_cast<long long>(d->h + 2 * bp) * (d->w + 2 * bp) * cs; L.in_cstride = cs; L.in_coff = 0;
   L.batch = d->batch; L.h = d->h; L.w = d->w; L.ho = ho; L.wo = wo;
   L.in_pad = bp; L.out_pad = bp;
+  if (bp) pack_pair_weights(&pc);
   if (c0) {  // the timed launches read the same bytes as an already space-to-depth tensor
     L.in_cstride = 4 * c0; L.h = d->h / 2; L.w = d->w / 2; L.ho = L.h; L.wo = L.w;
   }
