@@ -52,7 +52,7 @@ constexpr int EPI_WARPS = 16;
 constexpr int THREADS = (EPI_WARPS + 3) * 32;
 constexpr uint32_t OFF_BIAS = 256, OFF_W = 1024, OFF_A = OFF_W + W_BYTES, OFF_CONV = OFF_A + STAGES * STAGE_BYTES;
 constexpr uint32_t CONV_TILE_BYTES = 256 * PITCH;
-constexpr uint32_t SMEM_BYTES = OFF_CONV + 2 * CONV_TILE_BYTES;  // convolution tile double-buffered: one barrier per tile
+constexpr uint32_t SMEM_BYTES = OFF_CONV + 4 * CONV_TILE_BYTES;  // two epilogue groups x double-buffered convolution tile
 
 struct StemArgs {
   const __nv_bfloat16* wgt;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(THREADS, 1) reid_stem_pool_kernel(const StemAr
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);
-      mbar_init(bar_acc_empty + 8 * s, EPI_WARPS * 32);
+      mbar_init(bar_acc_empty + 8 * s, EPI_WARPS * 32 / 2);  // one group of 8 epilogue warps per accumulator buffer
     }
     mbar_init(bar_w_full, 1);
     mbar_init_fence();
@@ -138,55 +138,61 @@ __global__ void __launch_bounds__(THREADS, 1) reid_stem_pool_kernel(const StemAr
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp < EPI_WARPS) {
-    // ================================================================== epilogue + pooling
-    const int wg = warp >> 2, wq = warp & 3;
-    const int j = wg >> 1;                 // which 128-row accumulator
-    const int c_lo = (wg & 1) * 32;        // my 32 of its 64 columns
+    // ================================================================== epilogue + pooling, two groups of 8 warps
+    // Group g owns the tiles with (it & 1) == g, i.e. always accumulator buffer g and convolution tile g: while one
+    // group waits for TMEM or pools, the other is in the opposite phase - the phases of consecutive tiles overlap
+    // instead of all 16 warps marching through them together (one named barrier per group, 256 threads).
+    const int g = warp >> 3, lw = warp & 7;
+    const int wq = lw & 3;                   // TMEM lane quarter (= warp % 4)
+    const int j = lw >> 2;                   // which 128-row accumulator
     const int q = j * 128 + wq * 32 + lane;  // my raster position
     const int ry = q / RW, rx = q - ry * RW;
-    const uint32_t my_row_off = static_cast<uint32_t>(q) * PITCH + c_lo * 2;
-    const uint32_t taddr_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + j * COUT + c_lo;
-    // pooling role: thread t < 384 owns pooled pixel t / 8 of the tile and channels 8 (t % 8) .. + 7
-    const int pt = threadIdx.x;
-    const int pp = pt >> 3, pg = pt & 7;
-    const int ppy = pp / PW, ppx = pp - ppy * PW;
+    const uint32_t my_row_off = static_cast<uint32_t>(q) * PITCH;
+    const uint32_t taddr_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + g * 128 + j * COUT;
+    // pooling role: item i < 384 is pooled pixel i / 8 of the tile, channels 8 (i % 8) .. + 7; thread gt takes gt, gt + 256
+    const int gt = lw * 32 + lane;
+    const int pg = gt & 7;
     float pbias[8];  // bias and ReLU commute with the max: applied to the 48 pooled pixels, not the 231 convolution pixels
 #pragma unroll
     for (int i = 0; i < 8; ++i) pbias[i] = bias_s[pg * 8 + i];
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      uint8_t* conv_s = smem + OFF_CONV + buf * CONV_TILE_BYTES;
+    int it = g;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
+      // the group's convolution tile is double-buffered: a thread that is already writing tile it + 2 cannot disturb a
+      // slower thread still pooling tile it; tile it + 4 reuses the buffer only after the barrier of tile it + 2
+      uint8_t* conv_s = smem + OFF_CONV + (g * 2 + ((it >> 1) & 1)) * CONV_TILE_BYTES;
       const int n = tile / tiles_per_img;
       const int r2 = tile - n * tiles_per_img;
       const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
       const int y = 2 * ty * PH - 1 + ry, x = 2 * tx * PW - 1 + rx;  // my convolution pixel
       const bool valid = q < NPOS && rx < CC && y >= 0 && y < a.h && x >= 0 && x < a.w;
-      mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1);
+      mbar_wait(bar_acc_full + 8 * g, (it >> 1) & 1);
       tc_fence_after();
-      uint32_t v0[16], v1[16];
-      tc_ld16_nowait(taddr_lane + buf * 128, v0);
-      tc_ld16_nowait(taddr_lane + buf * 128 + 16, v1);
+      uint32_t v0[16], v1[16], v2[16], v3[16];
+      tc_ld16_nowait(taddr_lane, v0);
+      tc_ld16_nowait(taddr_lane + 16, v1);
+      tc_ld16_nowait(taddr_lane + 32, v2);
+      tc_ld16_nowait(taddr_lane + 48, v3);
       tc_ld_wait();
       tc_fence_before();
-      mbar_arrive(bar_acc_empty + 8 * buf);  // accumulator read: the MMA warp may reuse the buffer
+      mbar_arrive(bar_acc_empty + 8 * g);  // accumulator read: the MMA warp may reuse the buffer
       if (q < NPOS) {
         // raw accumulators as bf16; positions outside the crop lose every max (-inf)
-        uint32_t o[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          o[i] = valid ? pack_bf16x2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1])) : 0xFF80FF80u;
-          o[8 + i] = valid ? pack_bf16x2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1])) : 0xFF80FF80u;
-        }
         uint8_t* my_row = conv_s + my_row_off;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(my_row + i * 16) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        for (int h = 0; h < 4; ++h) {
+          const uint32_t(&v)[16] = h == 0 ? v0 : (h == 1 ? v1 : (h == 2 ? v2 : v3));
+          uint32_t o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = valid ? pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) : 0xFF80FF80u;
+          *reinterpret_cast<uint4*>(my_row + h * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(my_row + h * 32 + 16) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
       }
-      // convolution tile complete (the other buffer is still being pooled by nobody: every thread passed this
-      // barrier for tile it - 1 only after its own pooling of tile it - 2)
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-      if (pt < PH * PW * 8) {
+      // the group's convolution tile is complete (and every thread of the group has finished pooling the previous one)
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(256) : "memory");
+      for (int i = gt; i < PH * PW * 8; i += 256) {
+        const int pp = i >> 3;
+        const int ppy = pp / PW, ppx = pp - ppy * PW;
         const int py = ty * PH + ppy, px = tx * PW + ppx;
         if (py < a.ph && px < a.pw) {
           const uint8_t* base = conv_s + static_cast<size_t>((2 * ppy) * RW + 2 * ppx) * PITCH + pg * 16;
@@ -199,8 +205,8 @@ __global__ void __launch_bounds__(THREADS, 1) reid_stem_pool_kernel(const StemAr
           const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
           uint32_t ow[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            ow[i] = pack_bf16x2(fmaxf(bf16_lo(mw[i]) + pbias[2 * i], 0.0f), fmaxf(bf16_hi(mw[i]) + pbias[2 * i + 1], 0.0f));
+          for (int k = 0; k < 4; ++k)
+            ow[k] = pack_bf16x2(fmaxf(bf16_lo(mw[k]) + pbias[2 * k], 0.0f), fmaxf(bf16_hi(mw[k]) + pbias[2 * k + 1], 0.0f));
           *reinterpret_cast<uint4*>(a.out + ((static_cast<long long>(n) * (a.ph + 2 * a.out_pad) + py + a.out_pad) * (a.pw + 2 * a.out_pad) + px + a.out_pad) * COUT + pg * 8) =
               make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
