@@ -78,6 +78,9 @@ struct WinArgs {
   int flat;  // 1x1 mode: output and residual are dense, pixel p of the batch sits at p * cstride
   int out_pad;   // flat / im2col modes: output (and residual) images carry a one-pixel zero border, interior at (1, 1)
   int box_rows;  // mode 4: raster rows per TMA box (a patch is MT boxes)
+  int epi_alt;      // TMA epilogue, two accumulators per tile, narrow n-tiles: the two column teams take ALTERNATE tiles
+                    // (all columns each) instead of half the columns of every tile - each team then has two tile times
+                    // for its latency chain (TMEM read -> finish -> staging -> store hand-off)
   int res_inplace;  // TMA epilogue: the residual tile is loaded INTO the output staging buffer and finished in place
                     // (no residual ring): the store of tile i is followed by the residual load of tile i + nstage
   int direct_out;  // generic epilogue: every thread stores its finished 32-byte groups straight to global (whole
@@ -271,12 +274,12 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);
-      mbar_init(bar_acc_empty + 8 * s, 128 * NWG);
+      mbar_init(bar_acc_empty + 8 * s, a.epi_alt ? 64 * NWG : 128 * NWG);
     }
     mbar_init(bar_w_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_res_full + 8 * s, 1);
-      mbar_init(bar_res_empty + 8 * s, 128 * NWG);
+      mbar_init(bar_res_empty + 8 * s, a.epi_alt ? 64 * NWG : 128 * NWG);
     }
     mbar_init(bar_stage_free, 1);
     mbar_init(bar_stage_free + 8, 1);
@@ -324,15 +327,18 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
     }
     uint8_t* stage0 = smem + a.off_stage;
     const uint8_t* res_base = smem + (a.res_inplace ? a.off_stage : a.off_res);
-    uint32_t rslot = 0, rphase = 0;
+    const bool alt = MT == 2 && a.epi_alt != 0;
+    const uint32_t hand_off = alt ? 64 * NWG + 32 : 128 * NWG + 32;  // threads on the epilogue -> I/O warp barrier
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      if (alt && (it & 1) != part) continue;  // the other team's tile
       const int buf = it & 1;
+      const uint32_t rslot = a.nres == 2 ? (it & 1) : 0, rphase = a.nres == 2 ? ((it >> 1) & 1) : (it & 1);
       const int mt_idx = a.n_tiles == 1 ? tile : tile / a.n_tiles;
       const int n0 = (tile - mt_idx * a.n_tiles) * a.n_tile;
       const int ncols = min(a.n_tile, a.cout - n0);
       const int groups = (ncols + 15) >> 4;
-      const int g_lo = (groups * part) / PARTS, g_hi = (groups * (part + 1)) / PARTS;
+      const int g_lo = alt ? 0 : (groups * part) / PARTS, g_hi = alt ? groups : (groups * (part + 1)) / PARTS;
       if (threadIdx.x == 0) WIN_TRACE(it, 8);
       mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
@@ -385,15 +391,12 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       if (!stage_ok) mbar_wait(sfree_bar, sfree_par);  // (no column group: keep the phases in step)
       tc_fence_before();
       mbar_arrive(bar_acc_empty + 8 * buf);
-      if (a.res_mode) {
-        mbar_arrive(bar_res_empty + 8 * rslot);
-        if (++rslot == static_cast<uint32_t>(a.nres)) { rslot = 0; rphase ^= 1; }
-      }
+      if (a.res_mode) mbar_arrive(bar_res_empty + 8 * rslot);
       if (threadIdx.x == 0) WIN_TRACE(it, 12);
       fence_proxy_async();  // my staging writes -> visible to the TMA unit
       // hand the tile to the I/O warp: arrive without waiting (it syncs on the same barrier).  Two barrier ids
       // alternate: a thread can be one tile ahead of the I/O warp, never two (the staging-buffer wait above)
-      asm volatile("bar.arrive %0, %1;" ::"r"(2 + (it & 1)), "n"(128 * NWG + 32) : "memory");
+      asm volatile("bar.arrive %0, %1;" ::"r"(2 + (it & 1)), "r"(hand_off) : "memory");
       if (threadIdx.x == 0) WIN_TRACE(it, 13);
     }
   } else if (warp < 4 * NWG) {
@@ -793,7 +796,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       coords(tile, n0, cx, cy, cn);
       const int sbuf = a.nstage == 2 ? (io_it & 1) : 0;
       const uint32_t src = sbase + a.off_stage + sbuf * a.stage_buf_bytes;
-      asm volatile("bar.sync %0, %1;" ::"r"(2 + (io_it & 1)), "n"(128 * NWG + 32) : "memory");  // every epilogue thread has staged its part
+      asm volatile("bar.sync %0, %1;" ::"r"(2 + (io_it & 1)), "r"((MT == 2 && a.epi_alt) ? 64 * NWG + 32 : 128 * NWG + 32)
+                   : "memory");  // every epilogue thread (of the tile's team) has staged its part
       if (lane == 0) {
         const bool two = a.pieces == 2 && n0 + a.piece_ch[0] < a.cout;
         if (WINDOW) {
@@ -1211,6 +1215,8 @@ plan:
             (!res_mode || L.res_img_stride == static_cast<long long>(a.hw) * L.res_cstride)) ? 1 : 0;
   a.res_direct = (!epi && res_mode != 0 && !res_staged) ? 1 : 0;
   a.res_inplace = (epi && mode == 4) ? 1 : 0;
+  static const bool no_alt = getenv("AICAM_WIN_NO_EPI_ALT") != nullptr;
+  a.epi_alt = (!no_alt && epi && best.mt == 2 && n_tile <= 32 && best.nstage == 2 && (!res_mode || best.nres == 2) && !a.res_inplace) ? 1 : 0;
   const size_t smem = epi ? a.off_stage + static_cast<size_t>(best.stage_buf) * (best.nstage + (a.res_inplace ? 0 : best.nres))
                           : a.off_stage + (direct_out ? 0 : static_cast<size_t>(a.tm) * (stage_pitch + (res_staged ? res_pitch : 0)));
   if (smem > SMEM_LIMIT) return 0;
