@@ -313,7 +313,7 @@ def main():
     # DRAM bytes of the same kernels for one step, from the committed ncu pass (profiles/r1_step_traffic.json)
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_step_traffic_v5.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_step_traffic_v6.json")) as f:
             traffic = json.load(f)
     except Exception:
         pass
@@ -352,7 +352,7 @@ def main():
                 "note": "raw 1080p frames from pinned host memory, copy double-buffered against compute; "
                         "bounded by the PCIe host-to-device rate once compute is faster than the copy"},
         "gpu_launches": int(gpu_launches),
-        "roofline": {"kernel": "tcgen05 convolution kernels: conv_win_kernel + reid_stem_pool_kernel + conv_tc_kernel "
+        "roofline": {"kernel": "tcgen05 convolution kernels: conv_win_kernel + conv_pair_kernel + reid_stem_pool_kernel "
                                "(all %d launches of a step)" % (nl.value // prof_steps),
                      "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16"], "unit": "TFLOP/s",
                      "frac": achieved_tflops / peaks["bf16"], "traffic": traffic_per_launch, "traffic_unit": "bytes/launch",
