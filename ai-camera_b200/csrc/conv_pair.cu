@@ -553,9 +553,9 @@ int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t
   // Measured on B200 (1024 crops, same box, conv_win.cu mode 4 -> pairs): 128 channels 146 -> 135 us; 64 channels
   // 203 -> 190..224 us (the epilogue's shared-memory traffic competes with an operand fetch that now keeps the port 95 %
   // busy); 256 / 512 channels 148 -> 158 us and 197 -> 198 us (the 256-column single-CTA tile is already tensor-bound).
-  // So only the 128-channel layers run on pairs by default; AICAM_PAIR_ALL=1 sends every eligible layer here.
+  // So the 128- and 512-channel layers run on pairs by default; AICAM_PAIR_ALL=1 sends every eligible layer here.
   static const bool pair_all = getenv("AICAM_PAIR_ALL") != nullptr;
-  if (cout_pad != 128 && !pair_all) return 0;
+  if (cout_pad != 128 && cout_pad != 512 && !pair_all) return 0;  // (512 channels: 204 -> 195 us with the deeper weight ring)
   const int n_tile = std::min(cout_pad, 256), n_half = n_tile / 2, n_tiles = cout_pad / n_tile;
   const int tps = n_tile == 256 ? 1 : 3;
   const int res_mode = L.res ? L.res_mode : 0;
@@ -586,13 +586,15 @@ int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t
     const size_t wsm = resident ? (wbytes_half + 1023) / 1024 * 1024 : 0;
     // two staging buffers where they fit (the residual load of tile i + 1 then overlaps the epilogue of tile i),
     // at least two patches and three weight stages in flight
-    for (int nstage = 2; nstage >= 1 && !best_mt; --nstage) {
+    // (streamed weights: a tile's MMAs outlast the store -> residual-load chain of a single staging buffer, and the
+    //  weight ring needs the shared memory more: every stage makes a relay hop through the peer)
+    for (int nstage = resident ? 2 : 1; nstage >= 1 && !best_mt; --nstage) {
       const size_t fixed = OFF_RING_A + wsm + nstage * stage_buf + 1024;
       if (fixed + 2 * patch + (resident ? 0 : 3 * static_cast<size_t>(bstage)) > SMEM_LIMIT) continue;
       int sa = 2, sb = resident ? 1 : 3;
       size_t used = fixed + sa * patch + (resident ? 0 : static_cast<size_t>(sb) * bstage);
       if (!resident)
-        while (sb < MAX_RING && sb < 5 && used + bstage <= SMEM_LIMIT) { ++sb; used += bstage; }
+        while (sb < MAX_RING && used + bstage + (sa < 3 ? patch : 0) <= SMEM_LIMIT) { ++sb; used += bstage; }
       while (sa < std::max(3, 2 * slabs) && sa < MAX_RING && used + patch <= SMEM_LIMIT) { ++sa; used += patch; }
       best_mt = mt; best_sa = sa; best_sb = sb; best_nstage = nstage; best_bh = bh;
       best_smem = used;
