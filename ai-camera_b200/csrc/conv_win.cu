@@ -78,6 +78,8 @@ struct WinArgs {
   int flat;  // 1x1 mode: output and residual are dense, pixel p of the batch sits at p * cstride
   int out_pad;   // flat / im2col modes: output (and residual) images carry a one-pixel zero border, interior at (1, 1)
   int box_rows;  // mode 4: raster rows per TMA box (a patch is MT boxes)
+  int s2d_store;    // TMA epilogue of a space-to-depth output: the tile is stored through a 5-D map (2C, x/2, y&1, y/2, n) whose
+                    // box image is the plain compact [y][x][C] staging tile (no swizzle); tile origins and sizes are even
   int epi_alt;      // TMA epilogue, two accumulators per tile, narrow n-tiles: the two column teams take ALTERNATE tiles
                     // (all columns each) instead of half the columns of every tile - each team then has two tile times
                     // for its latency chain (TMEM read -> finish -> staging -> store hand-off)
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
       const uint32_t ro = static_cast<uint32_t>(crow) * pb;
       const uint32_t mask = pb == 128 ? 7u : (pb == 64 ? 3u : 1u);
       row_off[p] = a.piece_off[p] + ro;
-      row_xor[p] = ((ro >> 7) & mask) << 4;
+      row_xor[p] = a.s2d_store ? 0u : ((ro >> 7) & mask) << 4;
     }
     uint8_t* stage0 = smem + a.off_stage;
     const uint8_t* res_base = smem + (a.res_inplace ? a.off_stage : a.off_res);
@@ -800,7 +802,9 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
                    : "memory");  // every epilogue thread (of the tile's team) has staged its part
       if (lane == 0) {
         const bool two = a.pieces == 2 && n0 + a.piece_ch[0] < a.cout;
-        if (WINDOW) {
+        if (WINDOW && a.s2d_store) {
+          tma_store_5d(&maps.out[0], src + a.piece_off[0], 0, cx >> 1, 0, cy >> 1, cn);
+        } else if (WINDOW) {
           tma_store_4d(&maps.out[0], src + a.piece_off[0], n0, cx, cy, cn);
           if (two) tma_store_4d(&maps.out[1], src + a.piece_off[1], n0 + a.piece_ch[0], cx, cy, cn);
         } else {
@@ -1013,7 +1017,11 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
     const int rest = n_tile - first;
     if (rest == 0 || rest == 64 || rest == 32 || rest == 16) { piece_ch[0] = first; piece_ch[1] = rest; }
   }
-  bool epi = !no_tma_epi && piece_ch[0] != 0 && !L.out_f32 && !L.out_s2d && pc.cout % 8 == 0;
+  // a space-to-depth output can take the TMA epilogue when the tile is the whole channel width of a dense tensor
+  static const bool no_s2d_epi = getenv("AICAM_WIN_NO_S2D_EPI") != nullptr;
+  const bool s2d_store = L.out_s2d && !no_s2d_epi && !res_mode && n_tiles == 1 && piece_ch[1] == 0 && piece_ch[0] == pc.cout &&
+                         L.out_cstride == pc.cout && L.out_coff == 0 && L.ho % 2 == 0 && L.wo % 2 == 0 && pc.cout * 2 % 16 == 0;
+  bool epi = !no_tma_epi && piece_ch[0] != 0 && !L.out_f32 && (!L.out_s2d || s2d_store) && pc.cout % 8 == 0;
 
   // ---- choose the tiling: strips x (linear | row-aligned) x mt, cheapest estimated time
   WinPlan best;
@@ -1046,10 +1054,12 @@ plan:
         size_t stage_bytes = direct_out ? 0 : static_cast<size_t>(tm) * (stage_pitch + (res_staged ? res_pitch : 0));
         if (window) {
           p.tw = (win_w + strips - 1) / strips;
+          if (s2d_store && epi && (p.tw & 1)) ++p.tw;  // even strip widths: strips start on 2x2 block boundaries
           p.rw = p.tw + kw1;
           if (p.rw > 256 || (strips > 1 && p.tw < 8)) continue;
           if (aligned) {
-            const int th = tm / p.rw;
+            int th = tm / p.rw;
+            if (s2d_store && epi) th &= ~1;  // whole 2x2 blocks per tile
             if (th < 1) continue;
             p.tstep = th * p.rw;
             p.tiles_per_strip = (win_h + th - 1) / th;
@@ -1180,6 +1190,7 @@ plan:
   a.act = L.act;
   a.trace = L.trace;
   a.out_s2d = (window && L.out_s2d) ? 1 : 0;
+  a.s2d_store = (epi && s2d_store) ? 1 : 0;
   a.batch = L.batch; a.batch_dev = L.batch_dev;
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n_tile >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
   uint32_t cols = 32;
@@ -1281,6 +1292,19 @@ plan:
                                   fe, CU_TENSOR_MAP_INTERLEAVE_NONE, psw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         }
+        continue;
+      }
+      if (a.s2d_store) {
+        // [n][y/2][x/2][y&1][x&1][C] seen as (2C, x/2, y&1, y/2, n): a (tw x th) tile is the box (2C, tw/2, 2, th/2, 1)
+        const cuuint64_t C2 = static_cast<cuuint64_t>(pc.cout) * 2;
+        const cuuint64_t d5[5] = {C2, static_cast<cuuint64_t>(L.wo / 2), 2, static_cast<cuuint64_t>(L.ho / 2), static_cast<cuuint64_t>(L.batch)};
+        const cuuint64_t s5[4] = {2 * C2 * 2, C2 * 2, static_cast<cuuint64_t>(L.wo / 2) * 2 * C2 * 2,
+                                  static_cast<cuuint64_t>(L.out_img_stride) * 2};
+        const cuuint32_t b5[5] = {static_cast<cuuint32_t>(C2), static_cast<cuuint32_t>(best.tw / 2), 2, static_cast<cuuint32_t>(a.th / 2), 1};
+        const cuuint32_t e5[5] = {1, 1, 1, 1, 1};
+        cr = get_encode_tiled()(&maps.out[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, static_cast<__nv_bfloat16*>(L.out), d5, s5, b5, e5,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         continue;
       }
       const cuuint32_t box[4] = {static_cast<cuuint32_t>(piece_ch[q]), static_cast<cuuint32_t>(best.tw), static_cast<cuuint32_t>(a.th), 1};
