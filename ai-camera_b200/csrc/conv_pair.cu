@@ -574,7 +574,6 @@ int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t
 
   // tiling: MT accumulators per CTA; staging = the TMA-epilogue tile (residual finished in place)
   int best_mt = 0, best_sa = 0, best_sb = 0, best_nstage = 0, best_bh = 0;
-  size_t best_smem = 0;
   for (int mt = 2; mt >= 1; --mt) {
     if (force_mt && mt != force_mt) continue;
     if (2 * mt * n_tile > 512) continue;
@@ -597,7 +596,6 @@ int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t
         while (sb < MAX_RING && used + bstage + (sa < 3 ? patch : 0) <= SMEM_LIMIT) { ++sb; used += bstage; }
       while (sa < std::max(3, 2 * slabs) && sa < MAX_RING && used + patch <= SMEM_LIMIT) { ++sa; used += patch; }
       best_mt = mt; best_sa = sa; best_sb = sb; best_nstage = nstage; best_bh = bh;
-      best_smem = used;
     }
     if (best_mt) break;
   }
@@ -631,7 +629,6 @@ int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t
   a.res_tx_bytes = a.stage_buf_bytes;
   const size_t smem = a.off_stage + static_cast<size_t>(best_nstage) * a.stage_buf_bytes;
   if (smem > SMEM_LIMIT) return 0;
-  (void)best_smem;
 
   alignas(64) PairMaps maps;
   std::memset(&maps, 0, sizeof(maps));
@@ -681,8 +678,7 @@ int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t
   }
   const long long pair_tiles = (padded_pixels + 2 * tm - 1) / (2 * tm) * n_tiles;
   const unsigned pairs = static_cast<unsigned>(std::min<long long>(pair_tiles, num_sms / 2));
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(PAIR_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -1354,8 +1354,7 @@ plan:
     // programmatic dependent launch: this layer's prologue (barriers, TMEM, bias, resident weights / first weight
     // stages) overlaps the previous layer's tail; its activation traffic starts after griddepcontrol.wait
     static const bool no_pdl = getenv("AICAM_NO_PDL") != nullptr;
-    cudaLaunchConfig_t cfg;
-    std::memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(WIN_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
