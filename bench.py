@@ -131,10 +131,22 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT = None  # the real stdout; everything else written to file descriptor 1 (NCCL's version banner, library chatter) goes to stderr
+
+
+def emit(line):
+    _RESULT.write(json.dumps(line) + "\n")
+    _RESULT.flush()
 
 
 def main():
+    global _RESULT
+    sys.stdout.flush()
+    _RESULT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)  # stdout carries exactly one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -158,8 +170,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # stdout carries exactly one JSON line (NCCL prints its version banner there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     from ai_camera_b200 import _lib, sharding, synth
@@ -368,7 +379,7 @@ def main():
         fps, dt, cores = cpu_baseline_run(yolo, reid, bias, frames, cpu_steps, warmup=1)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": "%d streams x %d steps of the same 1080p frames (%.1f s)" % (n_sample, cpu_steps, dt)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
