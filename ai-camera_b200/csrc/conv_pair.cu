@@ -68,6 +68,7 @@ struct PairArgs {
   int nstage, pieces;
   uint32_t piece_off[4];
   uint32_t res_tx_bytes;
+  float4 bias4[128];  // the bias, read from the constant bank
   long long* trace;  // debug: clock64 stamps of CTA 0 (AICAM_CONV_TRACE in aicam_conv2d_bench), same slots as conv_win.cu
 };
 
@@ -146,7 +147,7 @@ __device__ __forceinline__ float activate(float x) {
 // 16 accumulator columns of one row: + bias (+ residual, read from the staging tile itself), activation, bf16, back
 // into the staging tile (two 16-byte chunks at swizzled positions o0 / o1)
 template <int ACT>
-__device__ __forceinline__ void finish16(const uint32_t (&v)[16], const float* bias, int res_mode, uint8_t* p0, uint8_t* p1) {
+__device__ __forceinline__ void finish16(const uint32_t (&v)[16], const float (&bias)[16], int res_mode, uint8_t* p0, uint8_t* p1) {
   float x[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]) + bias[i];
@@ -174,7 +175,8 @@ __device__ __forceinline__ void finish16(const uint32_t (&v)[16], const float* b
 }
 
 template <int MT, int ACT, int TPS>
-__global__ void __launch_bounds__(PAIR_THREADS, 1) conv_pair_kernel(const PairArgs a, const __grid_constant__ PairMaps maps) {
+__global__ void __launch_bounds__(PAIR_THREADS, 1) conv_pair_kernel(const __grid_constant__ PairArgs a,
+                                                                    const __grid_constant__ PairMaps maps) {
   constexpr int TM = 128 * MT;
   constexpr int TAPS = 9;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -185,7 +187,6 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) conv_pair_kernel(const PairAr
   const uint32_t bar_peer_w = sbase + 344;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 352);
   const uint32_t bar_peer_a = sbase + 384, bar_peer_b = sbase + 448, bar_peer_acc = sbase + 512;
-  float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -216,7 +217,6 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) conv_pair_kernel(const PairAr
   }
   if (warp == 4 * NWG) tc_alloc2(smem_u32(tmem_ptr_smem), a.tmem_cols);
   if (warp == 4 * NWG + 1 && lane == 0) tma_prefetch_desc(&maps.in);
-  for (int i = threadIdx.x; i < a.n_tile * a.n_tiles; i += PAIR_THREADS) bias_s[i] = i < a.cout ? __ldg(a.bias + i) : 0.0f;
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // both CTAs: barriers initialised, TMEM allocated
@@ -278,7 +278,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) conv_pair_kernel(const PairAr
             *reinterpret_cast<uint4*>(p0) = make_uint4(0u, 0u, 0u, 0u);
             *reinterpret_cast<uint4*>(p1) = make_uint4(0u, 0u, 0u, 0u);
           } else {
-            finish16<ACT>(hh ? v1 : v0, bias_s + n0 + c, a.res_mode, p0, p1);
+            float bv[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = a.bias4[((n0 + c) >> 2) + i];
+              bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
+            }
+            finish16<ACT>(hh ? v1 : v0, bv, a.res_mode, p0, p1);
           }
         }
       }
@@ -613,6 +619,8 @@ int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t
   a.n_tile = n_tile; a.n_half = n_half; a.cout = pc.cout; a.n_tiles = n_tiles; a.tps = tps;
   a.wgt_pair = pc.w_pair; a.half_elems = static_cast<long long>(pc.q_pad) * n_half * 8;
   a.bias = pc.bias; a.res_mode = res_mode;
+  if (!pc.bias_host) return 0;
+  std::memcpy(a.bias4, pc.bias_host, sizeof(float) * cout_pad);
   a.batch = L.batch; a.batch_dev = L.batch_dev;
   a.trace = L.trace;
   // instruction descriptor: fp32 accumulate, bf16 A / B, K-major, N = n_tile, M = 256 (the pair)

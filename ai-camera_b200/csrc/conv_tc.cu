@@ -649,6 +649,8 @@ int pack_conv_weights(const float* w, const float* bias, int cout, int cin, int 
   AICAM_CUDA_OK(cudaMalloc(&p.bias, b.size() * 4));
   AICAM_CUDA_OK(cudaMemcpy(p.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
   AICAM_CUDA_OK(cudaMemcpy(p.bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  p.bias_host = static_cast<float*>(std::malloc(b.size() * 4));
+  if (p.bias_host) std::memcpy(p.bias_host, b.data(), b.size() * 4);
   const int nb = cout_pad % 256 == 0 ? 256 : pick_n_tile(cout_pad, false);  // (conv_win.cu takes 256-column tiles when it can)
   if (nb < cout_pad) {  // n-tile-major copy for the streamed-weight window kernel
     std::vector<uint16_t> nt(packed.size());
@@ -692,6 +694,8 @@ int pack_conv_weights_s2d(const float* w, const float* bias, int cout, int cin, 
   AICAM_CUDA_OK(cudaMalloc(&p.bias, b.size() * 4));
   AICAM_CUDA_OK(cudaMemcpy(p.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
   AICAM_CUDA_OK(cudaMemcpy(p.bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  p.bias_host = static_cast<float*>(std::malloc(b.size() * 4));
+  if (p.bias_host) std::memcpy(p.bias_host, b.data(), b.size() * 4);
   *out = p;
   return AICAM_OK;
 }
@@ -701,6 +705,8 @@ void free_packed_conv(PackedConv* p) {
   if (p->bias) cudaFree(p->bias);
   if (p->w_nt) cudaFree(p->w_nt);
   if (p->w_pair) cudaFree(p->w_pair);
+  std::free(p->bias_host);
+  p->bias_host = nullptr;
   p->w_nt = nullptr;
   p->w_pair = nullptr;
   p->w = nullptr;

@@ -10,6 +10,8 @@ namespace aicam {
 struct PackedConv {
   __nv_bfloat16* w = nullptr;  // device
   float* bias = nullptr;       // device, [cout]
+  float* bias_host = nullptr;  // host copy, [cout padded to 16]: the TMA-epilogue kernels take the bias as a kernel argument
+                               // (constant bank) - a shared-memory copy cost a third of their LDS wavefronts
   int cin = 0;        // real input channels
   int cin_pad = 0;    // 4 (stem: 3 -> 4) or a multiple of 8
   int cout = 0, ksize = 1, stride = 1;

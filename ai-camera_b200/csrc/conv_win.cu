@@ -108,6 +108,7 @@ struct WinArgs {
   const int* batch_dev;
   uint32_t idesc, tmem_cols;
   uint32_t off_w, off_b, off_stage, off_res, stage_pitch, res_pitch;
+  float4 bias4[128];  // TMA epilogue: the bias (<= 512 channels) read from the constant bank, not from shared memory
 };
 
 __device__ __forceinline__ float silu_fast(float x) {
@@ -212,6 +213,43 @@ __device__ __forceinline__ void finish_group(const uint32_t (&v)[16], const floa
   }
 }
 
+// the same with the bias already in registers and bf16 output (TMA epilogue)
+template <int ACT>
+__device__ __forceinline__ void finish_group_b(const uint32_t (&v)[16], const float (&b)[16], const uint8_t* res_row, int res_mode,
+                                               uint8_t* dst, const uint8_t* res_hi, uint8_t* dst_hi) {
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]) + b[i];
+  if (res_mode) {
+    const uint4 q0v = *reinterpret_cast<const uint4*>(res_row);
+    const uint4 q1v = *reinterpret_cast<const uint4*>(res_hi);
+    const uint32_t rw_[8] = {q0v.x, q0v.y, q0v.z, q0v.w, q1v.x, q1v.y, q1v.z, q1v.w};
+    if (res_mode == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[2 * i] = activate<ACT>(x[2 * i] + bf16_lo(rw_[i]));
+        x[2 * i + 1] = activate<ACT>(x[2 * i + 1] + bf16_hi(rw_[i]));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[2 * i] = activate<ACT>(x[2 * i]) + bf16_lo(rw_[i]);
+        x[2 * i + 1] = activate<ACT>(x[2 * i + 1]) + bf16_hi(rw_[i]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = activate<ACT>(x[i]);
+  }
+  uint4 o0, o1;
+  o0.x = pack_bf16x2(x[0], x[1]);   o0.y = pack_bf16x2(x[2], x[3]);
+  o0.z = pack_bf16x2(x[4], x[5]);   o0.w = pack_bf16x2(x[6], x[7]);
+  o1.x = pack_bf16x2(x[8], x[9]);   o1.y = pack_bf16x2(x[10], x[11]);
+  o1.z = pack_bf16x2(x[12], x[13]); o1.w = pack_bf16x2(x[14], x[15]);
+  *reinterpret_cast<uint4*>(dst) = o0;
+  *reinterpret_cast<uint4*>(dst_hi) = o1;
+}
+
 // Tile index -> image, column strip and first raster position (window mode)
 struct TilePos {
   int n_img, strip, q0;
@@ -229,7 +267,7 @@ __device__ __forceinline__ TilePos tile_pos(const WinArgs& a, int mt_idx) {
 #define WIN_TRACE(it, who) do { if (a.trace && blockIdx.x == 0 && (it) < 32) a.trace[(it) * 16 + (who)] = clock64(); } while (0)
 
 template <int SLAB, int AMODE, int MT, int ACT, int EPI>
-__global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs a, const __grid_constant__ WinMaps maps) {
+__global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_constant__ WinArgs a, const __grid_constant__ WinMaps maps) {
   constexpr uint32_t ROW_BYTES = SLAB * 2;
   constexpr int K16S = SLAB / 16;
   constexpr uint32_t LTYPE = SLAB == 64 ? 2u : (SLAB == 32 ? 4u : 6u);
@@ -385,7 +423,13 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const WinArgs 
               *reinterpret_cast<uint4*>(stage + o0) = make_uint4(0u, 0u, 0u, 0u);
               *reinterpret_cast<uint4*>(stage + o1) = make_uint4(0u, 0u, 0u, 0u);
             } else {
-              finish_group<ACT>(h ? v1 : v0, bias_s + n0 + c, res_buf + o0, a.res_mode, 0, stage + o0, res_buf + o1, stage + o1);
+              float bv[16];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 b4 = a.bias4[((n0 + c) >> 2) + i];
+                bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
+              }
+              finish_group_b<ACT>(h ? v1 : v0, bv, res_buf + o0, a.res_mode, stage + o0, res_buf + o1, stage + o1);
             }
           }
         }
@@ -1184,6 +1228,10 @@ plan:
   a.wbytes = static_cast<uint32_t>(wbytes);
   a.n_tile = n_tile; a.n_tiles = n_tiles; a.cout = pc.cout; a.cout_pad = cout_pad;
   a.wgt = pc.w; a.bias = pc.bias;
+  if (epi) {
+    if (!pc.bias_host) return fail(AICAM_ERR_INVALID_ARG, "conv_win: packed layer has no host copy of its bias");
+    std::memcpy(a.bias4, pc.bias_host, sizeof(float) * cout_pad);
+  }
   a.wgt_nt = (pc.w_nt && pc.nt_block == n_tile) ? pc.w_nt : nullptr; a.q_pad = pc.q_pad;
   a.out = L.out; a.out_img_stride = L.out_img_stride; a.out_cstride = L.out_cstride; a.out_coff = L.out_coff; a.out_f32 = L.out_f32;
   a.res = L.res; a.res_img_stride = L.res_img_stride; a.res_cstride = L.res_cstride; a.res_coff = L.res_coff; a.res_mode = res_mode;

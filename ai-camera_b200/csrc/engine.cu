@@ -595,6 +595,7 @@ int aicam_engine_set_bias(aicam_engine* e, const char* name, const float* host, 
   if (n != pc.cout) return fail(AICAM_ERR_INVALID_ARG, "engine_set_bias: length differs from the layer's cout");
   AICAM_CUDA_OK(cudaSetDevice(e->device));
   AICAM_CUDA_OK(cudaMemcpy(pc.bias, host, sizeof(float) * n, cudaMemcpyHostToDevice));
+  if (pc.bias_host) std::memcpy(pc.bias_host, host, sizeof(float) * n);  // (kernel-argument copy: takes effect at the next launch / capture)
   return AICAM_OK;
 }
 
