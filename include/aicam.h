@@ -68,9 +68,9 @@ int aicam_engine_num_anchors(const aicam_engine* e); /* yolov8: 8400 at 640x640 
 double aicam_engine_flops_per_item(const aicam_engine* e); /* 2*MACs per frame / per crop */
 int aicam_engine_num_launches(const aicam_engine* e);      /* kernels per forward */
 /* Overwrite a bias vector by blob tensor name (host float32 in); used to calibrate the
- * synthetic detector/ReID heads.  aicam_engine_get_bias reads it back (host out).  * The bias of most layers is passed to the kernels as a launch argument: a change takes effect at the next launch and is NOT seen by
- * CUDA graphs captured earlier.
- */
+ * synthetic detector/ReID heads.  aicam_engine_get_bias reads it back (host out).
+ * The bias of most layers is passed to the kernels as a launch argument: a change takes effect
+ * at the next launch and is NOT seen by CUDA graphs captured earlier. */
 int aicam_engine_set_bias(aicam_engine* e, const char* name, const float* host, int n);
 int aicam_engine_get_bias(aicam_engine* e, const char* name, float* host, int n);
 
