@@ -241,9 +241,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) conv_pair_kernel(const __grid
     for (int pt = pair; pt < pair_tiles; pt += npairs, ++it) {
       const int buf = it & 1;
       const int mt_i = pt / a.n_tiles, n0 = (pt - mt_i * a.n_tiles) * a.n_tile;
-      const long long p = (static_cast<long long>(mt_i) * 2 + rank) * TM + r;
-      const int rem = static_cast<int>(p % a.hw);
-      const int yy = rem / a.rw, xx = rem - yy * a.rw;
+      const uint32_t p = (static_cast<uint32_t>(mt_i) * 2 + rank) * TM + r;  // (< 2^31 padded pixels, checked on the host)
+      const uint32_t rem = p % static_cast<uint32_t>(a.hw);
+      const int yy = static_cast<int>(rem / static_cast<uint32_t>(a.rw)), xx = static_cast<int>(rem) - yy * a.rw;
       const bool zero_row = !(yy >= 1 && yy <= a.h && xx >= 1 && xx <= a.w);
       if (threadIdx.x == 0) PAIR_TRACE(it, 8);
       mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1);

@@ -395,9 +395,11 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
       bool stage_ok = false;
       bool zero_row = false;
       if (FLATWIN) {  // my raster position of this tile: border positions are stored as zeros (the border stays zero)
-        const long long p = static_cast<long long>(mt_idx) * TM + r;
-        const int rem = static_cast<int>(p % a.hw);
-        const int yy = rem / a.rw, xx = rem - yy * a.rw;
+        // (32-bit unsigned arithmetic: the host guarantees fewer than 2^31 padded pixels; the 64-bit modulo was 9 % of
+        //  the kernel's instructions)
+        const uint32_t p = static_cast<uint32_t>(mt_idx) * TM + r;
+        const uint32_t rem = p % static_cast<uint32_t>(a.hw);
+        const int yy = static_cast<int>(rem / static_cast<uint32_t>(a.rw)), xx = static_cast<int>(rem) - yy * a.rw;
         zero_row = !(yy >= 1 && yy <= a.h && xx >= 1 && xx <= a.w);
       }
       for (int g = g_lo; g < g_hi; g += 2) {
