@@ -190,25 +190,39 @@ __global__ void __launch_bounds__(THREADS, 1) reid_stem_pool_kernel(const StemAr
       }
       // the group's convolution tile is complete (and every thread of the group has finished pooling the previous one)
       asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(256) : "memory");
-      for (int i = gt; i < PH * PW * 8; i += 256) {
-        const int pp = i >> 3;
-        const int ppy = pp / PW, ppx = pp - ppy * PW;
+      // pooling: one item = TWO horizontally adjacent pooled pixels x 8 channels: their windows share a column, so 15
+      // shared-memory reads serve two outputs (9 each before), and the 24 pairs x 8 channel groups = 192 items fit the
+      // group's 256 threads in a single round
+      if (gt < PH * (PW / 2) * 8) {
+        const int pr = gt >> 3;
+        const int ppy = pr / (PW / 2), ppx = (pr - ppy * (PW / 2)) * 2;
         const int py = ty * PH + ppy, px = tx * PW + ppx;
         if (py < a.ph && px < a.pw) {
           const uint8_t* base = conv_s + static_cast<size_t>((2 * ppy) * RW + 2 * ppx) * PITCH + pg * 16;
-          uint4 m = *reinterpret_cast<const uint4*>(base);
+          uint4 c[5];  // column maxima of the 3 x 5 window
 #pragma unroll
-          for (int t = 1; t < 9; ++t) {
-            const uint4 u = *reinterpret_cast<const uint4*>(base + static_cast<size_t>((t / 3) * RW + (t % 3)) * PITCH);
-            m.x = hmax2(m.x, u.x); m.y = hmax2(m.y, u.y); m.z = hmax2(m.z, u.z); m.w = hmax2(m.w, u.w);
+          for (int dx = 0; dx < 5; ++dx) {
+            uint4 m = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(dx) * PITCH);
+#pragma unroll
+            for (int dy = 1; dy < 3; ++dy) {
+              const uint4 u = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(dy * RW + dx) * PITCH);
+              m.x = hmax2(m.x, u.x); m.y = hmax2(m.y, u.y); m.z = hmax2(m.z, u.z); m.w = hmax2(m.w, u.w);
+            }
+            c[dx] = m;
           }
-          const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-          uint32_t ow[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ow[k] = pack_bf16x2(fmaxf(bf16_lo(mw[k]) + pbias[2 * k], 0.0f), fmaxf(bf16_hi(mw[k]) + pbias[2 * k + 1], 0.0f));
-          *reinterpret_cast<uint4*>(a.out + ((static_cast<long long>(n) * (a.ph + 2 * a.out_pad) + py + a.out_pad) * (a.pw + 2 * a.out_pad) + px + a.out_pad) * COUT + pg * 8) =
-              make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          for (int o = 0; o < 2; ++o) {
+            if (px + o >= a.pw) break;
+            const uint4 m0 = c[2 * o], m1 = c[2 * o + 1], m2 = c[2 * o + 2];
+            const uint32_t mw[4] = {hmax2(hmax2(m0.x, m1.x), m2.x), hmax2(hmax2(m0.y, m1.y), m2.y), hmax2(hmax2(m0.z, m1.z), m2.z),
+                                    hmax2(hmax2(m0.w, m1.w), m2.w)};
+            uint32_t ow[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ow[k] = pack_bf16x2(fmaxf(bf16_lo(mw[k]) + pbias[2 * k], 0.0f), fmaxf(bf16_hi(mw[k]) + pbias[2 * k + 1], 0.0f));
+            *reinterpret_cast<uint4*>(a.out + ((static_cast<long long>(n) * (a.ph + 2 * a.out_pad) + py + a.out_pad) * (a.pw + 2 * a.out_pad) + px + o + a.out_pad) * COUT + pg * 8) =
+                make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
         }
       }
     }
