@@ -324,7 +324,7 @@ def main():
     # DRAM bytes of the same kernels for one step, from the committed ncu pass (profiles/r1_step_traffic.json)
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_step_traffic_v7.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_step_traffic_v8.json")) as f:
             traffic = json.load(f)
     except Exception:
         pass
