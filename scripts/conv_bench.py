@@ -31,6 +31,10 @@ SHAPES = [
     ("reid.l2 128->128 @32x16", 1024, 32, 16, 128, 128, 3, 1, 2, 2, 0),
     ("reid.l3 256->256 @16x8", 1024, 16, 8, 256, 256, 3, 1, 2, 2, 0),
     ("reid.l4 512->512 @8x4", 1024, 8, 4, 512, 512, 3, 1, 2, 2, 0),
+    ("reid.s2.l2 64->128 s2 @64x32", 1024, 64, 32, 64, 128, 3, 2, 2, 0, 0),
+    ("reid.s2.l3 128->256 s2 @32x16", 1024, 32, 16, 128, 256, 3, 2, 2, 0, 0),
+    ("reid.s2.l4 256->512 s2 @16x8", 1024, 16, 8, 256, 512, 3, 2, 2, 0, 0),
+    ("reid.ds.l2 1x1 64->128 s2 @64x32", 1024, 64, 32, 64, 128, 1, 2, 0, 0, 0),
 ]
 
 lib = _lib.load()
