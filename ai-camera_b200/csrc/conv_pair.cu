@@ -40,8 +40,7 @@ using namespace ptx;
 constexpr int NWG = 4;
 constexpr int PAIR_THREADS = (4 * NWG + 4) * 32;
 constexpr int MAX_RING = 8;
-constexpr uint32_t OFF_BIAS = 1024;
-constexpr uint32_t OFF_RING_A = 3072;  // (bias: up to 512 channels of fp32 behind OFF_BIAS)
+constexpr uint32_t OFF_RING_A = 1024;  // barriers and the TMEM pointer live below
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 constexpr uint32_t ROW_BYTES = 128;  // 64-channel slabs
 // (filter taps per streamed weight stage - one contiguous bulk copy - are a launch parameter: 3, or 1 for 256-column tiles)
@@ -59,7 +58,6 @@ struct PairArgs {
   int n_tile, n_half, cout, n_tiles, tps;
   const __nv_bfloat16* wgt_pair;  // [n-tile][rank][slab][tap][8 K chunks][n_half][8]: the order in which the MMAs consume it
   long long half_elems;           // elements of one rank's weights of one n-tile
-  const float* bias;
   int res_mode;
   int batch;
   const int* batch_dev;
@@ -618,7 +616,7 @@ int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t
   a.bstage_bytes = bstage; a.wbytes_half = static_cast<uint32_t>(wbytes_half);
   a.n_tile = n_tile; a.n_half = n_half; a.cout = pc.cout; a.n_tiles = n_tiles; a.tps = tps;
   a.wgt_pair = pc.w_pair; a.half_elems = static_cast<long long>(pc.q_pad) * n_half * 8;
-  a.bias = pc.bias; a.res_mode = res_mode;
+  a.res_mode = res_mode;
   if (!pc.bias_host) return 0;
   std::memcpy(a.bias4, pc.bias_host, sizeof(float) * cout_pad);
   a.batch = L.batch; a.batch_dev = L.batch_dev;
