@@ -41,6 +41,11 @@ class TrackerConfig(C.Structure):
                 ("nn_budget", C.c_int), ("device", C.c_int)]
 
 
+class TensorInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("dtype", C.c_int), ("ndim", C.c_int), ("shape", C.c_int * 4),
+                ("is_dynamic", C.c_int)]
+
+
 _P = C.c_void_p
 _I = C.c_int
 # name -> (restype, argtypes); every symbol include/aicam.h declares
@@ -58,6 +63,8 @@ SIGNATURES = {
     "aicam_engine_num_anchors": (_I, [_P]),
     "aicam_engine_flops_per_item": (C.c_double, [_P]),
     "aicam_engine_num_launches": (_I, [_P]),
+    "aicam_engine_io_count": (_I, [_P, _I]),
+    "aicam_engine_io_info": (_I, [_P, _I, _I, _I, C.POINTER(TensorInfo)]),
     "aicam_engine_set_bias": (_I, [_P, C.c_char_p, _P, _I]),
     "aicam_engine_get_bias": (_I, [_P, C.c_char_p, _P, _I]),
     "aicam_yolo_forward": (_I, [_P, _P, _I, _P, _P]),
@@ -85,6 +92,7 @@ SIGNATURES = {
     "aicam_tracker_destroy": (None, [_P]),
     "aicam_tracker_reset": (_I, [_P, _P]),
     "aicam_tracker_step": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "aicam_tracker_cost_probe": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "aicam_tracker_snapshot": (_I, [_P, _I, _P, _P, _I]),
     "aicam_tracker_overflow": (_I, [_P, _P]),
     "aicam_lsap": (_I, [_P, _I, _I, _I, _P, _P]),

@@ -1,5 +1,7 @@
 // Error state, version and launch accounting shared by every entry point of the C ABI.
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -16,6 +18,35 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static std::mutex g_attr_mutex;
+static std::map<std::pair<int, const void*>, size_t> g_smem_limit;  // (device, kernel) -> bytes opted in to
+static std::map<int, int> g_num_sms;
+
+int ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  int dev = 0;
+  AICAM_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  size_t& have = g_smem_limit[std::make_pair(dev, kernel)];
+  if (bytes > have) {
+    if (bytes > 48 * 1024)
+      AICAM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    have = bytes;
+  }
+  return AICAM_OK;
+}
+
+int current_num_sms() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  auto it = g_num_sms.find(dev);
+  if (it != g_num_sms.end()) return it->second;
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  g_num_sms[dev] = n;
+  return n;
+}
 
 // ---- per-launch event timing of the convolution kernel ------------------------------------
 static bool g_profile = false;

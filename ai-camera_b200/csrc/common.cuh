@@ -34,6 +34,15 @@ inline int last_launch(const char* what) {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device.  cudaFuncSetAttribute is per device and
+// overwrites the previous limit, so the library keeps a running maximum per (device, kernel) and only ever raises it:
+// a second engine / tracker (smaller, or on another GPU of the same process) never lowers or misses the opt-in.
+int ensure_dynamic_smem(const void* kernel, size_t bytes);
+template <typename Fn>
+inline int ensure_dynamic_smem(Fn* kernel, size_t bytes) { return ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), bytes); }
+// SM count of the current device (cached per device)
+int current_num_sms();
+
 // ---- device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -669,19 +669,8 @@ int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t
     fprintf(stderr, "conv_pair: %dx%d c%d->%d mt %d n_tile %d resident %d sa %d sb %d patch %u bstage %u nstage %d smem %zu\n", L.h, L.w,
             pc.cin_pad, pc.cout, mt, n_tile, a.resident, a.sa, a.sb, a.patch_bytes, a.bstage_bytes, a.nstage, smem);
   PairKernelFn kernel = tps == 1 ? pick_pair<1, 1>(L.act) : (mt == 2 ? pick_pair<2, 3>(L.act) : pick_pair<1, 3>(L.act));
-  {
-    static std::vector<PairKernelFn> configured;
-    if (std::find(configured.begin(), configured.end(), kernel) == configured.end()) {
-      AICAM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM_LIMIT)));
-      configured.push_back(kernel);
-    }
-  }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    AICAM_CUDA_OK(cudaGetDevice(&dev));
-    AICAM_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  if (int rc = ensure_dynamic_smem(kernel, SMEM_LIMIT)) return rc;  // per (device, instantiation)
+  const int num_sms = current_num_sms();
   const long long pair_tiles = (padded_pixels + 2 * tm - 1) / (2 * tm) * n_tiles;
   const unsigned pairs = static_cast<unsigned>(std::min<long long>(pair_tiles, num_sms / 2));
   cudaLaunchConfig_t cfg = {};

@@ -812,18 +812,9 @@ int launch_conv(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream) 
   if (a.staged && 128 * (a.n_tile * (L.out_f32 ? 4 : 2) + 16) > static_cast<long long>(STAGES * a_stage)) a.staged = 0;
   size_t smem = SMEM_HEADER + STAGES * (a_stage + static_cast<size_t>(a.n_tile) * 16 * CHUNKS_PER_STAGE);
   a.res_stage_off = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AICAM_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
+  if (int rc = ensure_dynamic_smem(conv_tc_kernel, 160 * 1024)) return rc;
   // persistent CTAs: at most 3 resident per SM (registers / shared memory), each loops over tiles
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    AICAM_CUDA_OK(cudaGetDevice(&dev));
-    AICAM_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = current_num_sms();
   const long long tiles = static_cast<long long>(cdiv(a.m_total, TILE_M)) * (a.cout_pad / a.n_tile);
   const int per_sm = static_cast<int>(std::min<size_t>(3, (227 * 1024) / (smem + 1024)));
   dim3 grid(static_cast<unsigned>(std::min<long long>(tiles, static_cast<long long>(num_sms) * std::max(1, per_sm))));

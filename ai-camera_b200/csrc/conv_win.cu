@@ -1383,19 +1383,8 @@ plan:
             "epi %d direct %d tiles %lld smem %zu\n", L.h, L.w, pc.cin_pad, pc.cout, pc.ksize, pc.stride, mode, best.mt, n_tile, n_tiles,
             slab, slabs, resident ? 1 : 0, a.sa, a.sb, a.patch_bytes, a.bstage_bytes, epi ? 1 : 0, a.direct_out, best.tiles * n_tiles, smem);
   WinKernelFn kernel = pick_kernel(slab, mode, best.mt, L.act, epi ? 1 : 0);
-  {
-    static std::vector<WinKernelFn> configured;  // opt in to > 48 KB of dynamic shared memory once per instantiation
-    if (std::find(configured.begin(), configured.end(), kernel) == configured.end()) {
-      AICAM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM_LIMIT)));
-      configured.push_back(kernel);
-    }
-  }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    AICAM_CUDA_OK(cudaGetDevice(&dev));
-    AICAM_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  if (int rc = ensure_dynamic_smem(kernel, SMEM_LIMIT)) return rc;  // per (device, instantiation)
+  const int num_sms = current_num_sms();
   const long long total_tiles = best.tiles * n_tiles;
   dim3 grid(static_cast<unsigned>(std::min<long long>(total_tiles, num_sms)));
   size_t slot = 0;

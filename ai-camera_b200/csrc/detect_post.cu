@@ -276,11 +276,7 @@ int launch_nms(const float* boxes, const float* scores, const int* labels, int b
   a.frame_w = static_cast<float>(p->frame_w); a.frame_h = static_cast<float>(p->frame_h);
   a.num_dets = num_dets; a.boxes_lb = boxes_lb; a.boxes_orig = (p->frame_h > 0 && p->frame_w > 0) ? boxes_orig : nullptr;
   a.out_scores = out_scores; a.out_labels = out_labels; a.keep_index = keep_index; a.mask_ws = mask_ws;
-  static bool attr = false;
-  if (!attr) {
-    AICAM_CUDA_OK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(NMS_SMEM)));
-    attr = true;
-  }
+  if (int rc = ensure_dynamic_smem(nms_kernel, NMS_SMEM)) return rc;
   nms_kernel<<<batch, NMS_THREADS, NMS_SMEM, stream>>>(a);
   count_launch();
   return last_launch("nms_kernel");

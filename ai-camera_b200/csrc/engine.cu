@@ -501,7 +501,7 @@ int aicam_engine_create(const char* blob_path, int device, int max_batch, aicam_
   std::memcpy(head, raw.data() + 8, sizeof(head));
   const uint32_t kind = head[0], n_tensors = head[9];
   const size_t entry = 64 + 4 + 16 + 8 + 8;
-  if (48 + n_tensors * entry > size) return fail(AICAM_ERR_IO, "engine_create: truncated blob header");
+  if (n_tensors > (size - 48) / entry) return fail(AICAM_ERR_IO, "engine_create: truncated blob header");
   std::map<std::string, BlobTensor> tensors;
   for (uint32_t i = 0; i < n_tensors; ++i) {
     const char* p = raw.data() + 48 + i * entry;
@@ -513,11 +513,21 @@ int aicam_engine_create(const char* blob_path, int device, int max_batch, aicam_
     std::memcpy(dims, p + 68, 16);
     std::memcpy(&off, p + 84, 8);
     std::memcpy(&nbytes, p + 92, 8);
-    if (off + nbytes > size || nd > 4) return fail(AICAM_ERR_IO, "engine_create: corrupt tensor entry");
+    // (written so that nothing can wrap: off and nbytes are untrusted 64-bit values)
+    if (nd > 4 || off > size || nbytes > size - off || off % 4 != 0 || nbytes % 4 != 0)
+      return fail(AICAM_ERR_IO, "engine_create: corrupt tensor entry");
     BlobTensor t;
-    for (uint32_t d = 0; d < nd; ++d) t.dims.push_back(static_cast<int>(dims[d]));
+    uint64_t prod = 1;
+    for (uint32_t d = 0; d < nd; ++d) {
+      if (dims[d] == 0 || dims[d] > (1u << 24)) return fail(AICAM_ERR_IO, "engine_create: corrupt tensor dimensions");
+      t.dims.push_back(static_cast<int>(dims[d]));
+      prod *= dims[d];
+      if (prod > (1ull << 32)) return fail(AICAM_ERR_IO, "engine_create: corrupt tensor dimensions");
+    }
     t.data = reinterpret_cast<const float*>(raw.data() + off);
     t.count = nbytes / 4;
+    // every tensor must hold exactly prod(dims) floats: the packers index it by its dims
+    if (t.count != prod) return fail(AICAM_ERR_IO, "engine_create: tensor byte count differs from its dimensions");
     tensors[name] = t;
   }
   AICAM_CUDA_OK(cudaSetDevice(device));
@@ -585,6 +595,37 @@ int aicam_engine_num_launches(const aicam_engine* e) {
   int n = 0;
   for (const auto& op : e->ops) n += op.type == aicam::Op::STEMPOOL ? 2 : 1;  // NHWC8 repack + fused stem (upper bound)
   return n;
+}
+
+int aicam_engine_io_count(const aicam_engine* e, int is_output) {
+  if (!e) return 0;
+  if (e->kind == AICAM_KIND_YOLOV8) return is_output ? 4 : 1;
+  return 1;
+}
+
+int aicam_engine_io_info(const aicam_engine* e, int is_output, int index, int topk, aicam_tensor_info* info) {
+  if (!e || !info || index < 0 || index >= aicam_engine_io_count(e, is_output))
+    return fail(AICAM_ERR_INVALID_ARG, "engine_io_info: bad arguments");
+  std::memset(info, 0, sizeof(*info));
+  auto set = [&](const char* name, int dtype, int ndim, int d0, int d1, int d2, int d3, int dyn) {
+    std::strncpy(info->name, name, sizeof(info->name) - 1);
+    info->dtype = dtype; info->ndim = ndim; info->is_dynamic = dyn;
+    info->shape[0] = d0; info->shape[1] = d1; info->shape[2] = d2; info->shape[3] = d3;
+  };
+  if (e->kind == AICAM_KIND_YOLOV8) {
+    // the reference engine: `images` 1x3x640x640 (scripts/export_trt_engines.sh:25-28) and the four outputs of its
+    // embedded NMS (src/detector/yolo_detector.py:49-54)
+    if (!is_output) set("images", AICAM_DTYPE_F32, 4, 1, 3, e->in_h, e->in_w, 0);
+    else if (index == 0) set("num_dets", AICAM_DTYPE_I32, 2, 1, 1, 0, 0, 0);
+    else if (index == 1) set("bboxes", AICAM_DTYPE_F32, 3, 1, topk, 4, 0, 0);
+    else if (index == 2) set("scores", AICAM_DTYPE_F32, 2, 1, topk, 0, 0, 0);
+    else set("labels", AICAM_DTYPE_I32, 2, 1, topk, 0, 0, 0);
+  } else {
+    // `input` Nx3x128x64, dynamic batch (export_trt_engines.sh:31-34); one (N, feature_dim) output (reid_model.py:46)
+    if (!is_output) set("input", AICAM_DTYPE_F32, 4, -1, 3, e->in_h, e->in_w, 1);
+    else set("output", AICAM_DTYPE_F32, 2, -1, e->out_cstride, 0, 0, 1);
+  }
+  return AICAM_OK;
 }
 
 int aicam_engine_set_bias(aicam_engine* e, const char* name, const float* host, int n) {

@@ -214,11 +214,7 @@ int try_launch_sppf_pool3(__nv_bfloat16* buf, long long img_stride, int cstride,
                           cudaStream_t stream, const int* n_dev) {
   const size_t smem = static_cast<size_t>(3) * h * w * 64;
   if (hc % 32 || cstride % 8 || coff % 8 || smem > 200 * 1024 || batch <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(sppf_pool3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 0;
-    configured = true;
-  }
+  if (ensure_dynamic_smem(sppf_pool3_kernel, 200 * 1024) != AICAM_OK) return 0;
   sppf_pool3_kernel<<<static_cast<unsigned>(batch * (hc / 32)), 256, smem, stream>>>(buf, img_stride, cstride, coff, h, w, hc, n_dev);
   count_launch();
   const int rc = last_launch("sppf_pool3_kernel");

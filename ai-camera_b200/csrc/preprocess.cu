@@ -313,9 +313,9 @@ int aicam_preprocess(const uint8_t* frames, int batch, int h, int w, int format,
     const unsigned rows = static_cast<unsigned>(batch) * S;
     const size_t smem = static_cast<size_t>(w) * 3;
     if (smem > 48 * 1024) {
-      AICAM_CUDA_OK(cudaFuncSetAttribute(preprocess_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      AICAM_CUDA_OK(cudaFuncSetAttribute(preprocess_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      AICAM_CUDA_OK(cudaFuncSetAttribute(preprocess_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      if (int rc = ensure_dynamic_smem(format == 0 ? preprocess_rows_kernel<0> : (format == 1 ? preprocess_rows_kernel<1> : preprocess_rows_kernel<2>),
+                                       96 * 1024))
+        return rc;
     }
     if (format == 0)
       preprocess_rows_kernel<0><<<rows, S / PIX, smem, st>>>(frames, h, w, g.new_h, g.new_w, g.top, g.left, g.tab, out);

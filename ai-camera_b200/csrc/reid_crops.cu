@@ -106,7 +106,12 @@ __global__ void __launch_bounds__(1024) filter_kernel(const float* __restrict__ 
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *crop_count = min(s_base, max_crops);
+  if (threadIdx.x == 0) {
+    crop_count[0] = min(s_base, max_crops);
+    // high-water mark of the crops WANTED (un-clamped): > max_crops means detections lost their feature to the
+    // capacity (the reference always extracts one); sticky until the caller zeroes it
+    if (s_base > crop_count[1]) crop_count[1] = s_base;
+  }
 }
 
 // cv2 linear-resize tables for one axis, one entry per thread

@@ -385,17 +385,8 @@ int launch_stem_pool(const StemPool& sp, const __nv_bfloat16* in_nhwc8, int batc
                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(AICAM_ERR_CUDA, "stem_pool: cuTensorMapEncodeTiled failed with " + std::to_string(static_cast<int>(cr)));
-  static bool attr_set = false;
-  if (!attr_set) {
-    AICAM_CUDA_OK(cudaFuncSetAttribute(reid_stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM_BYTES)));
-    attr_set = true;
-  }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    AICAM_CUDA_OK(cudaGetDevice(&dev));
-    AICAM_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  if (int rc = ensure_dynamic_smem(reid_stem_pool_kernel, SMEM_BYTES)) return rc;
+  const int num_sms = current_num_sms();
   const long long tiles = static_cast<long long>(batch) * a.tiles_y * a.tiles_x;
   dim3 grid(static_cast<unsigned>(std::min<long long>(tiles, num_sms)));
   size_t slot = 0;

@@ -448,6 +448,8 @@ struct StepIO {
   const int* det_index; const int* det_count; const int* crop_slot;
   int* out_tracks; float* out_conf; int* out_count;
   int cm_in_smem;  // the T x D cost matrix fits in shared memory (else the per-stream global workspace)
+  int has_feats;   // 0: the frame carries no features at all (feats == NULL): every appearance cost is INFTY_COST and
+                   // nothing is appended to the galleries, as in the reference when every Detection.feature is None
 };
 
 // K7 + K9-K12: predict, cascade, IoU stage, update, initiate, prune, output.  One CTA per stream.
@@ -540,7 +542,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
       const int d = U[j];
       float c;
       if (metric == 0) {
-        c = t.app_cost[ts * Dm + d];
+        c = io.has_feats ? t.app_cost[ts * Dm + d] : INFTY_COST;
         // linear_assignment.py:160-212: gate by the squared Mahalanobis distance (4 dof, strict >)
         const float g = kf_gating(t.mean + ts * 8, t.cov + ts * 16, d_xyah + 4 * d, nU);
         if (g > CHI2_GATE) c = INFTY_COST;
@@ -603,7 +605,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
     const long long ts = sb + ord[k];
     const int d = match[k];
     if (d >= 0) {
-      const int row = io.crop_slot[static_cast<long long>(s) * io.stride_k + d];
+      const int row = io.has_feats ? io.crop_slot[static_cast<long long>(s) * io.stride_k + d] : -1;
       if (row >= 0) {  // track.py:70-74: append to the gallery, FIFO at the budget
         const int cnt = t.gal_count[ts], head = t.gal_head[ts];
         const int pos = cnt < t.G ? (head + cnt) % t.G : head;
@@ -677,7 +679,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
   for (int j = warp; j < s_nL; j += ASSOC_THREADS / 32) {
     const int d = U[j];
     const long long ts = sb + Utmp[j];
-    const int row = io.crop_slot[static_cast<long long>(s) * io.stride_k + d];
+    const int row = io.has_feats ? io.crop_slot[static_cast<long long>(s) * io.stride_k + d] : -1;
     if (row >= 0) {
       float* dst = t.gallery + ts * t.G * t.F;
       const float* src = t.featn + (static_cast<long long>(s) * Dm + d) * t.F;
@@ -749,6 +751,38 @@ __global__ void gating_kernel(const float* state, const float* meas, int n, int 
                       meas + static_cast<long long>(idx) * 4, m);
 }
 
+// Parity probe of K8 / K9 (no tracker state is changed): for every live track of every stream, in track-list order,
+// the raw appearance cost (appearance_kernel's output: min over the gallery of the clamped cosine distance,
+// INFTY_COST for tentative tracks / missing features) and the squared Mahalanobis distance of every filtered
+// detection to the track's PREDICTED state (kf_predict applied to a copy) - what linear_assignment.py:160-212 gates
+// with.  One block per (track position, stream).
+__global__ void __launch_bounds__(128) cost_probe_kernel(Dev t, const float* __restrict__ boxes, int stride_k,
+                                                         const int* __restrict__ det_index, const int* __restrict__ det_count,
+                                                         float* __restrict__ app_cost, float* __restrict__ gate_d2,
+                                                         int* __restrict__ track_ids, int* __restrict__ n_tracks) {
+  const int s = blockIdx.y, k = blockIdx.x;
+  const int nt = t.n_tracks[s];
+  if (k == 0 && threadIdx.x == 0) n_tracks[s] = nt;
+  if (k >= nt) return;
+  const long long sb = static_cast<long long>(s) * t.T;
+  const long long ts = sb + t.order[sb + k];
+  float mean[8], cov[16];
+  for (int i = 0; i < 8; ++i) mean[i] = t.mean[ts * 8 + i];
+  for (int i = 0; i < 16; ++i) cov[i] = t.cov[ts * 16 + i];
+  kf_predict(mean, cov);
+  const int nd = min(det_count[s], t.D);
+  const bool confirmed = t.state[ts] == CONFIRMED;
+  if (threadIdx.x == 0) track_ids[sb + k] = t.track_id[ts];
+  for (int d = threadIdx.x; d < nd; d += blockDim.x) {
+    const long long o = static_cast<long long>(s) * stride_k + det_index[static_cast<long long>(s) * stride_k + d];
+    const float4 b = reinterpret_cast<const float4*>(boxes)[o];
+    float tl[4] = {b.x, b.y, b.z - b.x, b.w - b.y}, z[4];
+    tlwh_to_xyah(tl, z);
+    app_cost[(sb + k) * t.D + d] = confirmed ? t.app_cost[ts * t.D + d] : INFTY_COST;
+    gate_d2[(sb + k) * t.D + d] = kf_gating(mean, cov, z, nd);
+  }
+}
+
 constexpr size_t CM_SMEM_LIMIT = 96 * 1024;  // cost matrices up to this size live in shared memory
 size_t assoc_smem(int T, int D, int* cm_in_smem = nullptr) {
   const size_t base = sizeof(float) * 8 * D + sizeof(int) * (3 * D + 8 * T) + 16 + lsap_bytes(std::max(T, D));
@@ -778,6 +812,22 @@ int dev_alloc(aicam_tracker* t, Tp** p, size_t n) {
   t->allocs.push_back(q);
   *p = static_cast<Tp*>(q);
   return AICAM_OK;
+}
+}  // namespace
+
+namespace {
+// K8: L2-normalise the frame's detection features, then the appearance cost of every confirmed track
+int launch_appearance(const Dev& d, const int32_t* det_count, const int32_t* crop_slot, int stride_k, const float* feats, cudaStream_t st) {
+  normalize_kernel<<<dim3(d.D, d.S), 128, 0, st>>>(d, det_count, crop_slot, stride_k, feats);
+  count_launch();
+  if (int rc = last_launch("normalize_kernel")) return rc;
+  static const bool no_gemm = getenv("AICAM_APPEARANCE_ROWS") != nullptr;
+  const int gemm_ok = (d.F % AG_KC == 0 && !no_gemm) ? 1 : 0;
+  const size_t sm = std::max((APP_DT * d.F + 8 * APP_DT) * sizeof(float), gemm_ok ? AG_SMEM : size_t(0));
+  if (int rc = ensure_dynamic_smem(appearance_kernel, sm)) return rc;
+  appearance_kernel<<<dim3(d.T, d.S), 256, sm, st>>>(d, det_count, crop_slot, stride_k, gemm_ok);
+  count_launch();
+  return last_launch("appearance_kernel");
 }
 }  // namespace
 
@@ -819,9 +869,8 @@ int aicam_tracker_create(const aicam_tracker_config* cfg, aicam_tracker** out) {
   if (rc) { aicam_tracker_destroy(t); return AICAM_ERR_CUDA; }
   const size_t sm = assoc_smem(d.T, d.D);
   if (sm > 200 * 1024) { aicam_tracker_destroy(t); return fail(AICAM_ERR_CAPACITY, "tracker_create: max_tracks/max_dets need too much shared memory"); }
-  cudaFuncSetAttribute(assoc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
-  cudaFuncSetAttribute(appearance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       static_cast<int>(std::max((APP_DT * d.F + 8 * APP_DT) * sizeof(float), AG_SMEM)));
+  // (the > 48 KB opt-ins are made per launch in aicam_tracker_step: a running maximum per device, so that trackers of
+  //  different sizes - or on different GPUs - never lower each other's limit)
   if (int r2 = aicam_tracker_reset(t, nullptr)) { aicam_tracker_destroy(t); return r2; }
   AICAM_CUDA_OK(cudaDeviceSynchronize());
   *out = t;
@@ -852,21 +901,29 @@ int aicam_tracker_step(aicam_tracker* t, const float* boxes, const float* scores
   const Dev& d = t->d;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (feats) {
-    normalize_kernel<<<dim3(d.D, d.S), 128, 0, st>>>(d, det_count, crop_slot, stride_k, feats);
-    count_launch();
-    if (int rc = last_launch("normalize_kernel")) return rc;
-    static const bool no_gemm = getenv("AICAM_APPEARANCE_ROWS") != nullptr;
-    const int gemm_ok = (d.F % AG_KC == 0 && !no_gemm) ? 1 : 0;
-    const size_t sm = std::max((APP_DT * d.F + 8 * APP_DT) * sizeof(float), gemm_ok ? AG_SMEM : size_t(0));
-    appearance_kernel<<<dim3(d.T, d.S), 256, sm, st>>>(d, det_count, crop_slot, stride_k, gemm_ok);
-    count_launch();
-    if (int rc = last_launch("appearance_kernel")) return rc;
+    if (int rc = launch_appearance(d, det_count, crop_slot, stride_k, feats, st)) return rc;
   }
-  StepIO io{boxes, scores, labels, stride_k, det_index, det_count, crop_slot, out_tracks, out_conf, out_count, 0};
+  StepIO io{boxes, scores, labels, stride_k, det_index, det_count, crop_slot, out_tracks, out_conf, out_count, 0, feats ? 1 : 0};
   const size_t asm_bytes = assoc_smem(d.T, d.D, &io.cm_in_smem);
+  if (int rc = ensure_dynamic_smem(assoc_kernel, asm_bytes)) return rc;
   assoc_kernel<<<d.S, ASSOC_THREADS, asm_bytes, st>>>(d, io);
   count_launch();
   return last_launch("assoc_kernel");
+}
+
+int aicam_tracker_cost_probe(aicam_tracker* t, const float* boxes, int stride_k, const int32_t* det_index,
+                             const int32_t* det_count, const int32_t* crop_slot, const float* feats, float* app_cost,
+                             float* gate_d2, int32_t* track_ids, int32_t* n_tracks, void* stream) {
+  if (!t || !boxes || !det_index || !det_count || !crop_slot || !feats || !app_cost || !gate_d2 || !track_ids || !n_tracks)
+    return fail(AICAM_ERR_INVALID_ARG, "tracker_cost_probe: null argument");
+  if (stride_k <= 0 || reinterpret_cast<uintptr_t>(boxes) % 16)
+    return fail(AICAM_ERR_INVALID_ARG, "tracker_cost_probe: stride_k must be positive and boxes 16-byte aligned");
+  const Dev& d = t->d;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = launch_appearance(d, det_count, crop_slot, stride_k, feats, st)) return rc;
+  cost_probe_kernel<<<dim3(d.T, d.S), 128, 0, st>>>(d, boxes, stride_k, det_index, det_count, app_cost, gate_d2, track_ids, n_tracks);
+  count_launch();
+  return last_launch("cost_probe_kernel");
 }
 
 int aicam_tracker_snapshot(aicam_tracker* t, int stream_index, int32_t* ints, float* floats, int capacity) {
@@ -918,7 +975,7 @@ int aicam_lsap(const float* cost, int count, int nr, int nc, int32_t* col_for_ro
     return fail(AICAM_ERR_INVALID_ARG, "lsap: bad arguments (sizes are limited to 1024)");
   if (count == 0) return AICAM_OK;
   const size_t sm = lsap_bytes(std::max(nr, nc)) + sizeof(int) * nr + 16;
-  cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+  if (int rc = ensure_dynamic_smem(lsap_kernel, sm)) return rc;
   lsap_kernel<<<count, 32, sm, static_cast<cudaStream_t>(stream)>>>(cost, nr, nc, col_for_row);
   count_launch();
   return last_launch("lsap_kernel");

@@ -95,7 +95,7 @@ class BatchTracker:
         self.det_count = torch.zeros(S, **i32)
         self.crop_slot = torch.zeros((S, K), **i32)
         self.crop_rect = torch.zeros((self.max_crops, 5), **i32)
-        self.crop_count = torch.zeros(1, **i32)
+        self.crop_count = torch.zeros(2, **i32)  # [crops written, high-water mark of crops wanted]
         # crops go straight into the layout the engine's first kernel reads (NHWC8 for the fused stem)
         self._nhwc8 = bool(self.lib.aicam_engine_accepts_nhwc8(self.reid.handle))
         self.crops = torch.zeros((self.max_crops, config.REID_INPUT_SHAPE[0], config.REID_INPUT_SHAPE[1],
@@ -119,6 +119,7 @@ class BatchTracker:
 
     def reset(self):
         _lib.check(self.lib.aicam_tracker_reset(self._h, _lib.stream_ptr(self.device)))
+        self.crop_count.zero_()
 
     def update(self, frames, num_dets, boxes, scores, labels):
         """One frame per stream.  frames uint8 cuda [S,H,W,3]; detections as BatchDetector returns
@@ -143,7 +144,7 @@ class BatchTracker:
                 _lib.ptr(self.det_count), _lib.ptr(self.crop_slot), _lib.ptr(self.feats), _lib.ptr(self.out_tracks),
                 _lib.ptr(self.out_conf), _lib.ptr(self.out_count), st))
             if self.count_stats:
-                self.crop_total += self.crop_count
+                self.crop_total += self.crop_count[0:1]
                 self.track_total += self.out_count.sum()
         return self.out_tracks, self.out_conf, self.out_count
 
@@ -151,6 +152,9 @@ class BatchTracker:
         import numpy as np
         f = np.zeros(self.S, np.int32)
         _lib.check(self.lib.aicam_tracker_overflow(self._h, _lib.ptr(f)))
+        # bit 2 (every stream): some step wanted more ReID crops than max_crops, so detections lost their feature
+        if int(self.crop_count[1].item()) > self.max_crops:
+            f |= 4
         return f
 
     def snapshot(self, stream_index=0):
@@ -170,8 +174,11 @@ class TrackingPipeline:
     """detect + track for ``n_streams`` streams of one frame size; one call per time step."""
 
     def __init__(self, yolo_engine_path, reid_engine_path, n_streams: int, device=None, max_tracks: int = 256,
-                 max_crops: Optional[int] = None, **tracker_kw):
-        self.detector = BatchDetector(yolo_engine_path, n_streams, device)
+                 max_crops: Optional[int] = None, conf_threshold=config.YOLO_CONF_THRESHOLD, **tracker_kw):
+        self.detector = BatchDetector(yolo_engine_path, n_streams, device, conf_threshold=conf_threshold)
+        # detect() drops detections below conf_threshold before update() sees them (yolo_detector.py:131); on the
+        # device that filter and DeepSORT's own (deepsort_tracker.py:88-95) are one comparison
+        tracker_kw.setdefault("min_detection_confidence", max(config.DEEPSORT_MIN_CONFIDENCE, conf_threshold))
         self.tracker = BatchTracker(reid_engine_path, n_streams, self.detector.device, max_dets=self.detector.topk,
                                     max_tracks=max_tracks, max_crops=max_crops, **tracker_kw)
         self.device = self.detector.device

@@ -79,7 +79,7 @@ class ReIDModel:
         ld = torch.zeros((1, n), **i32)
         nd = torch.full((1,), n, **i32)
         det_index, det_count, crop_slot = torch.zeros((1, n), **i32), torch.zeros(1, **i32), torch.zeros((1, n), **i32)
-        crop_rect, crop_count = torch.zeros((n, 5), **i32), torch.zeros(1, **i32)
+        crop_rect, crop_count = torch.zeros((n, 5), **i32), torch.zeros(2, **i32)
         x = torch.empty((n, self.input_shape[0], self.input_shape[1], 4), dtype=torch.bfloat16, device=dev)
         feats = torch.empty((n, self.feature_dim), dtype=torch.float32, device=dev)
         st = _lib.stream_ptr(dev)

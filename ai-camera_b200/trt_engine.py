@@ -55,12 +55,8 @@ class TRTEngine(torch.nn.Module):
             self.nc = self._lib.aicam_engine_num_classes(self._h)
             self.anchors = self._lib.aicam_engine_num_anchors(self._h)
             h, w = config.YOLO_INPUT_SHAPE
-            self.input_info_list: List[TensorInfo] = [TensorInfo('images', torch.float32, (1, 3, h, w), False)]
-            self.output_info_list: List[TensorInfo] = [
-                TensorInfo('num_dets', torch.int32, (1, 1), False),
-                TensorInfo('bboxes', torch.float32, (1, self.topk, 4), False),
-                TensorInfo('scores', torch.float32, (1, self.topk), False),
-                TensorInfo('labels', torch.int32, (1, self.topk), False)]
+            self.input_info_list: List[TensorInfo] = self._bindings(0)
+            self.output_info_list: List[TensorInfo] = self._bindings(1)
             self._nms = _lib.NmsParams(self.score_threshold, self.nms_threshold, self.topk, self.max_candidates, 0, 0)
             ws = self._lib.aicam_decode_nms_workspace(self.max_batch, self.anchors, C.byref(self._nms))
             self._ws = torch.empty(ws, dtype=torch.uint8, device=self.device)
@@ -69,9 +65,19 @@ class TRTEngine(torch.nn.Module):
         else:
             self.feature_dim = self._lib.aicam_engine_num_classes(self._h)
             h, w = config.REID_INPUT_SHAPE
-            self.input_info_list = [TensorInfo('input', torch.float32, (-1, 3, h, w), True)]
-            self.output_info_list = [TensorInfo('output', torch.float32, (-1, self.feature_dim), True)]
+            self.input_info_list = self._bindings(0)
+            self.output_info_list = self._bindings(1)
             self._nhwc = torch.empty((self.max_batch, h, w, 4), dtype=torch.bfloat16, device=self.device)
+
+    def _bindings(self, is_output: int) -> List[TensorInfo]:
+        """trt_engine.py:62-91 walks the engine's bindings; here the library reports them."""
+        out = []
+        for i in range(self._lib.aicam_engine_io_count(self._h, is_output)):
+            ti = _lib.TensorInfo()
+            _lib.check(self._lib.aicam_engine_io_info(self._h, is_output, i, self.topk, C.byref(ti)))
+            dt = torch.float32 if ti.dtype == 0 else torch.int32
+            out.append(TensorInfo(ti.name.decode(), dt, tuple(ti.shape[:ti.ndim]), bool(ti.is_dynamic)))
+        return out
 
     def __del__(self):
         try:

@@ -40,6 +40,9 @@ class YOLODetector:
         self._pack = torch.empty(1 + 6 * k, dtype=torch.int32, device=self.device)
         self._frame_dev = None
         self._frame_host = None
+        # the frame of the last detect() call as it lies in HBM (uint8 [1, H, W, 3]): DeepSORT.update accepts it in
+        # place of the numpy frame, so a detect -> update pair uploads the frame once
+        self.device_frame = None
         print(f"YOLODetector initialized with engine: {engine_path}")
         print(f"  Input name: {self.input_name}, Input shape: {self.input_shape}")
 
@@ -50,6 +53,7 @@ class YOLODetector:
             self._frame_dev = torch.empty((1,) + shape, dtype=torch.uint8, device=self.device)
         self._frame_host[0].numpy()[...] = frame_bgr
         self._frame_dev.copy_(self._frame_host, non_blocking=True)
+        self.device_frame = self._frame_dev
         return self._frame_dev
 
     def detect(self, frame_bgr: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:

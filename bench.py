@@ -314,7 +314,7 @@ def main():
     prof_crops = 0.0
     for _ in range(prof_steps):
         one_step()
-        prof_crops += float(pipe.tracker.crop_count.item())  # this step's crops (host sync: profiling pass only)
+        prof_crops += float(pipe.tracker.crop_count[0].item())  # this step's crops (host sync: profiling pass only)
     prof_crops /= prof_steps
     ms = _lib.C.c_double()
     nl = _lib.C.c_uint64()

@@ -56,8 +56,9 @@ int aicam_profile_conv(double* total_ms, uint64_t* launches);
 /* ------------------------------------------------------------------------------------------
  * Engine: replaces TRTEngine (src/trt_utils/trt_engine.py:15-216): __init__/_init_engine
  * (deserialize_cuda_engine, :45-60) -> aicam_engine_create on a flat ".aicw" weight blob;
- * get_input_details/get_output_details (:212-216) -> aicam_engine_io_*; infer (:151-203) ->
- * aicam_engine_infer.
+ * get_input_details/get_output_details (:212-216) -> aicam_engine_io_count / aicam_engine_io_info;
+ * infer (:151-203) -> aicam_nchw_to_nhwc4 + aicam_yolo_forward + aicam_decode_nms for the detector
+ * engine (whose ONNX embeds the NMS), aicam_nchw_to_nhwc4 + aicam_reid_forward for the ReID engine.
  * ---------------------------------------------------------------------------------------- */
 int aicam_engine_create(const char* blob_path, int device, int max_batch, aicam_engine** out);
 void aicam_engine_destroy(aicam_engine* e);
@@ -67,6 +68,20 @@ int aicam_engine_num_classes(const aicam_engine* e); /* yolov8: nc; reid: featur
 int aicam_engine_num_anchors(const aicam_engine* e); /* yolov8: 8400 at 640x640 */
 double aicam_engine_flops_per_item(const aicam_engine* e); /* 2*MACs per frame / per crop */
 int aicam_engine_num_launches(const aicam_engine* e);      /* kernels per forward */
+/* The engine's bindings as TRTEngine.get_input_details / get_output_details report them
+ * (TensorInfo(name, dtype, shape, is_dynamic), trt_engine.py:11,212-216).  topk: the K the caller
+ * runs aicam_decode_nms with (the detector's post-NMS outputs are [1][K]...); -1 in shape = dynamic. */
+#define AICAM_DTYPE_F32 0
+#define AICAM_DTYPE_I32 1
+typedef struct {
+  char name[32];
+  int dtype;      /* AICAM_DTYPE_* */
+  int ndim;
+  int shape[4];
+  int is_dynamic;
+} aicam_tensor_info;
+int aicam_engine_io_count(const aicam_engine* e, int is_output);
+int aicam_engine_io_info(const aicam_engine* e, int is_output, int index, int topk, aicam_tensor_info* info);
 /* Overwrite a bias vector by blob tensor name (host float32 in); used to calibrate the
  * synthetic detector/ReID heads.  aicam_engine_get_bias reads it back (host out).
  * The bias of most layers is passed to the kernels as a launch argument: a change takes effect
@@ -166,7 +181,7 @@ typedef struct {
   float score_thr;   /* src/config.py:17 */
   float iou_thr;     /* src/config.py:18 */
   int topk;          /* <= 1024 */
-  int max_candidates;/* <= 4096, pre-NMS candidates kept per frame */
+  int max_candidates;/* multiple of 32 in 32..2048: pre-NMS candidates kept per frame */
   int frame_h, frame_w; /* for boxes_orig */
 } aicam_nms_params;
 int aicam_decode_nms(const float* head, int batch, int anchors, int nc, const aicam_nms_params* p,
@@ -196,8 +211,10 @@ int aicam_nms(const float* boxes, const float* scores, const int32_t* labels, in
  *               format 1: bf16 [max_crops][128][64][4]
  *               format 2: bf16 [max_crops][128][64][8] (what aicam_reid_forward_nhwc8 consumes)
  *   crop_rect : i32 [max_crops][5] out: frame index, x1, y1, x2, y2 (int()-truncated, clamped)
- *   crop_count: i32 [1] total crops written (<= max_crops; crops beyond capacity are dropped
- *               and their crop_slot is -1)
+ *   crop_count: i32 [2]: [0] = crops written this call (<= max_crops; crops beyond the capacity are
+ *               dropped and their crop_slot is -1); [1] = high-water mark of the crops WANTED
+ *               (un-clamped) since the caller last zeroed it: [1] > max_crops means some detection
+ *               lost its feature to the capacity, which the reference never does
  * class_mask_lo/hi: bit c set = COCO class c is tracked (src/config.py:53 -> ids 0,2,3,5,7). */
 int aicam_reid_crops(const uint8_t* frames, int batch, int h, int w, const float* boxes,
                      const float* scores, const int32_t* labels, const int32_t* num_dets,
@@ -235,7 +252,8 @@ int aicam_tracker_reset(aicam_tracker* t, void* stream);
  * detect()/aicam_decode_nms) and which of them reach the tracker:
  *   boxes fp32 [n_streams][stride_k][4], scores fp32 [..][stride_k], labels i32 [..][stride_k]
  *   det_index/det_count/crop_slot as written by aicam_reid_crops
- *   feats fp32 [rows][feature_dim] indexed by crop_slot
+ *   feats fp32 [rows][feature_dim] indexed by crop_slot; NULL = the frame has no features at all
+ *         (every appearance cost is INFTY_COST, nothing is appended to the galleries)
  * Outputs (device):
  *   out_tracks i32 [n_streams][max_tracks][6] = x1,y1,x2,y2,track_id,class_id (rounded half-even)
  *   out_conf   fp32 [n_streams][max_tracks]     out_count i32 [n_streams]
@@ -252,6 +270,18 @@ int aicam_tracker_step(aicam_tracker* t, const float* boxes, const float* scores
  * returns n (>= 0) or a negative error. */
 int aicam_tracker_snapshot(aicam_tracker* t, int stream_index, int32_t* ints, float* floats,
                            int capacity);
+/* Parity probe of the appearance cost (K8, matching.py:109-217) and the Mahalanobis gate (K9,
+ * linear_assignment.py:160-212); changes no tracker state.  For every live track of every stream, in
+ * track-list order (k < n_tracks[s]), against every filtered detection d < det_count[s]:
+ *   app_cost [n_streams][max_tracks][max_dets]  min over the gallery of max(0, 1 - cosine), 1e5 for
+ *            tentative tracks, empty galleries or detections without a feature
+ *   gate_d2  [n_streams][max_tracks][max_dets]  squared Mahalanobis distance to the PREDICTED state
+ *   track_ids [n_streams][max_tracks], n_tracks [n_streams]
+ * Call it with the inputs of the next aicam_tracker_step. */
+int aicam_tracker_cost_probe(aicam_tracker* t, const float* boxes, int stride_k, const int32_t* det_index,
+                             const int32_t* det_count, const int32_t* crop_slot, const float* feats,
+                             float* app_cost, float* gate_d2, int32_t* track_ids, int32_t* n_tracks,
+                             void* stream);
 /* Sticky per-stream overflow flags since the last reset (host out i32[n_streams]):
  * bit 0 = track capacity exceeded, bit 1 = detection capacity exceeded. */
 int aicam_tracker_overflow(aicam_tracker* t, int32_t* flags_host);

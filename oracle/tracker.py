@@ -178,7 +178,7 @@ def min_cost_matching(metric, max_distance, tracks, dets, t_idx, d_idx, log=None
         return [], t_idx, d_idx
     cm = metric(tracks, dets, t_idx, d_idx)
     if log is not None:
-        log.append(("raw", list(t_idx), list(d_idx), cm.copy()))
+        log.append(("raw", list(t_idx), list(d_idx), cm.copy(), max_distance))
     cm[cm > max_distance] = max_distance + 1e-5
     rows, cols = linear_sum_assignment(cm)
     matches, un_t, un_d = [], list(t_idx), list(d_idx)
@@ -308,6 +308,47 @@ class DeepSORT:
         detections; used where the tracker is tested without the ReID net)."""
         self.frame_count += 1
         self.tracker_core.predict()
+        dets = self._detections(bboxes_xyxy, confidences, class_ids, frame_bgr, frame_hw, planted_features)
+        self.tracker_core.update(dets)
+        out = []
+        for t in self.tracker_core.tracks:  # :125-141
+            if t.state == CONFIRMED and t.time_since_update == 0:
+                x1, y1, w, h = t.to_tlwh()
+                w = max(0, w)
+                h = max(0, h)
+                x2, y2 = x1 + w, y1 + h
+                name = CLASSES[t.class_id] if 0 <= t.class_id < len(CLASSES) else "Unknown"
+                out.append((int(round(x1)), int(round(y1)), int(round(x2)), int(round(y2)),
+                            t.track_id, name, float(t.confidence)))
+        return out
+
+    def probe_costs(self, bboxes_xyxy, confidences, class_ids, frame_bgr=None, *, frame_hw=None,
+                    planted_features=None):
+        """What the matching of the NEXT ``update`` with these arguments would be computed from,
+        without changing any state: for every live track (track-list order) against every
+        filtered detection, the appearance cost (matching.py:144-217; INFTY_COST rows for
+        tentative tracks, which never enter the cascade, tracker_core.py:112-117) and the squared
+        Mahalanobis distance to the predicted state (linear_assignment.py:160-212).
+        Returns (track_ids [T], app_cost [T, D] float32, gate_d2 [T, D] float32)."""
+        import copy
+        tracks = copy.deepcopy(self.tracker_core.tracks)
+        for t in tracks:
+            t.predict()
+        dets = self._detections(bboxes_xyxy, confidences, class_ids, frame_bgr, frame_hw, planted_features)
+        T, D = len(tracks), len(dets)
+        app = np.full((T, D), INFTY_COST, dtype=F32)
+        d2 = np.zeros((T, D), dtype=F32)
+        if T and D:
+            conf = [i for i, t in enumerate(tracks) if t.state == CONFIRMED]
+            if conf:
+                app[conf] = appearance_cost(tracks, dets, conf, list(range(D)))
+            meas = np.asarray([d.to_xyah() for d in dets])
+            for r, t in enumerate(tracks):
+                d2[r] = kalman.gating_distance(t.mean, t.cov, meas)
+        return np.asarray([t.track_id for t in tracks], dtype=np.int64), app, d2
+
+    def _detections(self, bboxes_xyxy, confidences, class_ids, frame_bgr, frame_hw, planted_features):
+        """deepsort_tracker.py:82-121, :161-199: filter, crops, features, Detection objects."""
         bboxes_xyxy = np.asarray(bboxes_xyxy)
         keep = self.filter_indices(confidences, class_ids)
         dets: List[Det] = []
@@ -331,15 +372,4 @@ class DeepSORT:
                 x1, y1, x2, y2 = fb[i]
                 tlwh = np.array([x1, y1, x2 - x1, y2 - y1], dtype=F32)
                 dets.append(Det(tlwh, float(fc[i]), int(fk[i]), feats.get(i)))
-        self.tracker_core.update(dets)
-        out = []
-        for t in self.tracker_core.tracks:  # :125-141
-            if t.state == CONFIRMED and t.time_since_update == 0:
-                x1, y1, w, h = t.to_tlwh()
-                w = max(0, w)
-                h = max(0, h)
-                x2, y2 = x1 + w, y1 + h
-                name = CLASSES[t.class_id] if 0 <= t.class_id < len(CLASSES) else "Unknown"
-                out.append((int(round(x1)), int(round(y1)), int(round(x2)), int(round(y2)),
-                            t.track_id, name, float(t.confidence)))
-        return out
+        return dets

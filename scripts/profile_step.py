@@ -31,5 +31,5 @@ pipe.step(video.frames(3))
 e1.record()
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
-print("step ms %.3f crops %d tracks %d" % (e0.elapsed_time(e1), pipe.tracker.crop_count.item(),
+print("step ms %.3f crops %d tracks %d" % (e0.elapsed_time(e1), pipe.tracker.crop_count[0].item(),
                                            pipe.tracker.out_count.sum().item()))

@@ -117,7 +117,7 @@ class Tracker:
         self.det_count = torch.zeros(S, dtype=torch.int32, device=DEV)
         self.crop_slot = torch.zeros((S, K), dtype=torch.int32, device=DEV)
         self.crop_rect = torch.zeros((S * K, 5), dtype=torch.int32, device=DEV)
-        self.crop_count = torch.zeros(1, dtype=torch.int32, device=DEV)
+        self.crop_count = torch.zeros(2, dtype=torch.int32, device=DEV)
         self.feats = torch.zeros((S * K, self.F), dtype=torch.float32, device=DEV)
         self.out_tracks = torch.zeros((S, max_tracks, 6), dtype=torch.int32, device=DEV)
         self.out_conf = torch.zeros((S, max_tracks), dtype=torch.float32, device=DEV)
@@ -128,9 +128,10 @@ class Tracker:
             lib().aicam_tracker_destroy(self.h)
             self.h = None
 
-    def step(self, frames):
+    def step(self, frames, probe=False, feats_null=False):
         """frames: list (one per stream) of dicts boxes/scores/classes/feats (numpy).  Returns, per
-        stream, (out [n,6] int64, conf [n] float64)."""
+        stream, (out [n,6] int64, conf [n] float64).  probe=True: no step; returns, per stream,
+        (track_ids [T], app_cost [T,D], gate_d2 [T,D]) from aicam_tracker_cost_probe."""
         from ai_camera_b200.config import tracked_class_mask
         S, K = self.S, self.K
         b = np.zeros((S, K, 4), np.float32)
@@ -158,8 +159,21 @@ class Tracker:
                 if cs[s, k] >= 0:
                     feats[cs[s, k]] = f["feats"][di[s, k]]
         self.feats.copy_(torch.from_numpy(feats))
+        if probe:
+            Dm = self.cfg.max_dets
+            app = torch.zeros((S, self.T, Dm), dtype=torch.float32, device=DEV)
+            d2 = torch.zeros((S, self.T, Dm), dtype=torch.float32, device=DEV)
+            ids = torch.zeros((S, self.T), dtype=torch.int32, device=DEV)
+            nt = torch.zeros(S, dtype=torch.int32, device=DEV)
+            check(lib().aicam_tracker_cost_probe(self.h, ptr(self.boxes), K, ptr(self.det_index), ptr(self.det_count),
+                                                 ptr(self.crop_slot), ptr(self.feats), ptr(app), ptr(d2), ptr(ids),
+                                                 ptr(nt), None))
+            sync()
+            app, d2, ids, nt = app.cpu().numpy(), d2.cpu().numpy(), ids.cpu().numpy(), nt.cpu().numpy()
+            return [(ids[s, :nt[s]].astype(np.int64), app[s, :nt[s], :dc[s]], d2[s, :nt[s], :dc[s]]) for s in range(S)]
         check(lib().aicam_tracker_step(self.h, ptr(self.boxes), ptr(self.scores), ptr(self.labels), K,
-                                       ptr(self.det_index), ptr(self.det_count), ptr(self.crop_slot), ptr(self.feats),
+                                       ptr(self.det_index), ptr(self.det_count), ptr(self.crop_slot),
+                                       None if feats_null else ptr(self.feats),
                                        ptr(self.out_tracks), ptr(self.out_conf), ptr(self.out_count), None))
         sync()
         ot, oc, on = self.out_tracks.cpu().numpy(), self.out_conf.cpu().numpy(), self.out_count.cpu().numpy()

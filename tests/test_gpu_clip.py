@@ -1,0 +1,88 @@
+"""BASELINE.json configs[0] (C1): the reference's own clip, one stream, batch 1, through the reference-shaped
+facades (YOLODetector.detect -> DeepSORT.update, the loop of /root/reference/src/aicamera_tracker.py:169-207),
+against the CPU oracle pipeline on the same decoded frames; plus the single-upload path of the frame loop."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CLIP = os.path.join(GOLDEN, "aicamera_test_clip.mp4")
+
+
+def _clip_frames(n):
+    from ai_camera_b200.aicamera_tracker import video_frames
+    return list(video_frames(CLIP, n))
+
+
+@pytest.fixture(scope="module")
+def blobs(tmp_path_factory):
+    from ai_camera_b200 import synth
+    return synth.make_blobs(str(tmp_path_factory.mktemp("blobs")))
+
+
+def test_clip_decodes_as_recorded():
+    import hashlib
+    meta = json.load(open(os.path.join(GOLDEN, "clip_meta.json")))
+    frames = _clip_frames(8)
+    assert list(frames[0].shape) == meta["frame_shape"]
+    h = hashlib.sha256()
+    for f in frames:
+        h.update(f.tobytes())
+    assert h.hexdigest() == meta["decoded_sha256_first8"], "cv2 decodes the clip differently from the box the fixture was made on"
+
+
+def test_clip_single_stream_matches_oracle(blobs):
+    from ai_camera_b200 import synth
+    from ai_camera_b200.aicamera_tracker import run_single_stream
+    from ai_camera_b200.deepsort_tracker import DeepSORT
+    from ai_camera_b200.yolo_detector import YOLODetector
+    from e2e_compare import compare_runs, oracle_margins
+    from oracle.pipeline import Pipeline
+    yolo, reid = blobs
+    bias = synth.shifted_class_bias(yolo, synth.CLIP_LOGIT_SHIFT)
+    frames = _clip_frames(64)
+    det = YOLODetector(yolo)
+    synth.apply_class_bias(det.trt_engine, bias)
+    trk = DeepSORT(reid)
+    got, dets_got = [], []
+    stats = run_single_stream(frames, det, trk, on_frame=lambda i, f, d, tr: (got.append(tr), dets_got.append(len(d[0]))))
+    ora = Pipeline(yolo, reid, yolo_bias=bias)
+    ora.tracker.tracker_core.cost_log = []
+    want, scores = [], []
+    for f in frames:
+        b, s, c, _ = ora.detector.detect(f)
+        scores.append(s)
+        want.append(ora.tracker.update(b, s, c, f))
+    r = compare_runs(got, want)
+    m = oracle_margins(ora.tracker.tracker_core.cost_log, scores)
+    print("clip C1: %s" % r)
+    print("clip C1: detections/frame device %.1f oracle %.1f; margins %s; loop %s" % (
+        np.mean(dets_got), np.mean([len(s) for s in scores]), m, stats.summary()))
+    assert r["oracle_tracks"] > 100, "the clip run reported too few tracks to compare"
+    assert r["matched"] >= 0.85 * r["oracle_tracks"]
+    assert r["consistent"] >= 0.95 * r["matched"] and r["max_px"] <= 6
+
+
+def test_frame_loop_single_upload_equals_double_upload(blobs):
+    """detect() leaves the frame in HBM; update() given that device tensor returns exactly what update() given
+    the numpy frame returns (one H2D copy per frame instead of two)."""
+    from ai_camera_b200 import synth
+    from ai_camera_b200.aicamera_tracker import run_single_stream
+    from ai_camera_b200.deepsort_tracker import DeepSORT
+    from ai_camera_b200.yolo_detector import YOLODetector
+    yolo, reid = blobs
+    bias = synth.shifted_class_bias(yolo, synth.CLIP_LOGIT_SHIFT)
+    frames = _clip_frames(12)
+    outs = []
+    for share in (True, False):
+        det = YOLODetector(yolo)
+        synth.apply_class_bias(det.trt_engine, bias)
+        trk = DeepSORT(reid, n_init=2)
+        res = []
+        run_single_stream(frames, det, trk, on_frame=lambda i, f, d, tr: res.append(tr), share_upload=share)
+        outs.append(res)
+    assert outs[0] == outs[1] and sum(len(r) for r in outs[0]) > 0

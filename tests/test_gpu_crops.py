@@ -39,7 +39,7 @@ def test_crops_bit_exact_and_filter():
     det_count = torch.zeros(B, dtype=torch.int32, device=G.DEV)
     crop_slot = torch.full((B, K), -7, dtype=torch.int32, device=G.DEV)
     crop_rect = torch.zeros((cap, 5), dtype=torch.int32, device=G.DEV)
-    crop_count = torch.zeros(1, dtype=torch.int32, device=G.DEV)
+    crop_count = torch.zeros(2, dtype=torch.int32, device=G.DEV)
     crops0 = torch.zeros((cap, 3, 128, 64), dtype=torch.float32, device=G.DEV)
     crops1 = torch.zeros((cap, 128, 64, 4), dtype=torch.bfloat16, device=G.DEV)
     crops2 = torch.full((cap, 128, 64, 8), 7.0, dtype=torch.bfloat16, device=G.DEV)  # NHWC8 for the fused stem
@@ -50,7 +50,7 @@ def test_crops_bit_exact_and_filter():
                                          G.ptr(crops), G.ptr(crop_count), None))
     G.sync()
     di, dc, cs = det_index.cpu().numpy(), det_count.cpu().numpy(), crop_slot.cpu().numpy()
-    cr, cc = crop_rect.cpu().numpy(), int(crop_count.item())
+    cr, cc = crop_rect.cpu().numpy(), int(crop_count[0].item())
     ds = DeepSORT()
     row = 0
     for b in range(B):
