@@ -80,6 +80,8 @@ SIGNATURES = {
     "aicam_reid_stem_pool": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "aicam_letterbox_params": (_I, [_I, _I, C.POINTER(Letterbox)]),
     "aicam_preprocess": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "aicam_preprocess_nv12": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "aicam_nv12_to_bgr": (_I, [_P, _I, _I, _I, _P, _P]),
     "aicam_decode_nms": (_I, [_P, _I, _I, _I, C.POINTER(NmsParams), _P, _P, _P, _P, _P, _P,
                               C.c_size_t, _P]),
     "aicam_decode_nms_workspace": (C.c_size_t, [_I, _I, C.POINTER(NmsParams)]),
@@ -88,6 +90,8 @@ SIGNATURES = {
                        C.c_size_t, _P]),
     "aicam_reid_crops": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _I, C.c_float, C.c_uint64,
                               C.c_uint64, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "aicam_reid_crops_nv12": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _I, C.c_float, C.c_uint64,
+                                   C.c_uint64, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "aicam_tracker_create": (_I, [C.POINTER(TrackerConfig), C.POINTER(_P)]),
     "aicam_tracker_destroy": (None, [_P]),
     "aicam_tracker_reset": (_I, [_P, _P]),

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "frame_src.cuh"
 
 namespace aicam {
 
@@ -131,7 +132,7 @@ int get_geometry(int h, int w, Geometry* out) {
 
 constexpr int PIX = 4;  // output pixels per thread (consecutive x)
 
-template <int FORMAT>
+template <int FORMAT, int SRC>
 __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ frames, int h, int w, int mode,
                                                          int new_h, int new_w, int top, int left,
                                                          const int* __restrict__ tab, void* __restrict__ out,
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
   long long t = idx / (S / PIX);
   const int y = static_cast<int>(t % S);
   const int n = static_cast<int>(t / S);
-  const uint8_t* src = frames + static_cast<long long>(n) * h * w * 3;
+  const FrameSrc<SRC> src{frames + n * FrameSrc<SRC>::frame_bytes(h, w), h, w};
   const int dy = y - top;
   const bool row_in = dy >= 0 && dy < new_h;
   const int* tx = tab;
@@ -160,30 +161,29 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
     int v[3] = {114, 114, 114};  // BGR pad colour (image_processing.py:10)
     if (row_in && dx >= 0 && dx < new_w) {
       if (mode == 2) {
-        const uint8_t* s = src + (static_cast<long long>(dy) * w + dx) * 3;
-        v[0] = __ldg(s); v[1] = __ldg(s + 1); v[2] = __ldg(s + 2);
+        src.pix(dy, dx, v);
       } else if (mode == 1) {
-        const uint8_t* s0 = src + (static_cast<long long>(2 * dy) * w + 2 * dx) * 3;
-        const uint8_t* s1 = s0 + static_cast<long long>(w) * 3;
+        int p00[3], p01[3], p10[3], p11[3];
+        src.pix(2 * dy, 2 * dx, p00); src.pix(2 * dy, 2 * dx + 1, p01);
+        src.pix(2 * dy + 1, 2 * dx, p10); src.pix(2 * dy + 1, 2 * dx + 1, p11);
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          v[c] = (__ldg(s0 + c) + __ldg(s0 + 3 + c) + __ldg(s1 + c) + __ldg(s1 + 3 + c) + 2) >> 2;
+        for (int c = 0; c < 3; ++c) v[c] = (p00[c] + p01[c] + p10[c] + p11[c] + 2) >> 2;
       } else {
         const int sx0 = __ldg(tx + dx), sx1 = __ldg(tx + new_w + dx);
         const int a0 = __ldg(tx + 2 * new_w + dx), a1 = __ldg(tx + 3 * new_w + dx);
-        const uint8_t* r0 = src + static_cast<long long>(sy0) * w * 3;
-        const uint8_t* r1 = src + static_cast<long long>(sy1) * w * 3;
+        // taps with a zero weight are not fetched
+        int p00[3] = {0, 0, 0}, p01[3] = {0, 0, 0}, p10[3] = {0, 0, 0}, p11[3] = {0, 0, 0};
+        if (b0 != 0) {
+          src.pix(sy0, sx0, p00);
+          if (a1 != 0) src.pix(sy0, sx1, p01);
+        }
+        if (b1 != 0) {
+          src.pix(sy1, sx0, p10);
+          if (a1 != 0) src.pix(sy1, sx1, p11);
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          int h0 = 0, h1 = 0;
-          if (b0 != 0) {
-            h0 = __ldg(r0 + sx0 * 3 + c) * a0;
-            if (a1 != 0) h0 += __ldg(r0 + sx1 * 3 + c) * a1;
-          }
-          if (b1 != 0) {
-            h1 = __ldg(r1 + sx0 * 3 + c) * a0;
-            if (a1 != 0) h1 += __ldg(r1 + sx1 * 3 + c) * a1;
-          }
+          const int h0 = p00[c] * a0 + p01[c] * a1, h1 = p10[c] * a0 + p11[c] * a1;
           int o = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
           v[c] = min(max(o, 0), 255);
         }
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
 // brought into shared memory with coalesced 128-bit loads (every byte of the row is fetched, one in `ratio`
 // pixels is used: that is the algorithmic traffic counted in the header), then each thread picks the three
 // bytes of its four pixels from shared memory.  Rows of the letterbox border issue no loads.
-template <int FORMAT>
+template <int FORMAT, int SRC>
 __global__ void __launch_bounds__(S / PIX) preprocess_rows_kernel(const uint8_t* __restrict__ frames, int h, int w, int new_h,
                                                                   int new_w, int top, int left, const int* __restrict__ tab,
                                                                   void* __restrict__ out) {
@@ -236,12 +236,25 @@ __global__ void __launch_bounds__(S / PIX) preprocess_rows_kernel(const uint8_t*
   const bool row_in = dy >= 0 && dy < new_h;
   if (row_in) {
     const int sy = __ldg(tab + 4 * new_w + dy);
-    const uint4* src = reinterpret_cast<const uint4*>(frames + (static_cast<long long>(n) * h + sy) * w * 3);
-    const int chunks = (w * 3) >> 4;
-    for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
-      uint4 v;
-      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i));
-      reinterpret_cast<uint4*>(srow)[i] = v;
+    if (SRC == 0) {
+      const uint4* src = reinterpret_cast<const uint4*>(frames + (static_cast<long long>(n) * h + sy) * w * 3);
+      const int chunks = (w * 3) >> 4;
+      for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i));
+        reinterpret_cast<uint4*>(srow)[i] = v;
+      }
+    } else {  // NV12: the luma row, then the chroma row it shares with its neighbour: [w Y bytes][w UV bytes]
+      const uint8_t* fr = frames + n * FrameSrc<1>::frame_bytes(h, w);
+      const uint4* ysrc = reinterpret_cast<const uint4*>(fr + static_cast<long long>(sy) * w);
+      const uint4* csrc = reinterpret_cast<const uint4*>(fr + static_cast<long long>(h) * w + static_cast<long long>(sy >> 1) * w);
+      const int chunks = w >> 4;
+      for (int i = threadIdx.x; i < 2 * chunks; i += blockDim.x) {
+        const uint4* s = i < chunks ? ysrc + i : csrc + (i - chunks);
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(s));
+        reinterpret_cast<uint4*>(srow)[i] = v;
+      }
     }
   }
   __syncthreads();
@@ -252,8 +265,15 @@ __global__ void __launch_bounds__(S / PIX) preprocess_rows_kernel(const uint8_t*
     const int dx = xg * PIX + p - left;
     int v0 = 114, v1 = 114, v2 = 114;  // BGR pad colour (image_processing.py:10)
     if (row_in && dx >= 0 && dx < new_w) {
-      const uint8_t* sp = srow + __ldg(tab + dx) * 3;
-      v0 = sp[0]; v1 = sp[1]; v2 = sp[2];
+      const int sx = __ldg(tab + dx);
+      if (SRC == 0) {
+        const uint8_t* sp = srow + sx * 3;
+        v0 = sp[0]; v1 = sp[1]; v2 = sp[2];
+      } else {
+        int bgr[3];
+        yuv_to_bgr_601(srow[sx], srow[w + (sx & ~1)], srow[w + (sx & ~1) + 1], bgr);
+        v0 = bgr[0]; v1 = bgr[1]; v2 = bgr[2];
+      }
     }
     rgb[p][0] = __fdiv_rn(static_cast<float>(v2), 255.0f);
     rgb[p][1] = __fdiv_rn(static_cast<float>(v1), 255.0f);
@@ -289,6 +309,13 @@ __global__ void __launch_bounds__(S / PIX) preprocess_rows_kernel(const uint8_t*
 
 using namespace aicam;
 
+namespace aicam {
+namespace {
+template <int SRC>
+int preprocess_impl(const uint8_t* frames, int batch, int h, int w, int format, void* out, void* stream);
+}
+}  // namespace aicam
+
 extern "C" {
 
 int aicam_letterbox_params(int h, int w, aicam_letterbox* meta) {
@@ -299,6 +326,20 @@ int aicam_letterbox_params(int h, int w, aicam_letterbox* meta) {
 }
 
 int aicam_preprocess(const uint8_t* frames, int batch, int h, int w, int format, void* out, void* stream) {
+  return preprocess_impl<0>(frames, batch, h, w, format, out, stream);
+}
+
+int aicam_preprocess_nv12(const uint8_t* frames_nv12, int batch, int h, int w, int format, void* out, void* stream) {
+  if (h % 2 || w % 2) return fail(AICAM_ERR_INVALID_ARG, "preprocess_nv12: NV12 frames have even height and width");
+  return preprocess_impl<1>(frames_nv12, batch, h, w, format, out, stream);
+}
+
+}  // extern "C"
+
+namespace aicam {
+namespace {
+template <int SRC>
+int preprocess_impl(const uint8_t* frames, int batch, int h, int w, int format, void* out, void* stream) {
   if (!frames || !out || batch < 0 || h <= 0 || w <= 0) return fail(AICAM_ERR_INVALID_ARG, "preprocess: bad arguments");
   if (format < 0 || format > 2) return fail(AICAM_ERR_INVALID_ARG, "preprocess: format must be 0, 1 or 2");
   if (batch == 0) return AICAM_OK;
@@ -308,32 +349,23 @@ int aicam_preprocess(const uint8_t* frames, int batch, int h, int w, int format,
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static const bool no_fast = getenv("AICAM_PREPROCESS_GENERIC") != nullptr;
-  if (g.decimate && !no_fast && (w * 3) % 16 == 0 && reinterpret_cast<uintptr_t>(frames) % 16 == 0 &&
-      (static_cast<long long>(h) * w * 3) % 16 == 0 && w * 3 <= 96 * 1024) {
+  const int row_bytes = SRC == 0 ? w * 3 : w;  // bytes of one staged source row (NV12: luma row; the chroma row has as many)
+  if (g.decimate && !no_fast && row_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(frames) % 16 == 0 &&
+      FrameSrc<SRC>::frame_bytes(h, w) % 16 == 0 && (static_cast<long long>(h) * w) % 16 == 0 && w * 3 <= 96 * 1024) {
     const unsigned rows = static_cast<unsigned>(batch) * S;
-    const size_t smem = static_cast<size_t>(w) * 3;
+    const size_t smem = SRC == 0 ? static_cast<size_t>(w) * 3 : static_cast<size_t>(w) * 2;
+    auto kernel = format == 0 ? preprocess_rows_kernel<0, SRC> : (format == 1 ? preprocess_rows_kernel<1, SRC> : preprocess_rows_kernel<2, SRC>);
     if (smem > 48 * 1024) {
-      if (int rc = ensure_dynamic_smem(format == 0 ? preprocess_rows_kernel<0> : (format == 1 ? preprocess_rows_kernel<1> : preprocess_rows_kernel<2>),
-                                       96 * 1024))
-        return rc;
+      if (int rc = ensure_dynamic_smem(kernel, 96 * 1024)) return rc;
     }
-    if (format == 0)
-      preprocess_rows_kernel<0><<<rows, S / PIX, smem, st>>>(frames, h, w, g.new_h, g.new_w, g.top, g.left, g.tab, out);
-    else if (format == 1)
-      preprocess_rows_kernel<1><<<rows, S / PIX, smem, st>>>(frames, h, w, g.new_h, g.new_w, g.top, g.left, g.tab, out);
-    else
-      preprocess_rows_kernel<2><<<rows, S / PIX, smem, st>>>(frames, h, w, g.new_h, g.new_w, g.top, g.left, g.tab, out);
+    kernel<<<rows, S / PIX, smem, st>>>(frames, h, w, g.new_h, g.new_w, g.top, g.left, g.tab, out);
     count_launch();
     return last_launch("preprocess_rows_kernel");
   }
-  if (format == 0)
-    preprocess_kernel<0><<<blocks, 256, 0, st>>>(frames, h, w, g.mode, g.new_h, g.new_w, g.top, g.left, g.tab, out, total);
-  else if (format == 1)
-    preprocess_kernel<1><<<blocks, 256, 0, st>>>(frames, h, w, g.mode, g.new_h, g.new_w, g.top, g.left, g.tab, out, total);
-  else
-    preprocess_kernel<2><<<blocks, 256, 0, st>>>(frames, h, w, g.mode, g.new_h, g.new_w, g.top, g.left, g.tab, out, total);
+  auto kernel = format == 0 ? preprocess_kernel<0, SRC> : (format == 1 ? preprocess_kernel<1, SRC> : preprocess_kernel<2, SRC>);
+  kernel<<<blocks, 256, 0, st>>>(frames, h, w, g.mode, g.new_h, g.new_w, g.top, g.left, g.tab, out, total);
   count_launch();
   return last_launch("preprocess_kernel");
 }
-
-}  // extern "C"
+}  // namespace
+}  // namespace aicam

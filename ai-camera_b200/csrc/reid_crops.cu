@@ -14,6 +14,7 @@
 // resized crop, and therefore the float tensor, equals the reference's bit for bit.
 // HBM-bound: reads ~crop bytes, writes 128*64*8 B (NHWC4 bf16) or 128*64*16 B (NHWC8, what the fused ReID stem reads) per crop.
 #include "common.cuh"
+#include "frame_src.cuh"
 
 namespace aicam {
 
@@ -133,7 +134,7 @@ __device__ __forceinline__ void axis_entry(int src, int dst, int d, bool horizon
   *w1 = __float2int_rn(__fmul_rn(f, 2048.0f));
 }
 
-template <int FORMAT>
+template <int FORMAT, int SRC>
 __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ frames, int h, int w,
                                                    const int* __restrict__ crop_rect,
                                                    const int* __restrict__ crop_count, void* __restrict__ out) {
@@ -150,36 +151,35 @@ __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ f
     else if (t < RW + RH) axis_entry(ch, RH, t - RW, false, &ty[0][t - RW], &ty[1][t - RW], &ty[2][t - RW], &ty[3][t - RW]);
   }
   __syncthreads();
-  const uint8_t* src = frames + (static_cast<long long>(b) * h + y1) * w * 3 + static_cast<long long>(x1) * 3;
-  const long long rs = static_cast<long long>(w) * 3;
+  const FrameSrc<SRC> src{frames + b * FrameSrc<SRC>::frame_bytes(h, w), h, w};
   const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
   for (int p = threadIdx.x; p < RH * RW; p += blockDim.x) {
     const int oy = p / RW, ox = p - oy * RW;
     int v[3];
     if (mode == 2) {
-      const uint8_t* s = src + oy * rs + ox * 3;
-      v[0] = __ldg(s); v[1] = __ldg(s + 1); v[2] = __ldg(s + 2);
+      src.pix(y1 + oy, x1 + ox, v);
     } else if (mode == 1) {
-      const uint8_t* s0 = src + (2 * oy) * rs + (2 * ox) * 3;
-      const uint8_t* s1 = s0 + rs;
+      int p00[3], p01[3], p10[3], p11[3];
+      src.pix(y1 + 2 * oy, x1 + 2 * ox, p00); src.pix(y1 + 2 * oy, x1 + 2 * ox + 1, p01);
+      src.pix(y1 + 2 * oy + 1, x1 + 2 * ox, p10); src.pix(y1 + 2 * oy + 1, x1 + 2 * ox + 1, p11);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) v[c] = (__ldg(s0 + c) + __ldg(s0 + 3 + c) + __ldg(s1 + c) + __ldg(s1 + 3 + c) + 2) >> 2;
+      for (int c = 0; c < 3; ++c) v[c] = (p00[c] + p01[c] + p10[c] + p11[c] + 2) >> 2;
     } else {
-      const int sx0 = tx[0][ox], sx1 = tx[1][ox], a0 = tx[2][ox], a1 = tx[3][ox];
-      const int b0 = ty[2][oy], b1 = ty[3][oy];
-      const uint8_t* r0 = src + ty[0][oy] * rs;
-      const uint8_t* r1 = src + ty[1][oy] * rs;
+      const int sx0 = x1 + tx[0][ox], sx1 = x1 + tx[1][ox], a0 = tx[2][ox], a1 = tx[3][ox];
+      const int sy0 = y1 + ty[0][oy], sy1 = y1 + ty[1][oy], b0 = ty[2][oy], b1 = ty[3][oy];
+      // taps with a zero weight are not fetched
+      int p00[3] = {0, 0, 0}, p01[3] = {0, 0, 0}, p10[3] = {0, 0, 0}, p11[3] = {0, 0, 0};
+      if (b0 != 0) {
+        src.pix(sy0, sx0, p00);
+        if (a1 != 0) src.pix(sy0, sx1, p01);
+      }
+      if (b1 != 0) {
+        src.pix(sy1, sx0, p10);
+        if (a1 != 0) src.pix(sy1, sx1, p11);
+      }
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        int h0 = 0, h1 = 0;
-        if (b0 != 0) {
-          h0 = __ldg(r0 + sx0 * 3 + c) * a0;
-          if (a1 != 0) h0 += __ldg(r0 + sx1 * 3 + c) * a1;
-        }
-        if (b1 != 0) {
-          h1 = __ldg(r1 + sx0 * 3 + c) * a0;
-          if (a1 != 0) h1 += __ldg(r1 + sx1 * 3 + c) * a1;
-        }
+        const int h0 = p00[c] * a0 + p01[c] * a1, h1 = p10[c] * a0 + p11[c] * a1;
         const int o = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
         v[c] = min(max(o, 0), 255);
       }
@@ -208,11 +208,14 @@ __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ f
 
 using namespace aicam;
 
-extern "C" int aicam_reid_crops(const uint8_t* frames, int batch, int h, int w, const float* boxes, const float* scores,
-                                const int32_t* labels, const int32_t* num_dets, int stride_k, float min_confidence,
-                                uint64_t class_mask_lo, uint64_t class_mask_hi, int format, int max_crops,
-                                int32_t* det_index, int32_t* det_count, int32_t* crop_slot, int32_t* crop_rect,
-                                void* crops, int32_t* crop_count, void* stream) {
+namespace aicam {
+namespace {
+template <int SRC>
+int reid_crops_impl(const uint8_t* frames, int batch, int h, int w, const float* boxes, const float* scores,
+                    const int32_t* labels, const int32_t* num_dets, int stride_k, float min_confidence,
+                    uint64_t class_mask_lo, uint64_t class_mask_hi, int format, int max_crops,
+                    int32_t* det_index, int32_t* det_count, int32_t* crop_slot, int32_t* crop_rect,
+                    void* crops, int32_t* crop_count, void* stream) {
   if (!boxes || !scores || !labels || !num_dets || !det_index || !det_count || !crop_slot || !crop_rect || !crop_count)
     return fail(AICAM_ERR_INVALID_ARG, "reid_crops: null argument");
   if (batch < 0 || stride_k <= 0 || h <= 0 || w <= 0 || max_crops < 0 || (format < 0 || format > 2))
@@ -226,11 +229,66 @@ extern "C" int aicam_reid_crops(const uint8_t* frames, int batch, int h, int w, 
   if (int rc = last_launch("filter_kernel")) return rc;
   if (max_crops == 0 || !frames || !crops) return AICAM_OK;  // filter only
   if (format == 0)
-    crop_kernel<0><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
+    crop_kernel<0, SRC><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
   else if (format == 1)
-    crop_kernel<1><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
+    crop_kernel<1, SRC><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
   else
-    crop_kernel<2><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
+    crop_kernel<2, SRC><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
   count_launch();
   return last_launch("crop_kernel");
+}
+}  // namespace
+}  // namespace aicam
+
+extern "C" int aicam_reid_crops(const uint8_t* frames, int batch, int h, int w, const float* boxes, const float* scores,
+                                const int32_t* labels, const int32_t* num_dets, int stride_k, float min_confidence,
+                                uint64_t class_mask_lo, uint64_t class_mask_hi, int format, int max_crops,
+                                int32_t* det_index, int32_t* det_count, int32_t* crop_slot, int32_t* crop_rect,
+                                void* crops, int32_t* crop_count, void* stream) {
+  return reid_crops_impl<0>(frames, batch, h, w, boxes, scores, labels, num_dets, stride_k, min_confidence, class_mask_lo,
+                            class_mask_hi, format, max_crops, det_index, det_count, crop_slot, crop_rect, crops, crop_count, stream);
+}
+
+extern "C" int aicam_reid_crops_nv12(const uint8_t* frames_nv12, int batch, int h, int w, const float* boxes, const float* scores,
+                                     const int32_t* labels, const int32_t* num_dets, int stride_k, float min_confidence,
+                                     uint64_t class_mask_lo, uint64_t class_mask_hi, int format, int max_crops,
+                                     int32_t* det_index, int32_t* det_count, int32_t* crop_slot, int32_t* crop_rect,
+                                     void* crops, int32_t* crop_count, void* stream) {
+  if (h % 2 || w % 2) return fail(AICAM_ERR_INVALID_ARG, "reid_crops_nv12: NV12 frames have even height and width");
+  return reid_crops_impl<1>(frames_nv12, batch, h, w, boxes, scores, labels, num_dets, stride_k, min_confidence, class_mask_lo,
+                            class_mask_hi, format, max_crops, det_index, det_count, crop_slot, crop_rect, crops, crop_count, stream);
+}
+
+// NV12 -> packed BGR (cv2.cvtColor(.., COLOR_YUV2BGR_NV12)): the frames the NV12 entry points see, as the reference's
+// decoder would have handed them out; for parity tests and for callers that keep a BGR copy.
+namespace aicam {
+namespace {
+__global__ void __launch_bounds__(256) nv12_to_bgr_kernel(const uint8_t* __restrict__ nv12, int h, int w, uint8_t* __restrict__ bgr,
+                                                          long long total) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;  // one thread per 2 horizontal pixels
+  if (idx >= total) return;
+  const int xp = static_cast<int>(idx % (w / 2));
+  const long long t = idx / (w / 2);
+  const int y = static_cast<int>(t % h);
+  const long long n = t / h;
+  const uint8_t* f = nv12 + n * FrameSrc<1>::frame_bytes(h, w);
+  const uint8_t* c = f + static_cast<long long>(h) * w + static_cast<long long>(y >> 1) * w + 2 * xp;
+  const int u = __ldg(c), v = __ldg(c + 1);
+  int p0[3], p1[3];
+  yuv_to_bgr_601(__ldg(f + static_cast<long long>(y) * w + 2 * xp), u, v, p0);
+  yuv_to_bgr_601(__ldg(f + static_cast<long long>(y) * w + 2 * xp + 1), u, v, p1);
+  uint8_t* o = bgr + ((n * h + y) * w + 2 * xp) * 3;
+  o[0] = p0[0]; o[1] = p0[1]; o[2] = p0[2]; o[3] = p1[0]; o[4] = p1[1]; o[5] = p1[2];
+}
+}  // namespace
+}  // namespace aicam
+
+extern "C" int aicam_nv12_to_bgr(const uint8_t* frames_nv12, int batch, int h, int w, uint8_t* frames_bgr, void* stream) {
+  if (!frames_nv12 || !frames_bgr || batch < 0 || h <= 0 || w <= 0 || h % 2 || w % 2)
+    return fail(AICAM_ERR_INVALID_ARG, "nv12_to_bgr: bad arguments (NV12 frames have even height and width)");
+  if (batch == 0) return AICAM_OK;
+  const long long total = static_cast<long long>(batch) * h * (w / 2);
+  nv12_to_bgr_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(frames_nv12, h, w, frames_bgr, total);
+  count_launch();
+  return last_launch("nv12_to_bgr_kernel");
 }

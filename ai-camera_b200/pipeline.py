@@ -16,6 +16,17 @@ from . import _lib, config
 from .trt_engine import TRTEngine
 
 
+def frame_geometry(frames: torch.Tensor):
+    """(n, h, w, is_nv12) of a batch of frames: [n, H, W, 3] packed BGR or [n, H*3/2, W] NV12."""
+    if frames.dtype != torch.uint8 or not frames.is_contiguous():
+        raise _lib.AicamError(-1, "frames must be a contiguous uint8 tensor")
+    if frames.dim() == 4 and frames.shape[3] == 3:
+        return frames.shape[0], frames.shape[1], frames.shape[2], False
+    if frames.dim() == 3 and frames.shape[1] % 3 == 0:
+        return frames.shape[0], frames.shape[1] * 2 // 3, frames.shape[2], True
+    raise _lib.AicamError(-1, "frames must be [n, H, W, 3] (BGR) or [n, H*3/2, W] (NV12)")
+
+
 class BatchDetector:
     """K1-K4 + detect() post-processing for ``batch`` frames of one size."""
 
@@ -41,19 +52,21 @@ class BatchDetector:
         self._s2d = bool(self.lib.aicam_engine_accepts_s2d(e.handle))
 
     def detect(self, frames: torch.Tensor):
-        """frames: uint8 cuda [n<=batch, H, W, 3] BGR.  Returns device tensors (num_dets [n],
+        """frames: uint8 cuda [n<=batch, H, W, 3] BGR, or [n, H*3/2, W] NV12 (Y plane + interleaved UV plane, the
+        surface format of hardware decoders: half the bytes).  Returns device tensors (num_dets [n],
         boxes [n,topk,4] in frame pixels, scores [n,topk], labels [n,topk]); views of internal
         buffers, valid until the next call; asynchronous on the current stream."""
-        n, h, w, _ = frames.shape
+        n, h, w, nv12 = frame_geometry(frames)
+        pre = self.lib.aicam_preprocess_nv12 if nv12 else self.lib.aicam_preprocess
         if n > self.batch:
             raise _lib.AicamError(-4, "detect: %d frames exceed the detector's batch %d" % (n, self.batch))
         e, st = self.engine, _lib.stream_ptr(self.device)
         with torch.cuda.device(self.device):
             if self._s2d:  # same bytes, 2x2 pixel blocks: the stride-2 stem runs as a stride-1 window
-                _lib.check(self.lib.aicam_preprocess(_lib.ptr(frames), n, h, w, 2, _lib.ptr(e._nhwc), st))
+                _lib.check(pre(_lib.ptr(frames), n, h, w, 2, _lib.ptr(e._nhwc), st))
                 _lib.check(self.lib.aicam_yolo_forward_s2d(e.handle, _lib.ptr(e._nhwc), n, _lib.ptr(e._head), st))
             else:
-                _lib.check(self.lib.aicam_preprocess(_lib.ptr(frames), n, h, w, 1, _lib.ptr(e._nhwc), st))
+                _lib.check(pre(_lib.ptr(frames), n, h, w, 1, _lib.ptr(e._nhwc), st))
                 _lib.check(self.lib.aicam_yolo_forward(e.handle, _lib.ptr(e._nhwc), n, _lib.ptr(e._head), st))
             self._nms.frame_h, self._nms.frame_w = h, w
             _lib.check(self.lib.aicam_decode_nms(
@@ -122,15 +135,16 @@ class BatchTracker:
         self.crop_count.zero_()
 
     def update(self, frames, num_dets, boxes, scores, labels):
-        """One frame per stream.  frames uint8 cuda [S,H,W,3]; detections as BatchDetector returns
-        them ([S], [S,K,4], [S,K], [S,K]).  Returns device (out_tracks [S,T,6] int32 =
+        """One frame per stream.  frames uint8 cuda [S,H,W,3] BGR or [S,H*3/2,W] NV12; detections as BatchDetector
+        returns them ([S], [S,K,4], [S,K], [S,K]).  Returns device (out_tracks [S,T,6] int32 =
         x1,y1,x2,y2,id,class, out_conf [S,T], out_count [S]); asynchronous."""
-        S, h, w, _ = frames.shape
+        S, h, w, nv12 = frame_geometry(frames)
+        crops_fn = self.lib.aicam_reid_crops_nv12 if nv12 else self.lib.aicam_reid_crops
         if S != self.S or boxes.shape[1] != self.K:
             raise _lib.AicamError(-4, "update: expected %d streams x %d detections" % (self.S, self.K))
         st = _lib.stream_ptr(self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.aicam_reid_crops(
+            _lib.check(crops_fn(
                 _lib.ptr(frames), S, h, w, _lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(labels), _lib.ptr(num_dets),
                 self.K, self.min_conf, self._mask[0], self._mask[1], 2 if self._nhwc8 else 1, self.max_crops,
                 _lib.ptr(self.det_index),
@@ -174,8 +188,10 @@ class TrackingPipeline:
     """detect + track for ``n_streams`` streams of one frame size; one call per time step."""
 
     def __init__(self, yolo_engine_path, reid_engine_path, n_streams: int, device=None, max_tracks: int = 256,
-                 max_crops: Optional[int] = None, conf_threshold=config.YOLO_CONF_THRESHOLD, **tracker_kw):
-        self.detector = BatchDetector(yolo_engine_path, n_streams, device, conf_threshold=conf_threshold)
+                 max_crops: Optional[int] = None, conf_threshold=config.YOLO_CONF_THRESHOLD, topk=config.YOLO_TOPK,
+                 max_candidates=config.YOLO_MAX_CANDIDATES, **tracker_kw):
+        self.detector = BatchDetector(yolo_engine_path, n_streams, device, conf_threshold=conf_threshold, topk=topk,
+                                      max_candidates=max_candidates)
         # detect() drops detections below conf_threshold before update() sees them (yolo_detector.py:131); on the
         # device that filter and DeepSORT's own (deepsort_tracker.py:88-95) are one comparison
         tracker_kw.setdefault("min_detection_confidence", max(config.DEEPSORT_MIN_CONFIDENCE, conf_threshold))

@@ -45,12 +45,14 @@ class SynthVideo:
         self.n_streams, self.frame_hw, self.n_frames = n_streams, frame_hw, n_frames
         self.ring = torch.empty((n_frames, n_streams, H, W, 3), dtype=torch.uint8, device=device)
         max_shift = 6 * n_frames
+        self.velocity = []  # per stream (vx, vy) in network pixels per frame; 3 source pixels each
         for s in range(n_streams):
             g = torch.Generator(device="cpu").manual_seed(seed + first_stream + s)
             hb, wb = (H + 2 * max_shift) // block + 2, (W + 2 * max_shift) // block + 2
             coarse = torch.randint(0, 256, (hb, wb, 3), generator=g, dtype=torch.uint8)
             fine = torch.randint(0, 48, (H + 2 * max_shift, W + 2 * max_shift, 3), generator=g, dtype=torch.uint8)
             vx, vy = (int(v) for v in torch.randint(-2, 3, (2,), generator=g))
+            self.velocity.append((vx, vy))
             tex = coarse.to(device).repeat_interleave(block, 0).repeat_interleave(block, 1)
             tex = tex[:H + 2 * max_shift, :W + 2 * max_shift]
             tex = (tex.to(torch.int16) * 3 // 4 + fine.to(device).to(torch.int16)).clamp_(0, 255).to(torch.uint8)
@@ -68,6 +70,25 @@ class SynthVideo:
 
     def frames(self, step):
         return self.ring[self.index(step)]
+
+
+def bgr_to_nv12(frames_bgr):
+    """uint8 [n, H, W, 3] BGR (any device) -> NV12 [n, H*3/2, W]: BT.601 limited-range integer RGB -> YCbCr, chroma
+    from the 2x2 block means.  Only a GENERATOR of synthetic NV12 surfaces (what a hardware decoder would hand over);
+    the conversion the path is held to is the inverse one (aicam_nv12_to_bgr == cv2 COLOR_YUV2BGR_NV12)."""
+    n, H, W, _ = frames_bgr.shape
+    f = frames_bgr.to(torch.int32)
+    b, g, r = f[..., 0], f[..., 1], f[..., 2]
+    y = ((66 * r + 129 * g + 25 * b + 128) >> 8) + 16
+    m = f.view(n, H // 2, 2, W // 2, 2, 3).sum(dim=(2, 4))  # 2x2 block sums
+    mb, mg, mr = (m[..., 0] + 2) >> 2, (m[..., 1] + 2) >> 2, (m[..., 2] + 2) >> 2
+    u = ((-38 * mr - 74 * mg + 112 * mb + 128) >> 8) + 128
+    v = ((112 * mr - 94 * mg - 18 * mb + 128) >> 8) + 128
+    out = torch.empty((n, H * 3 // 2, W), dtype=torch.uint8, device=frames_bgr.device)
+    out[:, :H] = y.clamp_(0, 255).to(torch.uint8)
+    uv = torch.stack([u, v], dim=-1).clamp_(0, 255).to(torch.uint8)  # [n, H/2, W/2, 2]
+    out[:, H:] = uv.view(n, H // 2, W)
+    return out
 
 
 CLS_LAYERS = ["model.22.cv3.%d.2" % l for l in range(3)]

@@ -165,6 +165,16 @@ typedef struct {
 int aicam_letterbox_params(int h, int w, aicam_letterbox* meta);
 int aicam_preprocess(const uint8_t* frames, int batch, int h, int w, int format, void* out,
                      void* stream);
+/* The same from NV12 frames (u8 [batch][h * 3 / 2][w]: Y plane, then the interleaved U, V plane; h, w even):
+ * the surface format of hardware video decoders, 1.5 bytes per pixel instead of 3.  Where the reference's
+ * loop receives BGR from cv2.VideoCapture.read() (src/aicamera_tracker.py:170), the decoder underneath
+ * converted exactly such a surface; here that conversion (OpenCV's COLOR_YUV2BGR_NV12: BT.601, 20-bit fixed
+ * point) is applied per fetched pixel, so the output equals aicam_preprocess on the converted BGR frame bit
+ * for bit.  aicam_nv12_to_bgr makes that BGR frame (u8 [batch][h][w][3]). */
+int aicam_preprocess_nv12(const uint8_t* frames_nv12, int batch, int h, int w, int format, void* out,
+                          void* stream);
+int aicam_nv12_to_bgr(const uint8_t* frames_nv12, int batch, int h, int w, uint8_t* frames_bgr,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Detection post-processing: the decode + NMS the reference's engine embeds (it returns
@@ -222,6 +232,13 @@ int aicam_reid_crops(const uint8_t* frames, int batch, int h, int w, const float
                      uint64_t class_mask_hi, int format, int max_crops, int32_t* det_index,
                      int32_t* det_count, int32_t* crop_slot, int32_t* crop_rect, void* crops,
                      int32_t* crop_count, void* stream);
+/* The same with NV12 frames (see aicam_preprocess_nv12): crops equal those of the converted BGR frame. */
+int aicam_reid_crops_nv12(const uint8_t* frames_nv12, int batch, int h, int w, const float* boxes,
+                          const float* scores, const int32_t* labels, const int32_t* num_dets,
+                          int stride_k, float min_confidence, uint64_t class_mask_lo,
+                          uint64_t class_mask_hi, int format, int max_crops, int32_t* det_index,
+                          int32_t* det_count, int32_t* crop_slot, int32_t* crop_rect, void* crops,
+                          int32_t* crop_count, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Tracker: replaces TrackerCore / Track / KalmanFilter / matching / linear_assignment

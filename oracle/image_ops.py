@@ -170,3 +170,23 @@ def reid_batch(frame_bgr, rects, target_shape=(128, 64)):
         return np.empty((0, 3, target_shape[0], target_shape[1]), F32)
     return np.concatenate([preprocess_reid_input(frame_bgr[y1:y2, x1:x2], target_shape)
                            for (x1, y1, x2, y2) in rects], axis=0)
+
+
+def nv12_to_bgr(nv12, h, w):
+    """cv2.cvtColor(nv12, cv2.COLOR_YUV2BGR_NV12) restated (OpenCV imgproc color_yuv: ITU-R BT.601 limited
+    range, 20-bit fixed point: ITUR_BT_601_CY 1220542, CUB 2116026, CUG -409993, CVG -852492, CVR 1673527,
+    rounding 1 << 19).  nv12: uint8 (h*3/2, w): the Y plane, then rows of interleaved U, V at half
+    resolution.  This is the conversion the video decoder under ``cv2.VideoCapture.read()``
+    (/root/reference/src/aicamera_tracker.py:170) applies before the reference ever sees a frame; the
+    device path can take the NV12 surface itself (aicam_preprocess_nv12 / aicam_reid_crops_nv12).
+    Verified equal to cv2 4.13 in tests/test_oracle_imageops.py."""
+    nv12 = np.asarray(nv12, np.uint8).reshape(h * 3 // 2, w)
+    Y = nv12[:h].astype(np.int32)
+    uv = nv12[h:].reshape(h // 2, w // 2, 2).astype(np.int32)
+    U = np.repeat(np.repeat(uv[..., 0], 2, 0), 2, 1) - 128
+    V = np.repeat(np.repeat(uv[..., 1], 2, 0), 2, 1) - 128
+    yy = np.maximum(0, Y - 16) * 1220542 + (1 << 19)
+    b = (yy + 2116026 * U) >> 20
+    g = (yy - 852492 * V - 409993 * U) >> 20
+    r = (yy + 1673527 * V) >> 20
+    return np.clip(np.stack([b, g, r], -1), 0, 255).astype(np.uint8)

@@ -66,3 +66,20 @@ def test_resize_against_cv2_when_available():
         img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
         want = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)
         assert np.array_equal(image_ops.resize_linear_u8(img, dw, dh), want), (sh, sw, dw, dh)
+
+
+def test_nv12_to_bgr_equals_cv2():
+    """The oracle's NV12 -> BGR restatement against OpenCV itself (the conversion under VideoCapture.read())."""
+    import cv2
+    from oracle import image_ops
+    rng = np.random.default_rng(11)
+    for (h, w) in [(36, 64), (540, 960), (1080, 1920), (2, 2)]:
+        nv12 = rng.integers(0, 256, (h * 3 // 2, w), dtype=np.uint8)
+        assert np.array_equal(image_ops.nv12_to_bgr(nv12, h, w), cv2.cvtColor(nv12, cv2.COLOR_YUV2BGR_NV12)), (h, w)
+    # every (Y, U, V) triple the 8-bit domain has along the extremes
+    ys, us, vs = np.meshgrid(np.arange(256), [0, 1, 16, 127, 128, 129, 240, 255], [0, 1, 16, 127, 128, 129, 240, 255], indexing="ij")
+    n = ys.size
+    img = np.zeros((3, 2 * n), np.uint8)  # 2 rows of luma (same Y twice), 1 row of UV pairs
+    img[0, 0::2] = img[0, 1::2] = img[1, 0::2] = img[1, 1::2] = ys.ravel()
+    img[2, 0::2], img[2, 1::2] = us.ravel(), vs.ravel()
+    assert np.array_equal(image_ops.nv12_to_bgr(img, 2, 2 * n), cv2.cvtColor(img, cv2.COLOR_YUV2BGR_NV12))
