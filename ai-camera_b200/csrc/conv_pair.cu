@@ -51,6 +51,7 @@ struct PairMaps {
 
 struct PairArgs {
   int h, w, hw, rw;           // logical image size, padded pixels per image, padded row pitch
+  int lo;                     // offset of the interior inside the padded image (1 symmetric border, 0 shared border)
   int slabs, cin_pad;
   int sa, sb, resident;
   uint32_t patch_bytes, box_bytes, bstage_bytes, wbytes_half;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) conv_pair_kernel(const __grid
       const uint32_t p = (static_cast<uint32_t>(mt_i) * 2 + rank) * TM + r;  // (< 2^31 padded pixels, checked on the host)
       const uint32_t rem = p % static_cast<uint32_t>(a.hw);
       const int yy = static_cast<int>(rem / static_cast<uint32_t>(a.rw)), xx = static_cast<int>(rem) - yy * a.rw;
-      const bool zero_row = !(yy >= 1 && yy <= a.h && xx >= 1 && xx <= a.w);
+      const bool zero_row = !(yy >= a.lo && yy < a.lo + a.h && xx >= a.lo && xx < a.lo + a.w);
       if (threadIdx.x == 0) PAIR_TRACE(it, 8);
       mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
@@ -563,7 +564,8 @@ int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t
   const int n_tile = std::min(cout_pad, 256), n_half = n_tile / 2, n_tiles = cout_pad / n_tile;
   const int tps = n_tile == 256 ? 1 : 3;
   const int res_mode = L.res ? L.res_mode : 0;
-  const int hp = L.h + 2, wp = L.w + 2;
+  if (L.in_pad != L.out_pad) return 0;
+  const int hp = L.h + pad_ext(L.in_pad), wp = L.w + pad_ext(L.in_pad);
   if (L.in_cstride % 8 || L.in_coff % 8 || L.out_cstride % 8 || L.out_coff % 8 || (res_mode && (L.res_cstride % 8 || L.res_coff % 8))) return 0;
   if (L.in_img_stride != static_cast<long long>(hp) * wp * L.in_cstride || L.out_img_stride != static_cast<long long>(hp) * wp * L.out_cstride ||
       (res_mode && L.res_img_stride != static_cast<long long>(hp) * wp * L.res_cstride))
@@ -607,7 +609,7 @@ int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t
   const int mt = best_mt, tm = 128 * mt;
   PairArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.h = L.h; a.w = L.w; a.hw = hp * wp; a.rw = wp;
+  a.h = L.h; a.w = L.w; a.hw = hp * wp; a.rw = wp; a.lo = pad_lo(L.in_pad);
   a.slabs = slabs; a.cin_pad = pc.cin_pad;
   a.sa = best_sa; a.sb = best_sb; a.resident = resident ? 1 : 0;
   a.box_rows = best_bh;

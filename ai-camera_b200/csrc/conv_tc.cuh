@@ -48,8 +48,17 @@ struct ConvLaunch {
   // h / w / ho / wo stay the logical sizes and the image strides describe the padded images.  The border is
   // never written, so a 3x3 stride-1 layer can run over the flat raster of ALL padded pixels (window kernel,
   // operand mode 4) without per-image halo handling.  The residual shares the output's layout.
+  //   pad = 1  symmetric border: [h + 2][w + 2], interior at (1, 1);
+  //   pad = 2  SHARED border: [h + 1][w + 1], interior at (0, 0).  The zero column x = w is the right border of its row AND
+  //            the left border of the next row (the raster wraps), the zero row y = h the bottom border of its image AND
+  //            the top border of the next image; what lies above the first image are the TMA unit's out-of-bounds zeros.
+  //            Same flat-raster arithmetic, fewer wasted positions: h w / ((h + 1)(w + 1)) useful instead of
+  //            h w / ((h + 2)(w + 2)) - 71 % instead of 53 % on the 8 x 4 maps of ReID layer 4.
   int in_pad = 0, out_pad = 0;
 };
+
+inline int pad_lo(int pad) { return pad == 1 ? 1 : 0; }                    // interior offset (rows and columns)
+inline int pad_ext(int pad) { return pad == 1 ? 2 : (pad == 2 ? 1 : 0); }  // extra rows / columns an image carries
 
 // host: pack OIHW fp32 weights (host) into the device layout above
 int pack_conv_weights(const float* w_oihw, const float* bias, int cout, int cin, int ksize, int stride,

@@ -76,7 +76,9 @@ struct WinArgs {
   int res_direct;  // residual read straight from global in the finish phase (no staging): deep, streamed layers
   int out_s2d;  // window modes: the output is stored space-to-depth: [h/2][w/2][2x2 sub-pixel][out_cstride]
   int flat;  // 1x1 mode: output and residual are dense, pixel p of the batch sits at p * cstride
-  int out_pad;   // flat / im2col modes: output (and residual) images carry a one-pixel zero border, interior at (1, 1)
+  int out_pad;   // flat / im2col modes: output (and residual) images carry a zero border: extra rows / columns per image ...
+  int out_lo;    // ... and the offset of the interior in it (conv_tc.cuh: pad kinds)
+  int in_lo;     // mode 4: offset of the interior inside the padded raster (1 symmetric border, 0 shared border)
   int box_rows;  // mode 4: raster rows per TMA box (a patch is MT boxes)
   int s2d_store;    // TMA epilogue of a space-to-depth output: the tile is stored through a 5-D map (2C, x/2, y&1, y/2, n) whose
                     // box image is the plain compact [y][x][C] staging tile (no swizzle); tile origins and sizes are even
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
         const uint32_t p = static_cast<uint32_t>(mt_idx) * TM + r;
         const uint32_t rem = p % static_cast<uint32_t>(a.hw);
         const int yy = static_cast<int>(rem / static_cast<uint32_t>(a.rw)), xx = static_cast<int>(rem) - yy * a.rw;
-        zero_row = !(yy >= 1 && yy <= a.h && xx >= 1 && xx <= a.w);
+        zero_row = !(yy >= a.in_lo && yy < a.in_lo + a.h && xx >= a.in_lo && xx < a.in_lo + a.w);
       }
       for (int g = g_lo; g < g_hi; g += 2) {
         uint32_t v0[16], v1[16];
@@ -500,14 +502,14 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
           if (FLATWIN) {  // p runs over the padded raster: only interior positions are outputs
             const int rem = pix - (pix / a.hw) * a.hw;
             const int yy = rem / a.rw, xx = rem - yy * a.rw;
-            valid = valid && yy >= 1 && yy <= a.h && xx >= 1 && xx <= a.w;
+            valid = valid && yy >= a.in_lo && yy < a.in_lo + a.h && xx >= a.in_lo && xx < a.in_lo + a.w;
           }
         } else {
           img = static_cast<int>(p) / a.hw;
           pix = static_cast<int>(p) - img * a.hw;
-          if (a.out_pad) {  // zero-bordered output image: (y, x) -> (y + 1, x + 1) of a (wo + 2)-wide raster
+          if (a.out_pad) {  // zero-bordered output image: (y, x) -> (y + lo, x + lo) of a (wo + border)-wide raster
             const int y = pix / a.wo, x = pix - y * a.wo;
-            pix = (y + 1) * (a.wo + 2) + x + 1;
+            pix = (y + a.out_lo) * (a.wo + a.out_pad) + x + a.out_lo;
           }
         }
       }
@@ -997,11 +999,14 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
     return 0;
   if (L.in_cstride % 8 != 0 || L.in_coff % 8 != 0 || reinterpret_cast<uintptr_t>(L.in) % 16 != 0) return 0;
   const int ip = L.in_pad ? 1 : 0, opd = L.out_pad ? 1 : 0;
-  const int hp = L.h + 2 * ip, wp = L.w + 2 * ip;  // input image as it lies in memory
+  const int ilo = pad_lo(L.in_pad), iext = pad_ext(L.in_pad), olo = pad_lo(L.out_pad), oext = pad_ext(L.out_pad);
+  const int hp = L.h + iext, wp = L.w + iext;  // input image as it lies in memory
   if (L.in_img_stride != static_cast<long long>(hp) * wp * L.in_cstride) return 0;
-  if (opd && (L.out_img_stride != static_cast<long long>(L.ho + 2) * (L.wo + 2) * L.out_cstride ||
-              (res_mode && L.res_img_stride != static_cast<long long>(L.ho + 2) * (L.wo + 2) * L.res_cstride) || L.out_s2d || s2d))
+  if (opd && (L.out_img_stride != static_cast<long long>(L.ho + oext) * (L.wo + oext) * L.out_cstride ||
+              (res_mode && L.res_img_stride != static_cast<long long>(L.ho + oext) * (L.wo + oext) * L.res_cstride) || L.out_s2d || s2d))
     return fail(AICAM_ERR_INVALID_ARG, "conv_win: padded output with an inconsistent image stride");
+  if (ip && opd && pc.stride == 1 && L.in_pad != L.out_pad)
+    return fail(AICAM_ERR_INVALID_ARG, "conv_win: a stride-1 layer over padded tensors needs the same border kind on both sides");
   const long long pixels = static_cast<long long>(L.batch) * L.ho * L.wo;  // output pixels
   const long long padded_pixels = static_cast<long long>(L.batch) * hp * wp;
   if (pixels >= (1ll << 31) || padded_pixels >= (1ll << 31)) return 0;
@@ -1137,6 +1142,7 @@ plan:
           p.bh = ((tm + 2 * wp + 2 + mt - 1) / mt + 7) / 8 * 8;
           if (p.bh > 256) continue;
           p.box_bytes = static_cast<uint32_t>(mt) * p.bh * row_bytes;
+          (void)ilo;
           p.patch_bytes = (p.box_bytes + 1023) / 1024 * 1024;
           p.tiles = (padded_pixels + tm - 1) / tm;
           if (epi) {
@@ -1219,8 +1225,8 @@ plan:
   WinArgs a;
   std::memset(&a, 0, sizeof(a));
   a.mode = mode; a.h = win_h; a.w = win_w; a.hw = mode == 4 ? hp * wp : L.ho * L.wo;
-  a.ksize = pc.ksize; a.stride = pc.stride; a.pad = pc.ksize / 2 - ip; a.wo = L.wo; a.slabs_per_tap = slabs;
-  a.out_pad = opd; a.box_rows = best.bh; a.direct_out = direct_out ? 1 : 0;
+  a.ksize = pc.ksize; a.stride = pc.stride; a.pad = pc.ksize / 2 - ilo; a.wo = L.wo; a.slabs_per_tap = slabs;
+  a.out_pad = oext; a.out_lo = olo; a.in_lo = ilo; a.box_rows = best.bh; a.direct_out = direct_out ? 1 : 0;
   a.rw = best.rw; a.tw = best.tw; a.strips = best.strips; a.tstep = best.tstep;
   a.tiles_per_strip = best.tiles_per_strip; a.tiles_per_img = best.strips * best.tiles_per_strip;
   a.mt = best.mt; a.tm = 128 * best.mt;
@@ -1304,8 +1310,9 @@ plan:
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(L.in_cstride) * 2, static_cast<cuuint64_t>(wp) * L.in_cstride * 2,
                                    static_cast<cuuint64_t>(hp) * wp * L.in_cstride * 2};
     const int pad = pc.ksize / 2;
-    const int lower[2] = {ip - pad, ip - pad};
-    const int upper[2] = {pad - (pc.ksize - 1) - ip, pad - (pc.ksize - 1) - ip};
+    const int ihi = iext - ilo;  // border rows / columns after the interior
+    const int lower[2] = {ilo - pad, ilo - pad};
+    const int upper[2] = {pad - (pc.ksize - 1) - ihi, pad - (pc.ksize - 1) - ihi};
     const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(pc.stride), static_cast<cuuint32_t>(pc.stride), 1};
     cr = get_encode_im2col()(&maps.in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, lower, upper, static_cast<cuuint32_t>(slab),
                              128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -35,7 +35,8 @@ struct BlobTensor {
 struct Buffer {
   __nv_bfloat16* ptr;
   int h, w, c;
-  int pad = 0;  // 1: stored [batch][h + 2][w + 2][c] with a zero border that no kernel ever writes (conv_tc.cuh)
+  int pad = 0;  // border kind (conv_tc.cuh): 1: stored [batch][h + 2][w + 2][c], 2: [batch][h + 1][w + 1][c] (shared border);
+                // the border is zero and no kernel ever writes anything but zeros there
 };
 
 struct View {
@@ -104,7 +105,7 @@ struct Builder {
 
   int buf(int h, int w, int c, int pad = 0) {
     Buffer b{nullptr, h, w, c, pad};
-    const size_t bytes = static_cast<size_t>(e->max_batch) * (h + 2 * pad) * (w + 2 * pad) * c * sizeof(__nv_bfloat16);
+    const size_t bytes = static_cast<size_t>(e->max_batch) * (h + pad_ext(pad)) * (w + pad_ext(pad)) * c * sizeof(__nv_bfloat16);
     if (cudaMalloc(&b.ptr, bytes) != cudaSuccess) {
       err = fail(AICAM_ERR_CUDA, "engine: cudaMalloc of an activation buffer failed");
       b.ptr = nullptr;
@@ -292,11 +293,13 @@ struct Builder {
     static const bool unfused = getenv("AICAM_NO_STEM_FUSION") != nullptr;
     static const bool no_pad = getenv("AICAM_NO_PADDED_REID") != nullptr;
     static const bool no_pad1 = getenv("AICAM_NO_PADDED_L1") != nullptr;
+    // border kind of the trunk's activations: 2 = shared border (default), 1 = symmetric border (AICAM_REID_PAD=1)
+    static const int pad_kind = getenv("AICAM_REID_PAD") ? std::max(1, std::min(2, atoi(getenv("AICAM_REID_PAD")))) : 2;
     auto wi = tensors->find("conv.0.weight");
     auto bi = tensors->find("conv.0.bias");
     if (!unfused && wi != tensors->end() && bi != tensors->end() && wi->second.dims.size() == 4 && wi->second.dims[0] == 64 &&
         wi->second.dims[1] == 3 && wi->second.dims[2] == 3 && static_cast<int>(bi->second.count) == 64) {
-      pad1 = (no_pad || no_pad1) ? 0 : 1;  // the fused stem writes the zero-bordered layout directly
+      pad1 = (no_pad || no_pad1) ? 0 : pad_kind;  // the fused stem writes the zero-bordered layout directly
       cur = buf(h, w, c, pad1);
       // fused stem: crops NHWC4 -> NHWC8 -> conv3x3 + ReLU + maxpool 3x3 s2 in one kernel (stem_pool.cu)
       if (int rc = pack_stem_pool(wi->second.data, bi->second.data, 64, 3, &e->stem)) { err = rc; return; }
@@ -319,7 +322,7 @@ struct Builder {
         const int ho = h / s, wo = w / s;
         // layers 2-4 live in zero-bordered buffers: their 3x3 stride-1 convolutions run over the flat padded
         // raster (conv_win.cu, operand mode 4) instead of nine im2col loads per tile on these small maps
-        const int pd = li > 0 ? (no_pad ? 0 : 1) : pad1;
+        const int pd = li > 0 ? (no_pad ? 0 : pad_kind) : pad1;
         const int t = buf(ho, wo, cout, pd), o = buf(ho, wo, cout, pd);
         conv(name + ".conv1", V(cur), h, w, V(t), c, cout, 3, s, 2);
         int resbuf = cur;
@@ -380,7 +383,7 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
     auto geom = [&](const View& v, int fallback_c, const __nv_bfloat16** ptr, long long* img_stride, int* cstride) {
       if (v.buf >= 0) {
         const Buffer& b = e->buffers[v.buf];
-        *ptr = b.ptr; *cstride = b.c; *img_stride = static_cast<long long>(b.h + 2 * b.pad) * (b.w + 2 * b.pad) * b.c;
+        *ptr = b.ptr; *cstride = b.c; *img_stride = static_cast<long long>(b.h + pad_ext(b.pad)) * (b.w + pad_ext(b.pad)) * b.c;
       } else if (v.buf == -1) {
         *ptr = static_cast<const __nv_bfloat16*>(input); *cstride = 4;
         *img_stride = static_cast<long long>(e->in_h) * e->in_w * 4;
@@ -465,7 +468,7 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
       case Op::AVGL2: {
         // a padded buffer is summed border and all (the border is zero) and divided by the interior count
         const int pd = op.in.buf >= 0 ? e->buffers[op.in.buf].pad : 0;
-        rc = launch_avgpool_l2norm(ip, batch, (op.h + 2 * pd) * (op.w + 2 * pd), op.h * op.w, op.c, static_cast<float*>(output),
+        rc = launch_avgpool_l2norm(ip, batch, (op.h + pad_ext(pd)) * (op.w + pad_ext(pd)), op.h * op.w, op.c, static_cast<float*>(output),
                                    stream, n_dev);
         break;
       }
@@ -742,13 +745,14 @@ int aicam_conv2d_padded(const aicam_conv_desc* d, const void* in, const float* w
   if (int rc = pack_conv_weights(w, bias, d->cout, d->cin, d->ksize, d->stride, &pc)) return rc;
   ConvLaunch L;
   const int cs = pc.cin_pad;
-  const int ip = in_pad ? 1 : 0, opd = out_pad ? 1 : 0;
+  if (in_pad < 0 || in_pad > 2 || out_pad < 0 || out_pad > 2) return fail(AICAM_ERR_INVALID_ARG, "conv2d_padded: border kinds are 0, 1, 2");
+  const int ip = in_pad, opd = out_pad;
   L.in = static_cast<const __nv_bfloat16*>(in);
-  L.in_img_stride = static_cast<long long>(d->h + 2 * ip) * (d->w + 2 * ip) * cs; L.in_cstride = cs; L.in_coff = 0;
+  L.in_img_stride = static_cast<long long>(d->h + pad_ext(ip)) * (d->w + pad_ext(ip)) * cs; L.in_cstride = cs; L.in_coff = 0;
   L.batch = d->batch; L.h = d->h; L.w = d->w;
   L.ho = (d->h + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
   L.wo = (d->w + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
-  L.out = out; L.out_img_stride = static_cast<long long>(L.ho + 2 * opd) * (L.wo + 2 * opd) * d->cout; L.out_cstride = d->cout;
+  L.out = out; L.out_img_stride = static_cast<long long>(L.ho + pad_ext(opd)) * (L.wo + pad_ext(opd)) * d->cout; L.out_cstride = d->cout;
   L.out_coff = 0; L.out_f32 = d->out_f32;
   L.res = static_cast<const __nv_bfloat16*>(res); L.res_img_stride = L.out_img_stride; L.res_cstride = d->cout;
   L.res_coff = 0; L.res_mode = res ? d->res_mode : 0;
@@ -801,9 +805,10 @@ int aicam_conv2d_bench(const aicam_conv_desc* d, int iters, double* mean_ms, voi
   const int ho = (d->h + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
   const int wo = (d->w + 2 * (d->ksize / 2) - d->ksize) / d->stride + 1;
   // AICAM_BENCH_PAD=1: 3x3 stride-1 layers are timed over zero-bordered tensors (operand mode 4)
-  const int bp = (getenv("AICAM_BENCH_PAD") && d->ksize == 3 && d->stride == 1 && !c0) ? 1 : 0;
-  const size_t in_elems = static_cast<size_t>(d->batch) * (d->h + 2 * bp) * (d->w + 2 * bp) * cs;
-  const size_t out_elems = static_cast<size_t>(d->batch) * (ho + 2 * bp) * (wo + 2 * bp) * d->cout;
+  const int bp = (getenv("AICAM_BENCH_PAD") && d->ksize == 3 && d->stride == 1 && !c0) ? std::max(1, std::min(2, atoi(getenv("AICAM_BENCH_PAD")))) : 0;
+  const int be = pad_ext(bp);
+  const size_t in_elems = static_cast<size_t>(d->batch) * (d->h + be) * (d->w + be) * cs;
+  const size_t out_elems = static_cast<size_t>(d->batch) * (ho + be) * (wo + be) * d->cout;
   __nv_bfloat16 *in = nullptr, *res = nullptr;
   void* out = nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -814,14 +819,14 @@ int aicam_conv2d_bench(const aicam_conv_desc* d, int iters, double* mean_ms, voi
     AICAM_CUDA_OK(cudaMalloc(&res, out_elems * 2));
     AICAM_CUDA_OK(cudaMemset(res, 0x3c, out_elems * 2));
   }
-  L.in = in; L.in_img_stride = static_cast<long long>(d->h + 2 * bp) * (d->w + 2 * bp) * cs; L.in_cstride = cs; L.in_coff = 0;
+  L.in = in; L.in_img_stride = static_cast<long long>(d->h + be) * (d->w + be) * cs; L.in_cstride = cs; L.in_coff = 0;
   L.batch = d->batch; L.h = d->h; L.w = d->w; L.ho = ho; L.wo = wo;
   L.in_pad = bp; L.out_pad = bp;
   if (bp) pack_pair_weights(&pc);
   if (c0) {  // the timed launches read the same bytes as an already space-to-depth tensor
     L.in_cstride = 4 * c0; L.h = d->h / 2; L.w = d->w / 2; L.ho = L.h; L.wo = L.w;
   }
-  L.out = out; L.out_img_stride = static_cast<long long>(ho + 2 * bp) * (wo + 2 * bp) * d->cout; L.out_cstride = d->cout; L.out_coff = 0;
+  L.out = out; L.out_img_stride = static_cast<long long>(ho + be) * (wo + be) * d->cout; L.out_cstride = d->cout; L.out_coff = 0;
   L.out_f32 = d->out_f32;
   L.res = res; L.res_img_stride = L.out_img_stride; L.res_cstride = d->cout; L.res_coff = 0; L.res_mode = d->res_mode;
   L.act = d->act;

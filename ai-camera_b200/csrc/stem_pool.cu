@@ -23,6 +23,7 @@
 #include <cstring>
 #include <vector>
 
+#include "conv_tc.cuh"
 #include "stem_pool.cuh"
 #include "tc_ptx.cuh"
 
@@ -59,7 +60,8 @@ struct StemArgs {
   const float* bias;
   __nv_bfloat16* out;
   int h, w, ph, pw;  // convolution size (= input size), pooled size
-  int out_pad;       // 1: the output images are zero-bordered, [ph + 2][pw + 2][64] with the interior at (1, 1)
+  int out_pad;       // extra rows / columns of a zero-bordered output image ([ph + out_pad][pw + out_pad][64]) ...
+  int out_lo;        // ... and the offset of the interior in it (conv_tc.cuh: pad kinds)
   int tiles_y, tiles_x;
   int batch;
   const int* batch_dev;
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(THREADS, 1) reid_stem_pool_kernel(const StemAr
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               ow[k] = pack_bf16x2(fmaxf(bf16_lo(mw[k]) + pbias[2 * k], 0.0f), fmaxf(bf16_hi(mw[k]) + pbias[2 * k + 1], 0.0f));
-            *reinterpret_cast<uint4*>(a.out + ((static_cast<long long>(n) * (a.ph + 2 * a.out_pad) + py + a.out_pad) * (a.pw + 2 * a.out_pad) + px + o + a.out_pad) * COUT + pg * 8) =
+            *reinterpret_cast<uint4*>(a.out + ((static_cast<long long>(n) * (a.ph + a.out_pad) + py + a.out_lo) * (a.pw + a.out_pad) + px + o + a.out_lo) * COUT + pg * 8) =
                 make_uint4(ow[0], ow[1], ow[2], ow[3]);
           }
         }
@@ -372,7 +374,7 @@ int launch_stem_pool(const StemPool& sp, const __nv_bfloat16* in_nhwc8, int batc
   if (h % 2 || w % 2) return fail(AICAM_ERR_INVALID_ARG, "stem_pool: even input sizes only");
   StemArgs a;
   a.wgt = sp.w; a.bias = sp.bias; a.out = out;
-  a.h = h; a.w = w; a.ph = h / 2; a.pw = w / 2; a.out_pad = out_pad ? 1 : 0;
+  a.h = h; a.w = w; a.ph = h / 2; a.pw = w / 2; a.out_pad = pad_ext(out_pad); a.out_lo = pad_lo(out_pad);
   a.tiles_y = cdiv(a.ph, PH); a.tiles_x = cdiv(a.pw, PW);
   a.batch = batch; a.batch_dev = n_dev;
   alignas(64) CUtensorMap tmap;

@@ -131,11 +131,16 @@ typedef struct {
 } aicam_conv_desc;
 int aicam_conv2d(const aicam_conv_desc* d, const void* in_nhwc, const float* weights_oihw,
                  const float* bias, const void* res_nhwc, void* out_nhwc, void* stream);
-/* The same operator over zero-bordered ("padded") tensors: with in_pad / out_pad = 1 the input / the output and
- * residual are [batch][h + 2][w + 2][c] with a one-pixel border of zeros, interior at (1, 1); the border of
- * the output is never written (it must be zero already).  This is the layout the ReID engine keeps layers 2-4
- * in, so that their 3x3 stride-1 layers run over one flat raster of padded pixels (csrc/conv_win.cu, mode 4).
- * Supported: 3x3 stride 1 with in_pad = out_pad = 1; any stride-2 layer with either flag. */
+/* The same operator over zero-bordered ("padded") tensors.  in_pad / out_pad give the border kind of the input /
+ * of the output and residual:
+ *   1  symmetric: [batch][h + 2][w + 2][c], a one-pixel border of zeros all round, interior at (1, 1);
+ *   2  shared:    [batch][h + 1][w + 1][c], interior at (0, 0), one zero column x = w and one zero row y = h: in the
+ *                 flat raster of all pixels the column is the right border of its row and the left border of the
+ *                 next, the row the bottom border of its image and the top border of the next (what precedes the
+ *                 first image is read as zeros).  This is the layout the ReID engine keeps its trunk in.
+ * The border of the output must be zero already; kernels write only zeros there.  The 3x3 stride-1 layers then run
+ * over one flat raster of padded pixels (csrc/conv_win.cu mode 4, csrc/conv_pair.cu).
+ * Supported: 3x3 stride 1 with in_pad = out_pad != 0; any stride-2 layer with either. */
 int aicam_conv2d_padded(const aicam_conv_desc* d, const void* in_nhwc, const float* weights_oihw,
                         const float* bias, const void* res_nhwc, void* out_nhwc, int in_pad, int out_pad,
                         void* stream);

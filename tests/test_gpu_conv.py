@@ -102,13 +102,17 @@ PADDED_CASES = [
 ]
 
 
+@pytest.mark.parametrize("kind", [1, 2], ids=["symmetric", "shared"])
 @pytest.mark.parametrize("case", PADDED_CASES, ids=[c[0] for c in PADDED_CASES])
-def test_padded_conv_matches_torch(case):
-    """Same operator over zero-bordered tensors; the output border must stay exactly zero."""
+def test_padded_conv_matches_torch(case, kind):
+    """Same operator over zero-bordered tensors (border kind 1: [h+2][w+2] interior at (1,1); kind 2: shared border,
+    [h+1][w+1] interior at (0,0)); the output border must stay exactly zero."""
     import ctypes as C
     import gpu_util as G
     from ai_camera_b200._lib import ConvDesc, check, ptr
     name, B, H, W, cin, cout, k, s, act, res_mode, ipad, opad = case
+    ipad, opad = ipad * kind, opad * kind
+    lo, ext = (1, 2) if kind == 1 else (0, 1)
     rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
     x = G.bf16_round_np(rng.normal(0, 1, (B, H, W, cin)))
     w = G.bf16_round_np(rng.normal(0, 1.0 / np.sqrt(cin * k * k), (cout, cin, k, k)))
@@ -117,20 +121,21 @@ def test_padded_conv_matches_torch(case):
     res = G.bf16_round_np(rng.normal(0, 1, (B, ho, wo, cout))) if res_mode else None
 
     def padded(a, on):
-        return np.pad(a, ((0, 0), (1, 1), (1, 1), (0, 0))) if on else a
+        return np.pad(a, ((0, 0), (lo, ext - lo), (lo, ext - lo), (0, 0))) if on else a
 
     xd = torch.from_numpy(padded(x, ipad)).to(G.DEV).to(torch.bfloat16).contiguous()
     rd = torch.from_numpy(padded(res, opad)).to(G.DEV).to(torch.bfloat16).contiguous() if res_mode else None
-    out = torch.zeros((B, ho + 2 * opad, wo + 2 * opad, cout), dtype=torch.bfloat16, device=G.DEV)
+    oe = ext if opad else 0
+    out = torch.zeros((B, ho + oe, wo + oe, cout), dtype=torch.bfloat16, device=G.DEV)
     d = ConvDesc(B, H, W, cin, cout, k, s, act, res_mode, 0)
     check(G.lib().aicam_conv2d_padded(C.byref(d), ptr(xd), ptr(np.ascontiguousarray(w)), ptr(b), ptr(rd), ptr(out),
                                       ipad, opad, None))
     got = out.float().cpu().numpy()
     if opad:
         border = got.copy()
-        border[:, 1:-1, 1:-1, :] = 0
+        border[:, lo:lo + ho, lo:lo + wo, :] = 0
         assert not border.any(), "%s: the zero border was written" % name
-        got = got[:, 1:-1, 1:-1, :]
+        got = got[:, lo:lo + ho, lo:lo + wo, :]
     y = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(w), torch.from_numpy(b), stride=s,
                  padding=k // 2)
     r = torch.from_numpy(res).permute(0, 3, 1, 2) if res_mode else None

@@ -143,3 +143,28 @@ def test_engine_errors(blobs, tmp_path):
     bad.write_bytes(b"not a blob at all, definitely" * 4)
     assert G.lib().aicam_engine_create(str(bad).encode(), 0, 1, C.byref(h)) == -3
     assert b"AICW0001" in G.lib().aicam_last_error()
+
+
+def test_engine_rejects_corrupt_tensor_entries(blobs, tmp_path):
+    """A blob whose tensor table lies (short byte count for its dims, offset past the file, offset + size wrapping
+    around 2^64, unaligned offset) is refused with AICAM_ERR_IO instead of being read out of bounds."""
+    import struct
+    import gpu_util as G
+    raw = bytearray(open(blobs["reid"], "rb").read())
+    entry = struct.Struct("<64sI4IQQ")
+    name, nd, d0, d1, d2, d3, off, nbytes = entry.unpack_from(raw, 48)
+    h = C.c_void_p()
+
+    def attempt(new_off, new_nbytes, tag):
+        bad = bytearray(raw)
+        entry.pack_into(bad, 48, name, nd, d0, d1, d2, d3, new_off, new_nbytes)
+        path = tmp_path / ("corrupt_%s.aicw" % tag)
+        path.write_bytes(bytes(bad))
+        rc = G.lib().aicam_engine_create(str(path).encode(), 0, 1, C.byref(h))
+        assert rc == -3, (tag, rc, G.lib().aicam_last_error())
+
+    attempt(off, nbytes // 2, "short")                     # dims promise twice the floats the entry holds
+    attempt(len(raw) + 64, nbytes, "past_end")
+    attempt(2 ** 64 - 64, 128, "wraps")                    # off + nbytes overflows to a small number
+    attempt(off + 2, nbytes, "unaligned")
+    attempt(off, nbytes + 4, "long")
