@@ -30,6 +30,16 @@ namespace aicam {
 
 extern void count_launch();
 
+// appearance_tf32.cu: K8 of crowded frames on the tensor cores (TF32x3)
+struct AppearanceTf32;
+bool appearance_tf32_eligible(int S, int F, int G, int D);
+int appearance_tf32_create(AppearanceTf32** out, int S, int T, int D, int F, int G, const float* gal_hi, const float* gal_lo,
+                           const float* feat_hi, const float* feat_lo);
+void appearance_tf32_destroy(AppearanceTf32* p);
+int launch_appearance_tf32(const AppearanceTf32* p, int S, int T, int D, int F, int G, int min_dets, const int* n_tracks,
+                           const int* order, const int* state, const int* gal_count, const int* det_count, const int* crop_slot,
+                           int stride_k, float* app_cost, cudaStream_t stream);
+
 namespace {
 
 constexpr int TENTATIVE = 1, CONFIRMED = 2, DELETED = 3;  // track.py:10-14
@@ -48,7 +58,12 @@ struct Dev {
   float* app_cost;  // [S][T][D] by (slot, det)
   float* cost_ws;   // [S][T*D]
   float* featn;     // [S][D][F]
+  // TF32 split copies (x = hi + lo, hi exactly representable with a 10-bit mantissa) of the gallery and of the
+  // normalised detection features: the operands of appearance_tf32.cu; null when that path is not in use
+  float* gal_hi; float* gal_lo; float* featn_hi; float* featn_lo;
 };
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 // ---- float32 building blocks (oracle/kalman.py) ------------------------------------------------
 __device__ __forceinline__ float sq_via_double(float x) {
@@ -285,8 +300,16 @@ __global__ void __launch_bounds__(128) normalize_kernel(Dev t, const int* __rest
     __syncthreads();
   }
   const float nrm = fmaxf(sqrtf(red[0]), 1e-7f);
-  float* o = t.featn + (static_cast<long long>(s) * t.D + d) * t.F;
-  for (int k = threadIdx.x; k < t.F; k += blockDim.x) o[k] = f[k] / nrm;
+  const long long ob = (static_cast<long long>(s) * t.D + d) * t.F;
+  for (int k = threadIdx.x; k < t.F; k += blockDim.x) {
+    const float v = f[k] / nrm;
+    t.featn[ob + k] = v;
+    if (t.featn_hi) {
+      const float h = tf32_hi(v);
+      t.featn_hi[ob + k] = h;
+      t.featn_lo[ob + k] = v - h;
+    }
+  }
 }
 
 // K8: cost[slot][d] = min over the gallery of max(0, 1 - <g, f_d>)  (matching.py:109-217)
@@ -439,7 +462,9 @@ constexpr size_t AG_SMEM = (AG_KC * (AG_ROWS + 4) + AG_KC * (AG_DT + 4) + 16 * A
 __global__ void __launch_bounds__(256) appearance_kernel(Dev t, const int* __restrict__ det_count,
                                                          const int* __restrict__ crop_slot, int stride_k, int gemm_ok) {
   extern __shared__ __align__(16) float sm_f[];
-  if (gemm_ok && min(det_count[blockIdx.y], t.D) > APP_GEMM_MIN) appearance_gemm(t, det_count, crop_slot, stride_k, sm_f);
+  const bool crowded = min(det_count[blockIdx.y], t.D) > APP_GEMM_MIN;
+  if (crowded && gemm_ok == 2) return;  // appearance_tf32_kernel owns this stream's frame
+  if (crowded && gemm_ok == 1) appearance_gemm(t, det_count, crop_slot, stride_k, sm_f);
   else appearance_rows(t, det_count, crop_slot, stride_k, sm_f);
 }
 
@@ -609,9 +634,11 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
       if (row >= 0) {  // track.py:70-74: append to the gallery, FIFO at the budget
         const int cnt = t.gal_count[ts], head = t.gal_head[ts];
         const int pos = cnt < t.G ? (head + cnt) % t.G : head;
-        float* dst = t.gallery + (ts * t.G + pos) * t.F;
-        const float* src = t.featn + (static_cast<long long>(s) * Dm + d) * t.F;
-        for (int f = lane; f < t.F; f += 32) dst[f] = src[f];
+        const long long go = (ts * t.G + pos) * t.F, so = (static_cast<long long>(s) * Dm + d) * t.F;
+        for (int f = lane; f < t.F; f += 32) {
+          t.gallery[go + f] = t.featn[so + f];
+          if (t.gal_hi) { t.gal_hi[go + f] = t.featn_hi[so + f]; t.gal_lo[go + f] = t.featn_lo[so + f]; }
+        }
         if (lane == 0) {
           if (cnt < t.G) t.gal_count[ts] = cnt + 1; else t.gal_head[ts] = (head + 1) % t.G;
         }
@@ -681,9 +708,11 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
     const long long ts = sb + Utmp[j];
     const int row = io.has_feats ? io.crop_slot[static_cast<long long>(s) * io.stride_k + d] : -1;
     if (row >= 0) {
-      float* dst = t.gallery + ts * t.G * t.F;
-      const float* src = t.featn + (static_cast<long long>(s) * Dm + d) * t.F;
-      for (int f = lane; f < t.F; f += 32) dst[f] = src[f];
+      const long long go = ts * t.G * t.F, so = (static_cast<long long>(s) * Dm + d) * t.F;
+      for (int f = lane; f < t.F; f += 32) {
+        t.gallery[go + f] = t.featn[so + f];
+        if (t.gal_hi) { t.gal_hi[go + f] = t.featn_hi[so + f]; t.gal_lo[go + f] = t.featn_lo[so + f]; }
+      }
       if (lane == 0) t.gal_count[ts] = 1;
     }
     if (lane == 0) {
@@ -799,6 +828,7 @@ struct aicam_tracker {
   aicam::Dev d;
   aicam_tracker_config cfg;
   std::vector<void*> allocs;
+  aicam::AppearanceTf32* tf = nullptr;  // tensor-core appearance path (frames with more than APP_GEMM_MIN detections)
 };
 
 using namespace aicam;
@@ -817,17 +847,24 @@ int dev_alloc(aicam_tracker* t, Tp** p, size_t n) {
 
 namespace {
 // K8: L2-normalise the frame's detection features, then the appearance cost of every confirmed track
-int launch_appearance(const Dev& d, const int32_t* det_count, const int32_t* crop_slot, int stride_k, const float* feats, cudaStream_t st) {
+int launch_appearance(const Dev& d, const AppearanceTf32* tf, const int32_t* det_count, const int32_t* crop_slot, int stride_k,
+                      const float* feats, cudaStream_t st) {
   normalize_kernel<<<dim3(d.D, d.S), 128, 0, st>>>(d, det_count, crop_slot, stride_k, feats);
   count_launch();
   if (int rc = last_launch("normalize_kernel")) return rc;
   static const bool no_gemm = getenv("AICAM_APPEARANCE_ROWS") != nullptr;
-  const int gemm_ok = (d.F % AG_KC == 0 && !no_gemm) ? 1 : 0;
-  const size_t sm = std::max((APP_DT * d.F + 8 * APP_DT) * sizeof(float), gemm_ok ? AG_SMEM : size_t(0));
+  // 0: row kernel for every frame; 1: fp32 FFMA tiling for crowded frames; 2: crowded frames are left to the
+  // tensor-core kernel launched below (their blocks return at once here)
+  const int gemm_ok = tf ? 2 : ((d.F % AG_KC == 0 && !no_gemm) ? 1 : 0);
+  const size_t sm = std::max((APP_DT * d.F + 8 * APP_DT) * sizeof(float), gemm_ok == 1 ? AG_SMEM : size_t(0));
   if (int rc = ensure_dynamic_smem(appearance_kernel, sm)) return rc;
   appearance_kernel<<<dim3(d.T, d.S), 256, sm, st>>>(d, det_count, crop_slot, stride_k, gemm_ok);
   count_launch();
-  return last_launch("appearance_kernel");
+  if (int rc = last_launch("appearance_kernel")) return rc;
+  if (tf)
+    return launch_appearance_tf32(tf, d.S, d.T, d.D, d.F, d.G, APP_GEMM_MIN, d.n_tracks, d.order, d.state, d.gal_count, det_count,
+                                  crop_slot, stride_k, d.app_cost, st);
+  return AICAM_OK;
 }
 }  // namespace
 
@@ -866,7 +903,23 @@ int aicam_tracker_create(const aicam_tracker_config* cfg, aicam_tracker** out) {
   rc |= dev_alloc(t, &d.overflow, d.S);
   rc |= dev_alloc(t, &d.app_cost, ST * d.D); rc |= dev_alloc(t, &d.cost_ws, ST * d.D);
   rc |= dev_alloc(t, &d.featn, static_cast<size_t>(d.S) * d.D * d.F);
+  d.gal_hi = d.gal_lo = d.featn_hi = d.featn_lo = nullptr;
+  static const bool no_tf32 = getenv("AICAM_APPEARANCE_NO_TF32") != nullptr;
+  // frames can only be crowded when the detection capacity allows it: the split copies cost 2 x the gallery memory
+  const bool want_tf = !no_tf32 && d.D > APP_GEMM_MIN && appearance_tf32_eligible(d.S, d.F, d.G, d.D);
+  if (want_tf) {
+    rc |= dev_alloc(t, &d.gal_hi, ST * d.G * d.F + static_cast<size_t>(128) * d.F);  // (+ slack: the last tile's masked rows)
+    rc |= dev_alloc(t, &d.gal_lo, ST * d.G * d.F + static_cast<size_t>(128) * d.F);
+    rc |= dev_alloc(t, &d.featn_hi, static_cast<size_t>(d.S) * d.D * d.F);
+    rc |= dev_alloc(t, &d.featn_lo, static_cast<size_t>(d.S) * d.D * d.F);
+  }
   if (rc) { aicam_tracker_destroy(t); return AICAM_ERR_CUDA; }
+  if (want_tf) {
+    if (int r3 = appearance_tf32_create(&t->tf, d.S, d.T, d.D, d.F, d.G, d.gal_hi, d.gal_lo, d.featn_hi, d.featn_lo)) {
+      aicam_tracker_destroy(t);
+      return r3;
+    }
+  }
   const size_t sm = assoc_smem(d.T, d.D);
   if (sm > 200 * 1024) { aicam_tracker_destroy(t); return fail(AICAM_ERR_CAPACITY, "tracker_create: max_tracks/max_dets need too much shared memory"); }
   // (the > 48 KB opt-ins are made per launch in aicam_tracker_step: a running maximum per device, so that trackers of
@@ -881,6 +934,7 @@ void aicam_tracker_destroy(aicam_tracker* t) {
   if (!t) return;
   cudaSetDevice(t->cfg.device);
   for (void* p : t->allocs) cudaFree(p);
+  if (t->tf) appearance_tf32_destroy(t->tf);
   delete t;
 }
 
@@ -901,7 +955,7 @@ int aicam_tracker_step(aicam_tracker* t, const float* boxes, const float* scores
   const Dev& d = t->d;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (feats) {
-    if (int rc = launch_appearance(d, det_count, crop_slot, stride_k, feats, st)) return rc;
+    if (int rc = launch_appearance(d, t->tf, det_count, crop_slot, stride_k, feats, st)) return rc;
   }
   StepIO io{boxes, scores, labels, stride_k, det_index, det_count, crop_slot, out_tracks, out_conf, out_count, 0, feats ? 1 : 0};
   const size_t asm_bytes = assoc_smem(d.T, d.D, &io.cm_in_smem);
@@ -920,7 +974,7 @@ int aicam_tracker_cost_probe(aicam_tracker* t, const float* boxes, int stride_k,
     return fail(AICAM_ERR_INVALID_ARG, "tracker_cost_probe: stride_k must be positive and boxes 16-byte aligned");
   const Dev& d = t->d;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (int rc = launch_appearance(d, det_count, crop_slot, stride_k, feats, st)) return rc;
+  if (int rc = launch_appearance(d, t->tf, det_count, crop_slot, stride_k, feats, st)) return rc;
   cost_probe_kernel<<<dim3(d.T, d.S), 128, 0, st>>>(d, boxes, stride_k, det_index, det_count, app_cost, gate_d2, track_ids, n_tracks);
   count_launch();
   return last_launch("cost_probe_kernel");
