@@ -88,6 +88,7 @@ SIGNATURES = {
     "aicam_conv2d": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "aicam_conv2d_padded": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _I, _I, _P]),
     "aicam_conv_chain": (_I, [C.POINTER(ChainDesc), _P, C.POINTER(_P), C.POINTER(_P), _P, _P]),
+    "aicam_conv_chain_bench": (_I, [C.POINTER(ChainDesc), _I, C.POINTER(C.c_double), _P]),
     "aicam_conv2d_bench": (_I, [C.POINTER(ConvDesc), _I, C.POINTER(C.c_double), _P]),
     "aicam_reid_stem_pool": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "aicam_letterbox_params": (_I, [_I, _I, C.POINTER(Letterbox)]),

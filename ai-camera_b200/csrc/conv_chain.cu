@@ -51,7 +51,13 @@ constexpr int MAX_SLOTS = 16;
 constexpr int MAX_RING = 4;
 constexpr int MAX_PIECES = 6;
 constexpr size_t SMEM_LIMIT = 227 * 1024;
-constexpr uint32_t OFF_DATA = 2048;
+constexpr int MAX_OPS = 288;               // MMA instructions of one 128-row chunk, summed over the stages
+constexpr int MAX_GROUPS = 48;             // MMA groups (chunks issued together) per tile
+constexpr uint32_t OFF_ST = 1040;         // shared-memory copies of the stage / buffer descriptors (indexed constant-bank
+constexpr uint32_t OFF_BUF = 1840;        //   loads miss the constant cache once the parameters exceed a few KB)
+constexpr uint32_t OFF_OPS = 2048;        // the op table (16 bytes per op)
+constexpr uint32_t OFF_GROUPS = OFF_OPS + MAX_OPS * 16;  // the group table (32 bytes per group)
+constexpr uint32_t OFF_DATA = 8192;
 constexpr size_t RESIDENT_LIMIT = 72 * 1024;
 constexpr uint32_t RING_SLOT_MAX = 32 * 1024;
 
@@ -73,7 +79,18 @@ struct ChainSrcD {
   int shift;             // rows to add to the output row for tap (0, 0)
   int wk8;               // first K chunk (8 channels) of this source inside a tap's weight block
 };
+// One tcgen05.mma of a chunk, precomputed on the host (the issue loop is one 16-byte shared-memory load + a few adds per MMA):
+//   A descriptor low word = sbase / 16 + a_off + chunk * a_step (+ the patch's second buffer), high word a_hi;
+//   B descriptor low word = b_off (+ the ring slot's address / 16 when the weights are streamed).
+struct ChainOpD {
+  uint32_t a_off;    // ((buffer offset + slab offset + tap / shift rows) >> 4) + K offset inside the slab + LBO flag
+  uint32_t a_step;   // bits 0-15: 128 rows in 16-byte units; bit 31: reads the patch (buffer 0); bits 16-27: ops in the weight stage
+                     // this op starts (0: not the first op of a stage)
+  uint32_t a_hi;
+  uint32_t b_off;    // (byte offset >> 4) | N << 16
+};
 struct ChainStageD {
+  int op0, nops;
   int ksize, taps, nsrc;
   ChainSrcD src[2];
   int k8_per_tap;
@@ -107,8 +124,17 @@ struct ChainArgs {
   int npieces, out_es;
   int piece_start[MAX_PIECES], piece_bytes[MAX_PIECES], piece_map[MAX_PIECES], piece_c0[MAX_PIECES];
   uint32_t piece_off[MAX_PIECES];
+  long long* trace;
+  int ngroups;
   float4 bias4[128];
+  ChainOpD ops[MAX_OPS];
+  // MMA groups of one tile in issue order, 8 words each: op0 | nops << 16;  first chunk | chunks << 8 | flags << 24 (bit 0: the
+  // patch is free after this group);  idesc;  number of READY barriers to wait for;  then their indices, one byte each
+  uint32_t groups[MAX_GROUPS * 8];
 };
+static_assert(sizeof(ChainStageD) * CHAIN_MAX_STAGES <= OFF_BUF - OFF_ST, "stage descriptors do not fit their shared-memory area");
+static_assert(sizeof(ChainBufD) * MAX_BUFS <= OFF_OPS - OFF_BUF, "buffer descriptors do not fit their shared-memory area");
+static_assert(OFF_GROUPS + MAX_GROUPS * 32 <= OFF_DATA, "tables overlap the data area");
 struct ChainMaps {
   CUtensorMap in;
   CUtensorMap out[3];  // 128- / 64- / 32-byte channel pieces of an output row
@@ -156,6 +182,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// debug trace of CTA 0 (AICAM_CONV_TRACE in aicam_conv_chain_bench): six tracing threads (MMA lane 0, thread 0 of each epilogue
+// warpgroup, store-warp lane 0) own 600 (id, clock) slots each; the event count is kept in a register (tr_n)
+#define CH_TRACE(kind, id)                                                                   \
+  do {                                                                                       \
+    if (tr_role >= 0 && tr_n < 600) {                                                        \
+      a.trace[(tr_role * 600 + tr_n) * 2] = (static_cast<long long>(kind) << 32) | static_cast<long long>(id); \
+      a.trace[(tr_role * 600 + tr_n) * 2 + 1] = clock64();                                   \
+      ++tr_n;                                                                                \
+    }                                                                                        \
+  } while (0)
+
 struct TileXY {
   int n, x0, y0;
 };
@@ -176,6 +213,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = a.batch * a.tiles_per_img;
+  int tr_role = -1, tr_n = 0;
+  if (a.trace && blockIdx.x == 0) {
+    if (threadIdx.x < 128 * NWG && (threadIdx.x & 127) == 0) tr_role = 1 + (threadIdx.x >> 7);
+    else if (threadIdx.x == 128 * NWG) tr_role = 0;
+    else if (threadIdx.x == 128 * NWG + 96) tr_role = 5;
+  }
   pdl_trigger();
   if (static_cast<int>(blockIdx.x) >= total_tiles) return;
 
@@ -198,6 +241,21 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const __grid_
     for (int s = 0; s < MAX_BUFS * MAX_CHUNKS; ++s) mbar_init(sbase + BAR_READY + 8 * s, 128);
     mbar_init_fence();
   }
+  {  // descriptors and tables: constant bank -> shared memory
+    const int nops_total = a.st[a.nstages - 1].op0 + a.st[a.nstages - 1].nops;
+    uint4* dst = reinterpret_cast<uint4*>(smem + OFF_OPS);
+    for (int i = threadIdx.x; i < nops_total; i += CH_THREADS) dst[i] = make_uint4(a.ops[i].a_off, a.ops[i].a_step, a.ops[i].a_hi, a.ops[i].b_off);
+    uint32_t* gdst = reinterpret_cast<uint32_t*>(smem + OFF_GROUPS);
+    for (int i = threadIdx.x; i < a.ngroups * 8; i += CH_THREADS) gdst[i] = a.groups[i];
+    uint32_t* sdst = reinterpret_cast<uint32_t*>(smem + OFF_ST);
+    const uint32_t* ssrc = reinterpret_cast<const uint32_t*>(a.st);
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(ChainStageD) * CHAIN_MAX_STAGES / 4); i += CH_THREADS) sdst[i] = ssrc[i];
+    uint32_t* bdst = reinterpret_cast<uint32_t*>(smem + OFF_BUF);
+    const uint32_t* bsrc = reinterpret_cast<const uint32_t*>(a.buf);
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(ChainBufD) * MAX_BUFS / 4); i += CH_THREADS) bdst[i] = bsrc[i];
+  }
+  const ChainStageD* st_s = reinterpret_cast<const ChainStageD*>(smem + OFF_ST);
+  const ChainBufD* buf_s = reinterpret_cast<const ChainBufD*>(smem + OFF_BUF);
   if (warp == 4 * NWG) tc_alloc(smem_u32(tmem_ptr_smem), 512);
   if (warp == 4 * NWG + 1 && lane == 0) tma_prefetch_desc(&maps.in);
   if (warp == 4 * NWG + 3 && lane == 0) tma_prefetch_desc(&maps.out[0]);
@@ -212,6 +270,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const __grid_
     const int rloc = wq * 32 + lane;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
     int it = 0;
+    int e_slot = 0, e_wg = 0;  // accumulator slot / owning warpgroup of the running chunk index
+    uint32_t e_ph = 0;
+    const int nslot = a.nslot;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const TileXY t = tile_xy(a, tile);
       const int p0buf = a.p0_nbuf == 2 ? (it & 1) : 0;
@@ -220,16 +281,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const __grid_
       // residual rows are read from the patch with ordinary loads: observe the TMA's completion barrier myself
       if (a.p0_res_readers) mbar_wait(sbase + BAR_P0_FULL + 8 * p0buf, a.p0_nbuf == 2 ? ((it >> 1) & 1) : (it & 1));
       for (int s = 0; s < a.nstages; ++s) {
-        const ChainStageD& S = a.st[s];
+        const ChainStageD& S = st_s[s];
         const bool last = S.dst_buf < 0;
         const int ngroups = S.n_pad >> 4;
         for (int k = 0; k < S.nchunks; ++k) {
-          const int gidx = it * a.chunks_per_tile + S.chunk0 + k;
-          if ((gidx & (NWG - 1)) != wg) continue;  // another warpgroup's chunk
-          const int slot = gidx % a.nslot;
-          const uint32_t ph = static_cast<uint32_t>(gidx / a.nslot) & 1u;
+          const int slot = e_slot;
+          const uint32_t ph = e_ph;
+          const bool mine = e_wg == wg;
+          if (++e_slot == nslot) { e_slot = 0; e_ph ^= 1; }
+          e_wg = (e_wg + 1) & (NWG - 1);
+          if (!mine) continue;  // another warpgroup's chunk
           mbar_wait(sbase + BAR_ACC_FULL + 8 * slot, ph);
           tc_fence_after();
+          CH_TRACE(4, (it << 16) | (s << 8) | k);
           const int q = k * 128 + rloc;
           const int yl = __float2int_rd((static_cast<float>(q) + 0.5f) * a.inv_rw);
           const int xl = q - yl * a.rw;
@@ -239,7 +303,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const __grid_
           uint32_t d_row = 0, d_xor = 0, d_stride = 0;
           int d_shift = 0;
           if (!last) {
-            const ChainBufD& D = a.buf[S.dst_buf];
+            const ChainBufD& D = buf_s[S.dst_buf];
             const uint32_t ro = static_cast<uint32_t>(q) * D.row_bytes;
             d_row = D.off + ro;
             d_xor = ((ro >> 7) & D.xor_mask) << 4;
@@ -250,7 +314,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const __grid_
           uint32_t r_row = 0, r_xor = 0, r_stride = 0;
           int r_shift = 0;
           if (S.res_mode) {
-            const ChainBufD& R = a.buf[S.res_buf];
+            const ChainBufD& R = buf_s[S.res_buf];
             const uint32_t ro = static_cast<uint32_t>(q + S.res_shift) * R.row_bytes;
             r_row = R.off + (S.res_buf == 0 ? p0buf * a.p0_stride : 0u) + ro;
             r_xor = ((ro >> 7) & R.xor_mask) << 4;
@@ -351,6 +415,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const __grid_
             fence_proxy_async();
             mbar_arrive(sbase + BAR_READY + 8 * (S.dst_buf * MAX_CHUNKS + k));
           }
+          CH_TRACE(5, (it << 16) | (s << 8) | k);
         }
       }
       fence_proxy_async();  // staging writes -> visible to the TMA unit
@@ -363,81 +428,76 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const __grid_
     const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t b_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, no swizzle
     uint32_t rs = 0, rp = 0;                         // weight ring slot / parity
-    if (a.resident) mbar_wait(sbase + BAR_W_FULL, 0);
+    const int nslot = a.nslot, resident = a.resident, ngroups = a.ngroups;
+    const uint32_t ns = static_cast<uint32_t>(a.ns), sbase16 = sbase >> 4;
+    int slot0 = 0;       // accumulator slot of the next chunk to issue; its "drained" parity
+    uint32_t sph = 1;
+    if (resident) mbar_wait(sbase + BAR_W_FULL, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int p0buf = a.p0_nbuf == 2 ? (it & 1) : 0;
       const uint32_t p0par = a.p0_nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
       mbar_wait(sbase + BAR_P0_FULL + 8 * p0buf, p0par);
       tc_fence_after();
-      int waited[MAX_BUFS];
-#pragma unroll
-      for (int b = 0; b < MAX_BUFS; ++b) waited[b] = 0;
-      for (int s = 0; s < a.nstages; ++s) {
-        const ChainStageD& S = a.st[s];
-        const uint32_t lbo = static_cast<uint32_t>(S.n_pad);
-        for (int g0 = 0; g0 < S.nchunks; g0 += S.group) {
-          const int g1 = min(g0 + S.group, S.nchunks);
-          const int gbase = it * a.chunks_per_tile + S.chunk0;
-          for (int k = g0; k < g1; ++k) {  // the accumulator slots of the group have been drained
-            const int gi = gbase + k;
-            mbar_wait(sbase + BAR_ACC_EMPTY + 8 * (gi % a.nslot), (static_cast<uint32_t>(gi / a.nslot) & 1u) ^ 1u);
+      CH_TRACE(8, it << 16);
+      const uint32_t p0add = (static_cast<uint32_t>(p0buf) * a.p0_stride) >> 4;
+      const uint4* gtab = reinterpret_cast<const uint4*>(smem + OFF_GROUPS);
+      for (int gi = 0; gi < ngroups; ++gi) {
+        const uint4 gd = gtab[2 * gi], gw = gtab[2 * gi + 1];
+        const int nops = static_cast<int>(gd.x >> 16), k0 = static_cast<int>(gd.y & 255u), nk = static_cast<int>((gd.y >> 8) & 255u);
+        const uint32_t idesc = gd.z;
+        CH_TRACE(1, (it << 16) | gi);
+        {  // the accumulator slots of the group have been drained
+          int sl = slot0;
+          uint32_t ph = sph;
+          for (int k = 0; k < nk; ++k) {
+            mbar_wait(sbase + BAR_ACC_EMPTY + 8 * sl, ph);
+            if (++sl == nslot) { sl = 0; ph ^= 1; }
           }
-          // every row this group reads from a stage-written buffer has been published
-          for (int j = 0; j < S.nsrc; ++j) {
-            const int b = S.src[j].buf;
-            if (b == 0) continue;
-            const int reach = g1 * 128 + S.src[j].shift + (S.ksize - 1) * (a.rw + 1);
-            const int need = min(a.buf[b].nchunks, (reach + 127) >> 7);
-#pragma unroll
-            for (int bb = 1; bb < MAX_BUFS; ++bb)
-              if (bb == b)
-                while (waited[bb] < need) {
-                  mbar_wait(sbase + BAR_READY + 8 * (bb * MAX_CHUNKS + waited[bb]), it & 1);
-                  ++waited[bb];
-                }
-          }
-          tc_fence_after();
-          for (int tap = 0; tap < S.taps; ++tap) {
-            const int dy = tap / S.ksize, dx = tap - dy * S.ksize;
-            for (int j = 0; j < S.nsrc; ++j) {
-              const ChainSrcD& src = S.src[j];
-              const ChainBufD& B = a.buf[src.buf];
-              const uint32_t bufbase = sbase + B.off + (src.buf == 0 ? p0buf * a.p0_stride : 0u);
-              const int row_tap = src.shift + dy * a.rw + dx;
-              for (int sub0 = 0; sub0 < src.nc16; sub0 += S.gs) {
-                const int sub1 = min(sub0 + S.gs, src.nc16);
-                uint32_t b_base;
-                if (a.resident) {
-                  b_base = sbase + a.w_off + S.w_smem_off + static_cast<uint32_t>(tap * S.k8_per_tap + src.wk8 + sub0 * 2) * lbo * 16;
-                } else {
-                  mbar_wait(sbase + BAR_B_FULL + 8 * rs, rp);
-                  tc_fence_after();
-                  b_base = sbase + a.ring_off + rs * a.ring_slot_bytes;
-                }
-                const uint32_t b_lo0 = (b_base >> 4) | (lbo << 16);
-                const bool first_k = tap == 0 && j == 0 && sub0 == 0;
-                for (int k = g0; k < g1; ++k) {
-                  const uint32_t d_tmem = tmem0 + static_cast<uint32_t>(((gbase + k) % a.nslot) * a.ns);
-                  const uint32_t row = static_cast<uint32_t>(k * 128 + row_tap);
-                  for (int c = sub0; c < sub1; ++c) {
-                    const int c16 = src.c16_0 + c;
-                    const uint32_t a_addr = bufbase + static_cast<uint32_t>(c16 >> B.c16_shift) * B.slab_stride + row * B.row_bytes;
-                    const uint32_t a_lo = (a_addr >> 4) + static_cast<uint32_t>(c16 & ((1 << B.c16_shift) - 1)) * 2 + (1u << 16);
-                    mma_issue(leader, d_tmem, a_lo, B.a_hi, b_lo0 + static_cast<uint32_t>(c - sub0) * 2 * lbo, b_hi, S.idesc,
-                              (first_k && c == sub0) ? 0u : 1u);
-                  }
-                }
-                if (!a.resident) {
-                  tc_commit_if(leader, sbase + BAR_B_EMPTY + 8 * rs);
-                  if (++rs == static_cast<uint32_t>(a.ring_n)) { rs = 0; rp ^= 1; }
-                }
-              }
-            }
-          }
-          for (int k = g0; k < g1; ++k) tc_commit_if(leader, sbase + BAR_ACC_FULL + 8 * ((gbase + k) % a.nslot));
         }
-        if (S.p0_last) tc_commit_if(leader, sbase + BAR_P0_EMPTY + 8 * p0buf);
+        // every row this group reads from a stage-written buffer has been published
+        for (int w = 0; w < static_cast<int>(gd.w); ++w) {
+          const uint32_t word = w < 4 ? gw.x : (w < 8 ? gw.y : (w < 12 ? gw.z : gw.w));
+          mbar_wait(sbase + BAR_READY + 8 * ((word >> (8 * (w & 3))) & 255u), it & 1);
+        }
+        tc_fence_after();
+        CH_TRACE(2, (it << 16) | gi);
+        {
+          const uint4* ops = reinterpret_cast<const uint4*>(smem + OFF_OPS) + (gd.x & 0xffffu);
+          int i = 0;
+          while (i < nops) {
+            const int run = static_cast<int>((ops[i].y >> 16) & 0xfffu);
+            uint32_t b_base16 = sbase16;  // resident weights: b_off is relative to the start of shared memory
+            if (!resident) {
+              mbar_wait(sbase + BAR_B_FULL + 8 * rs, rp);
+              tc_fence_after();
+              b_base16 = (sbase + a.ring_off + rs * a.ring_slot_bytes) >> 4;
+            }
+            int sl = slot0;
+            for (int k = 0; k < nk; ++k) {
+              const uint32_t d_tmem = tmem0 + static_cast<uint32_t>(sl) * ns;
+              const uint32_t kk = static_cast<uint32_t>(k0 + k);
+#pragma unroll 4
+              for (int r = 0; r < run; ++r) {
+                const uint4 op = ops[i + r];
+                const uint32_t a_lo = sbase16 + op.x + kk * (op.y & 0xffffu) + ((op.y >> 31) ? p0add : 0u);
+                mma_issue(leader, d_tmem, a_lo, op.z, b_base16 + op.w, b_hi, idesc, (i + r) != 0 ? 1u : 0u);
+              }
+              if (++sl == nslot) sl = 0;
+            }
+            if (!resident) {
+              tc_commit_if(leader, sbase + BAR_B_EMPTY + 8 * rs);
+              if (++rs == static_cast<uint32_t>(a.ring_n)) { rs = 0; rp ^= 1; }
+            }
+            i += run;
+          }
+        }
+        for (int k = 0; k < nk; ++k) {
+          tc_commit_if(leader, sbase + BAR_ACC_FULL + 8 * slot0);
+          if (++slot0 == nslot) { slot0 = 0; sph ^= 1; }
+        }
+        if (gd.y >> 24) tc_commit_if(leader, sbase + BAR_P0_EMPTY + 8 * p0buf);
+        CH_TRACE(3, (it << 16) | gi);
       }
     }
     tc_fence_before();
@@ -445,7 +505,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const __grid_
     // ================================================================== patch producer
     if (lane == 0) {
       pdl_wait();  // the patch is the previous layer's output
-      const ChainBufD& B = a.buf[0];
+      const ChainBufD& B = buf_s[0];
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const TileXY t = tile_xy(a, tile);
@@ -467,7 +527,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const __grid_
         for (int s = 0; s < a.nstages; ++s) total += static_cast<uint32_t>(a.st[s].taps * a.st[s].k8_per_tap * a.st[s].n_pad * 16);
         mbar_arrive_expect_tx(sbase + BAR_W_FULL, total);
         for (int s = 0; s < a.nstages; ++s) {
-          const ChainStageD& S = a.st[s];
+          const ChainStageD& S = st_s[s];
           const uint32_t bytes = static_cast<uint32_t>(S.taps * S.k8_per_tap * S.n_pad * 16);
           const uint8_t* srcp = reinterpret_cast<const uint8_t*>(S.w_gmem);
           for (uint32_t off = 0; off < bytes; off += 16384)
@@ -477,7 +537,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const __grid_
         uint32_t rs = 0, rp = 1;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
           for (int s = 0; s < a.nstages; ++s) {
-            const ChainStageD& S = a.st[s];
+            const ChainStageD& S = st_s[s];
             for (int g0 = 0; g0 < S.nchunks; g0 += S.group)
               for (int tap = 0; tap < S.taps; ++tap)
                 for (int j = 0; j < S.nsrc; ++j)
@@ -502,6 +562,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const __grid_
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const TileXY t = tile_xy(a, tile);
       mbar_wait(sbase + BAR_TILE_DONE, it & 1);
+      CH_TRACE(6, it << 16);
       if (lane == 0) {
         for (int p = 0; p < a.npieces; ++p)
           tma_store_4d(&maps.out[a.piece_map[p]], sbase + a.stage_off + a.piece_off[p], a.piece_c0[p], t.x0, t.y0, t.n);
@@ -510,6 +571,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const __grid_
         mbar_arrive(sbase + BAR_STAGE_FREE);
       }
       __syncwarp();
+      CH_TRACE(7, it << 16);
     }
     if (lane == 0) bulk_wait_all();
   }
@@ -730,6 +792,7 @@ int try_launch_conv_chain(const ChainSpec& sp, cudaStream_t stream) {
   a.resident = resident ? 1 : 0;
   a.ns = ns_cols; a.nslot = nslot;
   a.out_es = es;
+  a.trace = sp.trace;
   uint32_t off = OFF_DATA;
   for (int b = 0; b < ns_; ++b) {
     ChainBufD& B = a.buf[b];
@@ -812,7 +875,10 @@ int try_launch_conv_chain(const ChainSpec& sp, cudaStream_t stream) {
     D.dst_buf = s + 1 < ns_ ? s + 1 : -1;
     D.margin = st_margin[s];
     D.nchunks = best.nchunks[s];
-    D.group = resident ? 1 : D.nchunks;
+    // chunks issued per commit: every commit exposes ~700 cycles of tensor-pipe latency to the issuing warp (measured), so a
+    // stage is issued as few groups as the accumulator slots allow (AICAM_CHAIN_GROUP overrides it for resident weights)
+    static const int group_env = getenv("AICAM_CHAIN_GROUP") ? atoi(getenv("AICAM_CHAIN_GROUP")) : 0;
+    D.group = resident ? std::max(1, std::min(group_env > 0 ? group_env : D.nchunks, nslot)) : D.nchunks;
     D.chunk0 = chunk0;
     chunk0 += D.nchunks;
     D.bias4_off = bias_off / 4;
@@ -825,6 +891,79 @@ int try_launch_conv_chain(const ChainSpec& sp, cudaStream_t stream) {
   a.chunks_per_tile = chunk0;
   if (last_p0_stage < 0) return 0;
   a.st[last_p0_stage].p0_last = 1;
+  // ---- the op table: every MMA of one chunk, stage by stage, in issue order (tap, source, 16-channel group); a weight
+  // stage (streamed form) is a run of ops that share one ring slot
+  {
+    int nops = 0;
+    for (int s = 0; s < ns_; ++s) {
+      ChainStageD& D = a.st[s];
+      D.op0 = nops;
+      const uint32_t lbo = static_cast<uint32_t>(D.n_pad);
+      for (int tap = 0; tap < D.taps; ++tap) {
+        const int dy = tap / D.ksize, dx = tap % D.ksize;
+        for (int j = 0; j < D.nsrc; ++j) {
+          const ChainSrcD& src = D.src[j];
+          const ChainBufD& B = a.buf[src.buf];
+          for (int c = 0; c < src.nc16; ++c) {
+            if (nops >= MAX_OPS) return 0;
+            const int c16 = src.c16_0 + c;
+            const uint32_t addr = B.off + static_cast<uint32_t>(c16 >> B.c16_shift) * B.slab_stride +
+                                  static_cast<uint32_t>(src.shift + dy * best.rw + dx) * B.row_bytes;
+            ChainOpD& op = a.ops[nops];
+            op.a_off = (addr >> 4) + static_cast<uint32_t>(c16 & ((1 << B.c16_shift) - 1)) * 2 + (1u << 16);
+            op.a_step = (128 * B.row_bytes) >> 4;
+            if (src.buf == 0) op.a_step |= 1u << 31;
+            op.a_hi = B.a_hi;
+            const int sub0 = (c / D.gs) * D.gs;  // first group of this op's weight stage
+            if (resident) {
+              const uint32_t wb = a.w_off + D.w_smem_off + static_cast<uint32_t>(tap * D.k8_per_tap + src.wk8 + c * 2) * lbo * 16;
+              op.b_off = (wb >> 4) | (lbo << 16);
+              if (nops == D.op0) op.a_step |= static_cast<uint32_t>(D.taps * D.k8_per_tap / 2) << 16;  // one run: the whole stage
+            } else {
+              op.b_off = ((static_cast<uint32_t>(c - sub0) * 2 * lbo * 16) >> 4) | (lbo << 16);
+              if (c == sub0) op.a_step |= static_cast<uint32_t>(std::min(D.gs, src.nc16 - sub0)) << 16;
+            }
+            ++nops;
+          }
+        }
+      }
+      D.nops = nops - D.op0;
+      if (D.nops > 0xfff) return 0;
+    }
+  }
+  // ---- the group table: which READY barriers each group waits for is static (the consumer's reach into each source
+  // buffer, minus what earlier groups of the tile have already waited for)
+  {
+    int waited[MAX_BUFS] = {0};
+    int ng = 0;
+    for (int s = 0; s < ns_; ++s) {
+      const ChainStageD& D = a.st[s];
+      for (int g0 = 0; g0 < D.nchunks; g0 += D.group) {
+        if (ng >= MAX_GROUPS) return 0;
+        const int g1 = std::min(g0 + D.group, D.nchunks);
+        uint32_t* G = a.groups + ng * 8;
+        std::memset(G, 0, 32);
+        G[0] = static_cast<uint32_t>(D.op0) | (static_cast<uint32_t>(D.nops) << 16);
+        G[1] = static_cast<uint32_t>(g0) | (static_cast<uint32_t>(g1 - g0) << 8) | ((D.p0_last && g1 == D.nchunks) ? (1u << 24) : 0u);
+        G[2] = D.idesc;
+        int nwait = 0;
+        for (int j = 0; j < D.nsrc; ++j) {
+          const int b = D.src[j].buf;
+          if (b == 0) continue;
+          const int reach = g1 * 128 + D.src[j].shift + (D.ksize - 1) * (best.rw + 1);
+          const int need = std::min(a.buf[b].nchunks, (reach + 127) >> 7);
+          for (; waited[b] < need; ++waited[b]) {
+            if (nwait >= 16) return 0;
+            G[4 + nwait / 4] |= static_cast<uint32_t>(b * MAX_CHUNKS + waited[b]) << (8 * (nwait % 4));
+            ++nwait;
+          }
+        }
+        G[3] = static_cast<uint32_t>(nwait);
+        ++ng;
+      }
+    }
+    a.ngroups = ng;
+  }
 
   // ---- tensor maps
   alignas(64) ChainMaps maps;
@@ -933,5 +1072,100 @@ extern "C" int aicam_conv_chain(const aicam_chain_desc* d, const void* in_nhwc, 
   for (int s = 0; s < made; ++s) free_packed_conv(&pcs[s]);
   if (rc) return rc;
   if (se != cudaSuccess) return fail(AICAM_ERR_CUDA, std::string("conv_chain: ") + cudaGetErrorString(se));
+  return AICAM_OK;
+}
+
+// Micro-benchmark of one fused chain on device-resident pseudo-random data (weights included): `iters` launches bracketed
+// by CUDA events.  AICAM_CONV_TRACE=1 prints the event trace of CTA 0 of one extra launch.
+extern "C" int aicam_conv_chain_bench(const aicam_chain_desc* d, int iters, double* mean_ms, void* stream) {
+  if (!d || !mean_ms || iters <= 0) return fail(AICAM_ERR_INVALID_ARG, "conv_chain_bench: bad arguments");
+  if (d->nstages < 2 || d->nstages > CHAIN_MAX_STAGES) return fail(AICAM_ERR_INVALID_ARG, "conv_chain_bench: 2 to 5 stages");
+  std::vector<PackedConv> pcs(d->nstages);
+  ChainSpec sp;
+  sp.nstages = d->nstages;
+  int rc = AICAM_OK, made = 0;
+  uint32_t seed = 12345u;
+  for (int s = 0; s < d->nstages && !rc; ++s) {
+    const aicam_chain_stage& S = d->st[s];
+    std::vector<float> w(static_cast<size_t>(S.cout) * S.cin * S.ksize * S.ksize), b(S.cout, 0.1f);
+    for (auto& v : w) { seed = seed * 1664525u + 1013904223u; v = (static_cast<int>(seed >> 16) % 2001 - 1000) * 1e-4f; }
+    rc = pack_conv_weights(w.data(), b.data(), S.cout, S.cin, S.ksize, 1, &pcs[s]);
+    if (rc) break;
+    ++made;
+    ChainStageSpec& T = sp.st[s];
+    T.pc = &pcs[s];
+    T.act = S.act; T.nsrc = S.nsrc;
+    for (int j = 0; j < 2; ++j) { T.src_buf[j] = S.src_buf[j]; T.src_coff[j] = S.src_coff[j]; T.src_c[j] = S.src_c[j]; }
+    T.res_buf = S.res_mode ? S.res_buf : -1; T.res_coff = S.res_coff; T.res_mode = S.res_mode;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* in = nullptr;
+  void* out = nullptr;
+  float ms = 0.0f;
+  if (!rc) {
+    const int cl = d->st[d->nstages - 1].cout;
+    const size_t in_elems = static_cast<size_t>(d->batch) * d->h * d->w * d->in_c, out_elems = static_cast<size_t>(d->batch) * d->h * d->w * cl;
+    if (cudaMalloc(&in, in_elems * 2) != cudaSuccess || cudaMalloc(&out, out_elems * (d->out_f32 ? 4 : 2)) != cudaSuccess) rc = fail(AICAM_ERR_CUDA, "conv_chain_bench: cudaMalloc failed");
+    if (!rc) {
+      cudaMemset(in, 0x3c, in_elems * 2);
+      sp.in = in; sp.in_cstride = d->in_c; sp.in_coff = 0; sp.in_c = d->in_c;
+      sp.in_img_stride = static_cast<long long>(d->h) * d->w * d->in_c;
+      sp.batch = d->batch; sp.h = d->h; sp.w = d->w;
+      sp.out = out; sp.out_cstride = cl; sp.out_coff = 0; sp.out_f32 = d->out_f32;
+      sp.out_img_stride = static_cast<long long>(d->h) * d->w * cl;
+      for (int i = 0; i < 3 && !rc; ++i) {
+        const int lrc = try_launch_conv_chain(sp, st);
+        if (lrc < 0) rc = lrc;
+        else if (lrc == 0) rc = fail(AICAM_ERR_UNSUPPORTED, "conv_chain_bench: this chain / geometry is not eligible for the fused kernel");
+      }
+      if (!rc && getenv("AICAM_CONV_TRACE")) {
+        long long* tr = nullptr;
+        const size_t tr_words = 6 * 600 * 2;
+        cudaMalloc(&tr, 8 * tr_words);
+        cudaMemset(tr, 0, 8 * tr_words);
+        sp.trace = tr;
+        try_launch_conv_chain(sp, st);
+        cudaStreamSynchronize(st);
+        sp.trace = nullptr;
+        std::vector<long long> h(tr_words);
+        cudaMemcpy(h.data(), tr, 8 * tr_words, cudaMemcpyDeviceToHost);
+        cudaFree(tr);
+        struct Ev { long long t, id; int role; };
+        std::vector<Ev> ev;
+        for (int r = 0; r < 6; ++r)
+          for (int i = 0; i < 600; ++i)
+            if (h[(r * 600 + i) * 2 + 1]) ev.push_back({h[(r * 600 + i) * 2 + 1], h[(r * 600 + i) * 2], r});
+        std::sort(ev.begin(), ev.end(), [](const Ev& x, const Ev& y) { return x.t < y.t; });
+        static const char* names[] = {"?", "mma_begin", "mma_deps_ok", "mma_issued", "epi_acc_full", "epi_done", "store_tile_done", "store_read_done", "mma_p0_full"};
+        static const char* roles[] = {"MMA", "WG0", "WG1", "WG2", "WG3", "STORE"};
+        printf("chain trace of CTA 0 (%zu events): cycles since the first event, role, kind, tile.stage.chunk\n", ev.size());
+        const int max_ev = getenv("AICAM_TRACE_EVENTS") ? atoi(getenv("AICAM_TRACE_EVENTS")) : 240;
+        for (size_t i = 0; i < ev.size() && static_cast<int>(i) < max_ev; ++i) {
+          const long long id = ev[i].id & 0xffffffffll, kind = ev[i].id >> 32;
+          printf("  %8lld %-5s %-15s %lld.%lld.%lld\n", ev[i].t - ev[0].t, roles[ev[i].role], names[kind < 9 ? kind : 0], id >> 16, (id >> 8) & 255, id & 255);
+        }
+        fflush(stdout);
+      }
+      if (!rc) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < iters && !rc; ++i) {
+          const int lrc = try_launch_conv_chain(sp, st);
+          if (lrc < 0) rc = lrc;
+        }
+        cudaEventRecord(e1, st);
+        const cudaError_t se = cudaStreamSynchronize(st);
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (!rc && se != cudaSuccess) rc = fail(AICAM_ERR_CUDA, std::string("conv_chain_bench: ") + cudaGetErrorString(se));
+      }
+    }
+  }
+  if (in) cudaFree(in);
+  if (out) cudaFree(out);
+  for (int s = 0; s < made; ++s) free_packed_conv(&pcs[s]);
+  if (rc) return rc;
+  *mean_ms = ms / iters;
   return AICAM_OK;
 }

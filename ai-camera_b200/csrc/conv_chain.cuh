@@ -32,6 +32,7 @@ struct ChainSpec {
   void* out = nullptr;                // NHWC bf16 or fp32 (channel slice [out_coff, out_coff + cout_last) of out_cstride)
   long long out_img_stride = 0;
   int out_cstride = 0, out_coff = 0, out_f32 = 0;
+  long long* trace = nullptr;         // debug: event trace of CTA 0 (aicam_conv_chain_bench)
 };
 
 // 1: launched, 0: this chain / geometry is not eligible (the caller launches the layers one by one), < 0: error

@@ -172,6 +172,8 @@ typedef struct {
 } aicam_chain_desc;
 int aicam_conv_chain(const aicam_chain_desc* d, const void* in_nhwc, const float* const* weights_oihw,
                      const float* const* bias, void* out_nhwc, void* stream);
+/* Micro-benchmark of one such chain on device-resident pseudo-random data (like aicam_conv2d_bench). */
+int aicam_conv_chain_bench(const aicam_chain_desc* d, int iters, double* mean_ms, void* stream);
 /* The fused ReID stem on its own (test entry): Conv3x3(3->64, s1, p1) + bias + ReLU + MaxPool(3, s2, p1),
  * the first two layers of the ReID engine (reid_model.py:115).
  *   in_nhwc4 : bf16 [n][h][w][4] (h, w even)   weights_oihw : fp32 host [64][3][3][3]   bias : fp32 host [64]

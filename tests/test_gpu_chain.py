@@ -68,7 +68,7 @@ CASES = [
     ("head128_64_64", 2, 40, 40, head(128, 64, 64)),
     ("head128_80_80", 3, 40, 40, head(128, 80, 80)),
     ("head256_64_64", 3, 20, 20, head(256, 64, 64)),
-    ("head256_80_80", 5, 20, 20, head(256, 80, 80)),
+    ("head256_64_80", 5, 20, 20, head(256, 64, 80)),
     ("tiny_7x9", 1, 7, 9, pair(32)),
     ("one_row", 2, 1, 33, pair(16)),
 ]
@@ -147,3 +147,19 @@ def test_chain_matches_torch(case):
     assert not bad.any(), "%s: %d/%d elements off, max abs err %.4g at %s (got %.5g want %.5g)" % (
         name, bad.sum(), bad.size, err.max(), np.unravel_index(err.argmax(), err.shape),
         got.flat[err.argmax()], want.flat[err.argmax()])
+
+
+def test_engine_with_fused_chains_matches_oracle():
+    """The detector engine built with its chains fused (AICAM_CHAIN=1: Bottleneck pairs, C2f tails, Detect-head
+    branches as single launches) must pass the same oracle comparison as the default single-layer engine; the switch is
+    read when the engine is built, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AICAM_CHAIN="1", AICAM_CHAIN_DEBUG="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_engine.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "yolov8n_head or yolov8_s_m", "-p", "no:cacheprovider", "-s"], env=env, capture_output=True, text=True, cwd=root)
+    tail = (r.stdout + r.stderr)[-2000:]
+    assert r.returncode == 0, tail
+    assert "conv_chain:" in r.stderr + r.stdout, "the engine did not launch any fused chain\n" + tail
