@@ -10,8 +10,8 @@
 // Appendix C).  This file spells those sequences out and is compiled with --fmad=false, so
 // no product-sum is contracted.  The assignment follows scipy's rectangular LSAP step by
 // step in float64 (oracle/lsap.py): the column scan is spread over
-// the 32 lanes of one warp, and the (value, first position, last unassigned position)
-// reduction reproduces the sequential tie rule exactly.  The only value that is NOT
+// one warp (small problems) or the whole CTA, and the (value, first position, last unassigned
+// position) reduction reproduces the sequential tie rule exactly.  The only value that is NOT
 // bit-reproducible is the cosine distance (a BLAS sgemm in the reference): parity there is
 // a tolerance, and assignments are bit-exact given the same cost matrix.
 //
@@ -45,7 +45,7 @@ namespace {
 constexpr int TENTATIVE = 1, CONFIRMED = 2, DELETED = 3;  // track.py:10-14
 constexpr float INFTY_COST = 1e5f;                         // linear_assignment.py:9
 constexpr float CHI2_GATE = 9.487729036781154f;            // kalman_filter.py:16, compared in float32
-constexpr int ASSOC_THREADS = 128;
+constexpr int ASSOC_THREADS = 256;
 
 struct Dev {
   int S, T, D, F, G;
@@ -182,73 +182,198 @@ __device__ __forceinline__ float iou_cost(const float a[4], const float c[4]) {
   return 1.0f - iou;
 }
 
-// ---- warp-level rectangular LSAP (scipy _lsap) -------------------------------------------------
+// ---- rectangular LSAP (scipy _lsap) on one warp or on the whole CTA ------------------------------
 struct LsapMem {
+  double* wmn; int* wf; int* wlu;  // cross-warp reduction slots, [2 parities][4 warps]
   double* u; double* v; double* spc;
   int* path; int* col4row; int* row4col; int* remaining;
   unsigned char* SR; unsigned char* SC;
 };
+constexpr int LSAP_MAX_WARPS = 4;
+constexpr int LSAP_WIDE = 48;  // problems with more columns than this are scanned by LSAP_MAX_WARPS warps
 
+// minimum over the warp of a non-NaN double in two redux.sync steps: the bit pattern is mapped to an unsigned key whose
+// order is the order of the values (-0.0 sorts below +0.0; the callers only compare the result with ==, which does not
+// tell them apart), high word first, then the low word among the lanes that hold the minimal high word
 __device__ __forceinline__ double warp_min_d(double x) {
-  for (int o = 16; o > 0; o >>= 1) x = fmin(x, __shfl_xor_sync(0xffffffffu, x, o));
-  return x;
+  unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
+  b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+  const unsigned hi = static_cast<unsigned>(b >> 32), lo = static_cast<unsigned>(b);
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  unsigned long long mb = (static_cast<unsigned long long>(mhi) << 32) | mlo;
+  mb = (mb >> 63) ? (mb & 0x7fffffffffffffffull) : ~mb;
+  return __longlong_as_double(static_cast<long long>(mb));
 }
 
-// cost(r, c) = cost[r * ld + c] for r < nr, c < nc.  Writes col_for_row[r] (or -1) for r < nr.
-// Must be called by one full warp; every array lives in shared memory.
-__device__ void lsap_warp(const float* cost, int ld, int nr, int nc, const LsapMem& m, int* col_for_row, int lane) {
+// cost(r, c) = cost[rmap[r] * ld + cmap[c]] (identity maps when null) for r < nr, c < nc.  Writes col_for_row[r] (or -1)
+// for r < nr.  Called by the first nw warps of the CTA (tid < 32 nw; nw = 1: warp-synchronous, nw > 1: named barrier 1); every array
+// lives in shared memory.  The column scan of the augmenting-path search - scipy's sequential loop over `remaining` - is
+// strided over the threads; each keeps (lowest value, first position holding it, last UNASSIGNED position holding it),
+// positions packed with their column as (position << 10 | column), and the reduction over lanes and warps reproduces the
+// sequential tie rule exactly: the last unassigned column among the minima if there is one, else the first minimum.
+// The thread that owns position `index` performs scipy's swap-removal itself, so one barrier per iteration suffices.
+__device__ void lsap_cta(const float* cost, int ld, int nr, int nc, const LsapMem& m, int* col_for_row, int tid, int nw,
+                         const int* rmap = nullptr, const int* cmap = nullptr) {
+  const int nth = nw * 32, lane = tid & 31, warp = tid >> 5;
+  auto sync = [&]() {
+    if (nw == 1) __syncwarp();
+    else asm volatile("bar.sync 1, %0;" ::"r"(nth) : "memory");
+  };
   const bool tr = nc < nr;  // scipy transposes so that rows <= cols
   const int R = tr ? nc : nr, C = tr ? nr : nc;
-  const int si = tr ? 1 : ld, sj = tr ? ld : 1;
-  for (int i = lane; i < R; i += 32) { m.u[i] = 0.0; m.col4row[i] = -1; }
-  for (int j = lane; j < C; j += 32) { m.v[j] = 0.0; m.row4col[j] = -1; m.path[j] = -1; }
-  __syncwarp();
+  // element (i, j) of the (possibly transposed) problem
+  auto at = [&](int i, int j) {
+    const int r = tr ? j : i, c = tr ? i : j;
+    return cost[static_cast<long long>(rmap ? rmap[r] : r) * ld + (cmap ? cmap[c] : c)];
+  };
+  if (R == 1) {
+    // One row (a cascade level that holds one track, or one detection left): the search above scans `remaining`, i.e.
+    // the columns in DESCENDING order, all of them unassigned, and keeps the last minimum it meets = the minimal cost at
+    // the smallest column index; the float64 arithmetic reduces to the cost itself.  Warp 0 finds it with two redux steps.
+    if (warp == 0) {
+      float best = __int_as_float(0x7f800000);
+      int bj = 0x7fffffff;
+      for (int j = lane; j < C; j += 32) {
+        const float c = at(0, j);
+        if (c < best) { best = c; bj = j; }
+      }
+      unsigned kb = __float_as_uint(best);
+      kb = (kb >> 31) ? ~kb : (kb | 0x80000000u);
+      const unsigned mk = __reduce_min_sync(0xffffffffu, kb);
+      // (== on the values, not on the keys: -0.0f and 0.0f are one minimum)
+      const float mv = __uint_as_float((mk >> 31) ? (mk & 0x7fffffffu) : ~mk);
+      const int j = __reduce_min_sync(0xffffffffu, best == mv ? bj : 0x7fffffff);
+      for (int r = lane; r < nr; r += 32) col_for_row[r] = -1;
+      __syncwarp();
+      if (lane == 0) col_for_row[tr ? j : 0] = tr ? 0 : j;
+      __syncwarp();
+    }
+    sync();
+    return;
+  }
+  if (C <= 32) {
+    // Up to 32 columns: the whole state lives in registers of warp 0 - lane j holds column j (v, shortest path cost,
+    // path, row4col, its position in scipy's `remaining` array) and lane i holds row i (u, col4row, SR).  Same search,
+    // same float64 arithmetic, same tie rule (positions instead of a scanned array: the swap-removal moves the column at
+    // the last position to `index`); no shared-memory traffic but the cost element.
+    if (warp == 0) {
+      const double inf = __longlong_as_double(0x7ff0000000000000ll);
+      const bool is_col = lane < C, is_row = lane < R;
+      // loop-invariant half of the element address
+      const int fix_c = is_col ? (tr ? (rmap ? rmap[lane] : lane) * ld : (cmap ? cmap[lane] : lane)) : 0;
+      double u = 0.0, v = 0.0;
+      int col4row = -1, row4col = -1, path = -1;
+      for (int cur = 0; cur < R; ++cur) {
+        double spc = inf, min_val = 0.0;
+        bool SC = false, SR = false;
+        int pos = C - 1 - lane, i = cur, num_remaining = C, sink = -1;
+        while (sink == -1) {
+          if (lane == i) SR = true;
+          const double ui = __shfl_sync(0xffffffffu, u, i);
+          const int var_i = tr ? (cmap ? cmap[i] : i) : (rmap ? rmap[i] : i) * ld;
+          const bool active = is_col && !SC;
+          if (active) {
+            const double r = ((min_val + static_cast<double>(cost[fix_c + var_i])) - ui) - v;
+            if (r < spc) { path = i; spc = r; }
+          }
+          const double sv = active ? spc : inf;
+          const double mn = warp_min_d(sv);
+          const bool ismin = active && sv == mn;
+          const int f = __reduce_min_sync(0xffffffffu, ismin ? pos : 0x7fffffff);
+          const int lu = __reduce_max_sync(0xffffffffu, (ismin && row4col == -1) ? pos : -1);
+          const int index = lu >= 0 ? lu : f;
+          const int jl = __ffs(__ballot_sync(0xffffffffu, active && pos == index)) - 1;
+          const int owner = __shfl_sync(0xffffffffu, row4col, jl);
+          min_val = mn;
+          if (owner == -1) sink = jl; else i = owner;
+          if (active && pos == num_remaining - 1) pos = index;  // remaining[index] = remaining[--num_remaining]
+          if (lane == jl) SC = true;
+          --num_remaining;
+        }
+        // dual variables (rows in SR other than cur are assigned: col4row is a lane)
+        const double spc_of_mine = __shfl_sync(0xffffffffu, spc, col4row < 0 ? 0 : col4row);
+        if (lane == cur) u += min_val;
+        else if (is_row && SR) u += min_val - spc_of_mine;
+        if (SC) v -= min_val - spc;
+        // augment along the path
+        for (int j = sink;;) {
+          const int ii = __shfl_sync(0xffffffffu, path, j);
+          if (lane == j) row4col = ii;
+          const int nxt = __shfl_sync(0xffffffffu, col4row, ii);
+          if (lane == ii) col4row = j;
+          j = nxt;
+          if (ii == cur) break;
+        }
+      }
+      for (int r = lane; r < nr; r += 32) col_for_row[r] = -1;
+      __syncwarp();
+      if (is_row) col_for_row[tr ? col4row : lane] = tr ? lane : col4row;
+      __syncwarp();
+    }
+    sync();
+    return;
+  }
+  for (int i = tid; i < R; i += nth) { m.u[i] = 0.0; m.col4row[i] = -1; }
+  for (int j = tid; j < C; j += nth) { m.v[j] = 0.0; m.row4col[j] = -1; m.path[j] = -1; }
+  sync();
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  int par = 0;
   for (int cur = 0; cur < R; ++cur) {
-    for (int j = lane; j < C; j += 32) { m.spc[j] = inf; m.SC[j] = 0; m.remaining[j] = C - 1 - j; }
-    for (int i = lane; i < R; i += 32) m.SR[i] = 0;
-    __syncwarp();
+    for (int j = tid; j < C; j += nth) { m.spc[j] = inf; m.SC[j] = 0; m.remaining[j] = C - 1 - j; }
+    for (int i = tid; i < R; i += nth) m.SR[i] = 0;
+    sync();
     double min_val = 0.0;
     int i = cur, num_remaining = C, sink = -1;
     while (sink == -1) {
-      if (lane == 0) m.SR[i] = 1;
+      if (tid == 0) m.SR[i] = 1;
       const double ui = m.u[i];
-      const float* crow = cost + static_cast<long long>(i) * si;
       double lowest = inf;
-      int first_it = 0x7fffffff, last_un = -1;
-      for (int it = lane; it < num_remaining; it += 32) {
+      int first_key = 0x7fffffff, last_un = -1;
+      for (int it = tid; it < num_remaining; it += nth) {
         const int j = m.remaining[it];
-        const double r = ((min_val + static_cast<double>(crow[static_cast<long long>(j) * sj])) - ui) - m.v[j];
+        const double r = ((min_val + static_cast<double>(at(i, j))) - ui) - m.v[j];
         double sv = m.spc[j];
         if (r < sv) { m.path[j] = i; m.spc[j] = r; sv = r; }
         const bool unassigned = m.row4col[j] == -1;
-        if (sv < lowest) { lowest = sv; first_it = it; last_un = unassigned ? it : -1; }
-        else if (sv == lowest && unassigned) { last_un = it; }
+        const int key = (it << 10) | j;
+        if (sv < lowest) { lowest = sv; first_key = key; last_un = unassigned ? key : -1; }
+        else if (sv == lowest && unassigned) { last_un = key; }
       }
-      const double mn = warp_min_d(lowest);
-      int f = (lowest == mn) ? first_it : 0x7fffffff;
-      int lu = (lowest == mn) ? last_un : -1;
-      for (int o = 16; o > 0; o >>= 1) {
-        f = min(f, __shfl_xor_sync(0xffffffffu, f, o));
-        lu = max(lu, __shfl_xor_sync(0xffffffffu, lu, o));
+      double mn = warp_min_d(lowest);
+      int f = __reduce_min_sync(0xffffffffu, lowest == mn ? first_key : 0x7fffffff);
+      int lu = __reduce_max_sync(0xffffffffu, lowest == mn ? last_un : -1);
+      if (nw > 1) {
+        if (lane == 0) { m.wmn[par * LSAP_MAX_WARPS + warp] = mn; m.wf[par * LSAP_MAX_WARPS + warp] = f; m.wlu[par * LSAP_MAX_WARPS + warp] = lu; }
+        sync();
+        double g = m.wmn[par * LSAP_MAX_WARPS];
+        for (int w = 1; w < nw; ++w) g = fmin(g, m.wmn[par * LSAP_MAX_WARPS + w]);
+        f = 0x7fffffff; lu = -1;
+        for (int w = 0; w < nw; ++w)
+          if (m.wmn[par * LSAP_MAX_WARPS + w] == g) { f = min(f, m.wf[par * LSAP_MAX_WARPS + w]); lu = max(lu, m.wlu[par * LSAP_MAX_WARPS + w]); }
+        mn = g;
+        par ^= 1;
       }
-      const int index = lu >= 0 ? lu : f;
+      const int key = lu >= 0 ? lu : f;
+      const int index = key >> 10, j = key & 1023;
       min_val = mn;
-      const int j = m.remaining[index];
       const int owner = m.row4col[j];
-      __syncwarp();
       if (owner == -1) sink = j; else i = owner;
-      if (lane == 0) { m.SC[j] = 1; m.remaining[index] = m.remaining[num_remaining - 1]; }
+      // scipy: remaining[index] = remaining[--num_remaining].  Position `index` is scanned by thread index % nth, which
+      // does the swap; the moved element was last written before this iteration's barrier
+      if (index % nth == tid) m.remaining[index] = m.remaining[num_remaining - 1];
+      if (tid == 0) m.SC[j] = 1;
       --num_remaining;
-      __syncwarp();
+      if (nw == 1) __syncwarp();
     }
-    if (lane == 0) m.u[cur] += min_val;
-    for (int i2 = lane; i2 < R; i2 += 32)
+    sync();
+    if (tid == 0) m.u[cur] += min_val;
+    for (int i2 = tid; i2 < R; i2 += nth)
       if (m.SR[i2] && i2 != cur) m.u[i2] += min_val - m.spc[m.col4row[i2]];
-    for (int j2 = lane; j2 < C; j2 += 32)
+    for (int j2 = tid; j2 < C; j2 += nth)
       if (m.SC[j2]) m.v[j2] -= min_val - m.spc[j2];
-    __syncwarp();
-    if (lane == 0) {
+    sync();
+    if (tid == 0) {
       int j = sink;
       for (;;) {
         const int ii = m.path[j];
@@ -259,21 +384,24 @@ __device__ void lsap_warp(const float* cost, int ld, int nr, int nc, const LsapM
         if (ii == cur) break;
       }
     }
-    __syncwarp();
+    sync();
   }
-  for (int r = lane; r < nr; r += 32) col_for_row[r] = -1;
-  __syncwarp();
-  if (tr) { for (int k = lane; k < R; k += 32) col_for_row[m.col4row[k]] = k; }
-  else    { for (int k = lane; k < R; k += 32) col_for_row[k] = m.col4row[k]; }
-  __syncwarp();
+  for (int r = tid; r < nr; r += nth) col_for_row[r] = -1;
+  sync();
+  if (tr) { for (int k = tid; k < R; k += nth) col_for_row[m.col4row[k]] = k; }
+  else    { for (int k = tid; k < R; k += nth) col_for_row[k] = m.col4row[k]; }
+  sync();
 }
 
+__host__ __device__ inline int lsap_warps(int nr, int nc) { return (nr > nc ? nr : nc) > LSAP_WIDE ? LSAP_MAX_WARPS : 1; }
+
 __host__ __device__ inline size_t lsap_bytes(int n) {
-  return (static_cast<size_t>(n) * (3 * 8 + 4 * 4 + 2) + 64 + 15) / 16 * 16;
+  return (128 + static_cast<size_t>(n) * (3 * 8 + 4 * 4 + 2) + 64 + 15) / 16 * 16;
 }
 __device__ inline LsapMem lsap_carve(uint8_t* p, int n) {
   LsapMem m;
-  m.u = reinterpret_cast<double*>(p); m.v = m.u + n; m.spc = m.v + n;
+  m.wmn = reinterpret_cast<double*>(p); m.wf = reinterpret_cast<int*>(m.wmn + 2 * LSAP_MAX_WARPS); m.wlu = m.wf + 2 * LSAP_MAX_WARPS;
+  m.u = reinterpret_cast<double*>(p + 128); m.v = m.u + n; m.spc = m.v + n;
   m.path = reinterpret_cast<int*>(m.spc + n); m.col4row = m.path + n; m.row4col = m.col4row + n;
   m.remaining = m.row4col + n;
   m.SR = reinterpret_cast<unsigned char*>(m.remaining + n); m.SC = m.SR + n;
@@ -473,9 +601,34 @@ struct StepIO {
   const int* det_index; const int* det_count; const int* crop_slot;
   int* out_tracks; float* out_conf; int* out_count;
   int cm_in_smem;  // the T x D cost matrix fits in shared memory (else the per-stream global workspace)
+  long long* trace;  // debug (AICAM_ASSOC_TRACE): clock64 stamps of stream 0's CTA, see aicam_tracker_destroy
   int has_feats;   // 0: the frame carries no features at all (feats == NULL): every appearance cost is INFTY_COST and
                    // nothing is appended to the galleries, as in the reference when every Detection.feature is None
 };
+
+// one normalised detection feature (and its TF32 split copies) -> a gallery row, by one warp.  Feature rows are 16-byte
+// aligned when F is a multiple of 4; all loads are issued before the first store (the compiler cannot hoist them itself:
+// the pointers may alias), so a row costs one memory round trip instead of F / 32.
+__device__ __forceinline__ void copy_feature_row(const Dev& t, long long go, long long so, int lane) {
+  const int F = t.F;
+  const int nsrc = t.gal_hi ? 3 : 1;
+  for (int a = 0; a < nsrc; ++a) {
+    const float* src = (a == 0 ? t.featn : a == 1 ? t.featn_hi : t.featn_lo) + so;
+    float* dst = (a == 0 ? t.gallery : a == 1 ? t.gal_hi : t.gal_lo) + go;
+    if (F % 128 == 0 && F <= 1024) {
+      float4 v[8];
+      const int n4 = F / 128;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < n4) v[i] = reinterpret_cast<const float4*>(src)[lane + 32 * i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < n4) reinterpret_cast<float4*>(dst)[lane + 32 * i] = v[i];
+    } else {
+      for (int f = lane; f < F; f += 32) dst[f] = src[f];
+    }
+  }
+}
 
 // K7 + K9-K12: predict, cascade, IoU stage, update, initiate, prune, output.  One CTA per stream.
 __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) {
@@ -487,7 +640,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
   float* d_tlwh = reinterpret_cast<float*>(p); p += sizeof(float) * 4 * Dm;
   float* d_xyah = reinterpret_cast<float*>(p); p += sizeof(float) * 4 * Dm;
   int* U = reinterpret_cast<int*>(p); p += sizeof(int) * Dm;          // unmatched detections, ordered
-  int* Utmp = reinterpret_cast<int*>(p); p += sizeof(int) * Dm;
+  int* Utmp = reinterpret_cast<int*>(p); p += sizeof(int) * max(T, Dm);  // (also the costs of a one-column problem)
   int* conf_list = reinterpret_cast<int*>(p); p += sizeof(int) * T;   // order positions of confirmed tracks
   int* tent_list = reinterpret_cast<int*>(p); p += sizeof(int) * T;
   int* L = reinterpret_cast<int*>(p); p += sizeof(int) * T;           // rows of the current problem (order positions)
@@ -500,16 +653,26 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
   int* st_state = reinterpret_cast<int*>(p); p += sizeof(int) * T;
   int* st_tsu = reinterpret_cast<int*>(p); p += sizeof(int) * T;
   p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~static_cast<uintptr_t>(15));
+  // predicted (x, y, a, h) and the four position variances per track-list position: all the gate and the IoU cost read
+  float4* st_mean4 = reinterpret_cast<float4*>(p); p += sizeof(float4) * T;
+  float4* st_cov4 = reinterpret_cast<float4*>(p); p += sizeof(float4) * T;
+  int* fstack = reinterpret_cast<int*>(p); p += sizeof(int) * T;     // the stream's free-slot stack (written back at the end)
+  int* gpos = reinterpret_cast<int*>(p); p += sizeof(int) * T;       // gallery row a matched track appends to, or -1
+  p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~static_cast<uintptr_t>(15));
   const int nmax = max(T, Dm);
   LsapMem lm = lsap_carve(p, nmax);
   p += lsap_bytes(nmax);
-  __shared__ int s_nconf, s_ntent, s_nU, s_nL, s_levels[8], s_nt;
+  __shared__ int s_nconf, s_ntent, s_nU, s_nL, s_levels[8], s_nt, s_nfree1;
 
+#define ASSOC_STAMP(i) do { if (io.trace && s == 0 && tid == 0) io.trace[i] = clock64(); } while (0)
+  ASSOC_STAMP(0);
   const long long sb = static_cast<long long>(s) * T;
   int nt = t.n_tracks[s];
   int nd = io.det_count[s];
   if (nd > Dm) { nd = Dm; if (tid == 0) atomicOr(&t.overflow[s], 2); }
   int* order = t.order + sb;
+  const int nfree0 = t.n_free[s];
+  for (int k = tid; k < nfree0; k += ASSOC_THREADS) fstack[k] = t.free_slots[sb + k];
 
   // -- K7 predict (tracker_core.py:44-49, track.py:76-80)
   for (int k = tid; k < nt; k += ASSOC_THREADS) {
@@ -525,6 +688,8 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
     const int tsu = t.tsu[ts] + 1;
     t.tsu[ts] = tsu;
     ord[k] = slot;
+    st_mean4[k] = make_float4(mean[0], mean[1], mean[2], mean[3]);
+    st_cov4[k] = make_float4(cov[0], cov[1], cov[2], cov[3]);
     st_tsu[k] = tsu;
     st_state[k] = t.state[ts];
     match[k] = -1;
@@ -539,143 +704,217 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
     U[k] = k;
     det_used[k] = 0;
   }
-  if (tid < 8) s_levels[tid] = 0;
   __syncthreads();
-  // -- confirmed / tentative lists in track-list order (tracker_core.py:112-117)
-  if (tid == 0) {
+  // -- confirmed / tentative lists in track-list order (tracker_core.py:112-117): ballot compaction by warp 0
+  if (warp == 0) {
     int nc = 0, nn = 0;
-    for (int k = 0; k < nt; ++k) {
-      if (st_state[k] == CONFIRMED) {
-        conf_list[nc++] = k;
+    unsigned lv_bits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b0 = 0; b0 < nt; b0 += 32) {
+      const int k = b0 + lane;
+      const int st = k < nt ? st_state[k] : 0;
+      const unsigned bc = __ballot_sync(0xffffffffu, st == CONFIRMED), bt = __ballot_sync(0xffffffffu, st == TENTATIVE);
+      const unsigned below = (1u << lane) - 1u;
+      if (st == CONFIRMED) {
+        conf_list[nc + __popc(bc & below)] = k;
         const int lv = st_tsu[k];
-        if (lv >= 1 && lv <= t.max_age && lv < 256) s_levels[lv >> 5] |= 1u << (lv & 31);
-      } else if (st_state[k] == TENTATIVE) {
-        tent_list[nn++] = k;
+        if (lv >= 1 && lv <= t.max_age && lv < 256) lv_bits[lv >> 5] |= 1u << (lv & 31);
+      } else if (st == TENTATIVE) {
+        tent_list[nn + __popc(bt & below)] = k;
       }
+      nc += __popc(bc); nn += __popc(bt);
     }
-    s_nconf = nc; s_ntent = nn; s_nU = nd;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const unsigned all = __reduce_or_sync(0xffffffffu, lv_bits[w]);
+      if (lane == 0) s_levels[w] = all;
+    }
+    if (lane == 0) { s_nconf = nc; s_ntent = nn; s_nU = nd; }
   }
   __syncthreads();
+  ASSOC_STAMP(1);
 
   float* cm = io.cm_in_smem ? reinterpret_cast<float*>(p) : t.cost_ws + static_cast<long long>(s) * T * Dm;
-  // One matching problem: rows L[0..nL), columns U[0..nU); metric 0 = gated appearance, 1 = IoU.
-  auto solve = [&](int metric, float thr, float clamp) {
-    const int nL = s_nL, nU = s_nU;
-    for (int idx = tid; idx < nL * nU; idx += ASSOC_THREADS) {
-      const int i = idx / nU, j = idx - i * nU;
-      const long long ts = sb + ord[L[i]];
-      const int d = U[j];
-      float c;
-      if (metric == 0) {
-        c = io.has_feats ? t.app_cost[ts * Dm + d] : INFTY_COST;
-        // linear_assignment.py:160-212: gate by the squared Mahalanobis distance (4 dof, strict >)
-        const float g = kf_gating(t.mean + ts * 8, t.cov + ts * 16, d_xyah + 4 * d, nU);
-        if (g > CHI2_GATE) c = INFTY_COST;
-      } else {
-        float tl[4];
-        mean_to_tlwh(t.mean + ts * 8, tl);
-        c = iou_cost(tl, d_tlwh + 4 * d);
-      }
-      if (c > thr) c = clamp;  // linear_assignment.py:58
-      cm[idx] = c;
-    }
-    __syncthreads();
-    if (warp == 0) lsap_warp(cm, nU, nL, nU, lm, cfr, lane);
-    __syncthreads();
-    // linear_assignment.py:64-88: keep pairs with cost <= max_distance, unmatched lists keep their order
-    for (int i = tid; i < nL; i += ASSOC_THREADS) {
-      const int j = cfr[i];
-      if (j >= 0 && cm[i * nU + j] <= thr) { match[L[i]] = U[j]; det_used[U[j]] = 1; }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int n = 0;
-      for (int j = 0; j < nU; ++j)
-        if (!det_used[U[j]]) Utmp[n++] = U[j];
-      for (int j = 0; j < n; ++j) U[j] = Utmp[j];
-      s_nU = n;
-    }
-    __syncthreads();
+  const int nconf = s_nconf;
+  // gated appearance cost of one (track position, detection) pair (linear_assignment.py:160-212: the squared Mahalanobis
+  // distance gates with a strict >; n_meas selects the reference's BLAS path, see kf_gating), thresholded (:58)
+  auto gated_cost = [&](int pos, int d, int n_meas) {
+    float c = io.has_feats ? t.app_cost[(sb + ord[pos]) * Dm + d] : INFTY_COST;
+    const float4 m4 = st_mean4[pos], c4 = st_cov4[pos];
+    const float mean4[4] = {m4.x, m4.y, m4.z, m4.w}, cov4[4] = {c4.x, c4.y, c4.z, c4.w};
+    if (kf_gating(mean4, cov4, d_xyah + 4 * d, n_meas) > CHI2_GATE) c = INFTY_COST;
+    return c > t.thr_cos ? t.clamp_cos : c;
   };
-
-  // -- stage 1: matching cascade over confirmed tracks (linear_assignment.py:91-157)
-  for (int level = 1; level <= t.max_age; ++level) {
-    if (level < 256 && !((s_levels[level >> 5] >> (level & 31)) & 1u)) continue;  // no track at this level
-    if (s_nU == 0) break;
-    if (tid == 0) {
-      int n = 0;
-      for (int k = 0; k < s_nconf; ++k)
-        if (st_tsu[conf_list[k]] == level) L[n++] = conf_list[k];
-      s_nL = n;
+  // unmatched detections keep their order (linear_assignment.py:64-88): in-place compaction of U by warp 0
+  auto compact_U = [&](int nU) {
+    int n = 0;
+    for (int b0 = 0; b0 < nU; b0 += 32) {
+      const int j = b0 + lane;
+      const int d = j < nU ? U[j] : 0;
+      const bool keep = j < nU && !det_used[d];
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();
+      if (keep) U[n + __popc(bal & ((1u << lane) - 1u))] = d;
+      n += __popc(bal);
     }
-    __syncthreads();
-    if (s_nL > 0) solve(0, t.thr_cos, t.clamp_cos);
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0) s_nU = n;
+  };
+  // -- stage 1: matching cascade over confirmed tracks (linear_assignment.py:91-157).  The cost of every (confirmed
+  //    track, detection) pair is computed ONCE, by track-list position; a level's problem is the sub-matrix (rows L,
+  //    columns U) read in place through the two index lists.  Levels that hold no track are skipped through the bitmap.
+  //    Frames whose problems all fit one warp run the whole cascade on warp 0 without a block barrier.
+  for (int idx = tid; idx < nconf * nd; idx += ASSOC_THREADS) {
+    const int i = idx / nd, d = idx - i * nd;
+    const int pos = conf_list[i];
+    cm[pos * nd + d] = gated_cost(pos, d, 2);
   }
+  __syncthreads();
+  {
+    const bool small = max(nconf, nd) <= LSAP_WIDE;
+    const int cth = small ? 32 : ASSOC_THREADS;
+    auto csync = [&]() { if (small) __syncwarp(); else __syncthreads(); };
+    float* colv = reinterpret_cast<float*>(Utmp);  // (a one-column problem's costs: nL <= T floats, see the carve-up)
+    if (!small || warp == 0) {
+      int level = 0, nU = nd;
+      for (;;) {
+        for (++level; level <= t.max_age; ) {  // next level that holds a confirmed track
+          const unsigned wbits = s_levels[level >> 5] >> (level & 31);
+          if (wbits) { level += __ffs(wbits) - 1; break; }
+          level = (level | 31) + 1;
+        }
+        if (level > t.max_age || nU == 0) break;
+        if (warp == 0) {  // L = the level's tracks in track-list order
+          int n = 0;
+          for (int b0 = 0; b0 < nconf; b0 += 32) {
+            const int k = b0 + lane;
+            const int pos = k < nconf ? conf_list[k] : 0;
+            const bool keep = k < nconf && st_tsu[pos] == level;
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) L[n + __popc(bal & ((1u << lane) - 1u))] = pos;
+            n += __popc(bal);
+          }
+          if (lane == 0) s_nL = n;
+        }
+        csync();
+        const int nL = s_nL;
+        const bool one_col = nU == 1;  // the gate's n_meas == 1 form: computed here
+        if (one_col) {
+          for (int i = tid; i < nL; i += cth) colv[i] = gated_cost(L[i], U[0], 1);
+          csync();
+        }
+        const int nw = small ? 1 : lsap_warps(nL, nU);
+        const long long c0 = (io.trace && s == 0 && tid == 0) ? clock64() : 0;
+        if (warp < nw) {
+          if (one_col) lsap_cta(colv, 1, nL, 1, lm, cfr, tid, nw);
+          else lsap_cta(cm, nd, nL, nU, lm, cfr, tid, nw, L, U);
+        }
+        csync();
+        if (io.trace && s == 0 && tid == 0) { io.trace[10] += clock64() - c0; io.trace[11] += 1; io.trace[12] += static_cast<long long>(nL) * 1024 + nU; }
+        for (int i = tid; i < nL; i += cth) {  // keep pairs with cost <= max_distance
+          const int j = cfr[i];
+          if (j < 0) continue;
+          const float c = one_col ? colv[i] : cm[L[i] * nd + U[j]];
+          if (c <= t.thr_cos) { match[L[i]] = U[j]; det_used[U[j]] = 1; }
+        }
+        csync();
+        if (warp == 0) compact_U(nU);
+        csync();
+        nU = s_nU;
+      }
+    }
+  }
+  __syncthreads();
+  ASSOC_STAMP(2);
   // -- stage 2: IoU matching (tracker_core.py:138-166)
   if (tid == 0) {
     int n = 0;
     for (int k = 0; k < s_ntent; ++k) L[n++] = tent_list[k];
-    for (int k = 0; k < s_nconf; ++k) {
+    for (int k = 0; k < nconf; ++k) {
       const int pos = conf_list[k];
       if (match[pos] < 0 && st_tsu[pos] == 1) L[n++] = pos;
     }
     s_nL = n;
   }
   __syncthreads();
-  if (s_nL > 0 && s_nU > 0) solve(1, t.thr_iou, t.clamp_iou);
+  if (s_nL > 0 && s_nU > 0) {
+    const int nL = s_nL, nU = s_nU;
+    for (int idx = tid; idx < nL * nU; idx += ASSOC_THREADS) {
+      const int i = idx / nU, j = idx - i * nU;
+      const float4 m4 = st_mean4[L[i]];
+      const float mean4[4] = {m4.x, m4.y, m4.z, m4.w};
+      float tl[4];
+      mean_to_tlwh(mean4, tl);
+      const float c = iou_cost(tl, d_tlwh + 4 * U[j]);
+      cm[idx] = c > t.thr_iou ? t.clamp_iou : c;  // linear_assignment.py:58
+    }
+    __syncthreads();
+    const int nw = lsap_warps(nL, nU);
+    const long long c0 = (io.trace && s == 0 && tid == 0) ? clock64() : 0;
+    if (warp < nw) lsap_cta(cm, nU, nL, nU, lm, cfr, tid, nw);
+    __syncthreads();
+    if (io.trace && s == 0 && tid == 0) { io.trace[10] += clock64() - c0; io.trace[11] += 1; io.trace[12] += static_cast<long long>(nL) * 1024 + nU; }
+    for (int i = tid; i < nL; i += ASSOC_THREADS) {
+      const int j = cfr[i];
+      if (j >= 0 && cm[i * nU + j] <= t.thr_iou) { match[L[i]] = U[j]; det_used[U[j]] = 1; }
+    }
+    __syncthreads();
+    if (warp == 0) compact_U(nU);
+    __syncthreads();
+  }
+  ASSOC_STAMP(3);
 
-  // -- update matched tracks / mark missed (tracker_core.py:62-68, track.py:82-119)
-  for (int k = warp; k < nt; k += ASSOC_THREADS / 32) {
+  // -- update matched tracks / mark missed (tracker_core.py:62-68, track.py:82-119): the Kalman update and the scalar
+  //    fields one thread per track, then the gallery rows one warp per matched track
+  for (int k = tid; k < nt; k += ASSOC_THREADS) {
     const long long ts = sb + ord[k];
     const int d = match[k];
     if (d >= 0) {
-      const int row = io.has_feats ? io.crop_slot[static_cast<long long>(s) * io.stride_k + d] : -1;
-      if (row >= 0) {  // track.py:70-74: append to the gallery, FIFO at the budget
+      float mean[8], cov[16];
+      for (int i = 0; i < 8; ++i) mean[i] = t.mean[ts * 8 + i];
+      for (int i = 0; i < 16; ++i) cov[i] = t.cov[ts * 16 + i];
+      kf_update(mean, cov, d_xyah + 4 * d);
+      for (int i = 0; i < 8; ++i) t.mean[ts * 8 + i] = mean[i];
+      for (int i = 0; i < 16; ++i) t.cov[ts * 16 + i] = cov[i];
+      const long long o = static_cast<long long>(s) * io.stride_k + io.det_index[static_cast<long long>(s) * io.stride_k + d];
+      const int hits = t.hits[ts] + 1;
+      t.hits[ts] = hits;
+      t.tsu[ts] = 0;
+      st_tsu[k] = 0;
+      t.conf[ts] = io.scores[o];
+      t.cls[ts] = io.labels[o];
+      if (st_state[k] == TENTATIVE && hits >= t.n_init) { t.state[ts] = CONFIRMED; st_state[k] = CONFIRMED; }
+      // track.py:70-74: the feature is appended to the gallery, FIFO at the budget (rows copied below, one warp each)
+      int gp = -1;
+      if (io.has_feats && io.crop_slot[static_cast<long long>(s) * io.stride_k + d] >= 0) {
         const int cnt = t.gal_count[ts], head = t.gal_head[ts];
-        const int pos = cnt < t.G ? (head + cnt) % t.G : head;
-        const long long go = (ts * t.G + pos) * t.F, so = (static_cast<long long>(s) * Dm + d) * t.F;
-        for (int f = lane; f < t.F; f += 32) {
-          t.gallery[go + f] = t.featn[so + f];
-          if (t.gal_hi) { t.gal_hi[go + f] = t.featn_hi[so + f]; t.gal_lo[go + f] = t.featn_lo[so + f]; }
-        }
-        if (lane == 0) {
-          if (cnt < t.G) t.gal_count[ts] = cnt + 1; else t.gal_head[ts] = (head + 1) % t.G;
-        }
+        gp = cnt < t.G ? (head + cnt) % t.G : head;
+        if (cnt < t.G) t.gal_count[ts] = cnt + 1; else t.gal_head[ts] = (head + 1) % t.G;
       }
-      if (lane == 0) {
-        float mean[8], cov[16];
-        for (int i = 0; i < 8; ++i) mean[i] = t.mean[ts * 8 + i];
-        for (int i = 0; i < 16; ++i) cov[i] = t.cov[ts * 16 + i];
-        kf_update(mean, cov, d_xyah + 4 * d);
-        for (int i = 0; i < 8; ++i) t.mean[ts * 8 + i] = mean[i];
-        for (int i = 0; i < 16; ++i) t.cov[ts * 16 + i] = cov[i];
-        const long long o = static_cast<long long>(s) * io.stride_k + io.det_index[static_cast<long long>(s) * io.stride_k + d];
-        const int hits = t.hits[ts] + 1;
-        t.hits[ts] = hits;
-        t.tsu[ts] = 0;
-        st_tsu[k] = 0;
-        t.conf[ts] = io.scores[o];
-        t.cls[ts] = io.labels[o];
-        if (st_state[k] == TENTATIVE && hits >= t.n_init) { t.state[ts] = CONFIRMED; st_state[k] = CONFIRMED; }
-      }
-    } else if (lane == 0) {
-      if (st_state[k] == TENTATIVE || (st_state[k] == CONFIRMED && st_tsu[k] > t.max_age)) {
-        t.state[ts] = DELETED;
-        st_state[k] = DELETED;
-      }
+      gpos[k] = gp;
+    } else if (st_state[k] == TENTATIVE || (st_state[k] == CONFIRMED && st_tsu[k] > t.max_age)) {
+      t.state[ts] = DELETED;
+      st_state[k] = DELETED;
     }
   }
   __syncthreads();
+  if (io.has_feats) {
+    for (int k = warp; k < nt; k += ASSOC_THREADS / 32) {
+      const int d = match[k];
+      if (d < 0 || gpos[k] < 0) continue;
+      copy_feature_row(t, ((sb + ord[k]) * t.G + gpos[k]) * t.F, (static_cast<long long>(s) * Dm + d) * t.F, lane);
+    }
+  }
+  __syncthreads();
+  ASSOC_STAMP(4);
   // -- prune deleted tracks, then initiate one track per unmatched detection in ascending order
   //    (tracker_core.py:70-75, :180-194; ids come from the stream's own counter)
   if (tid == 0) {
     int n = 0;
-    int nfree = t.n_free[s];
+    int nfree = nfree0;
     for (int k = 0; k < nt; ++k) {
       const int slot = ord[k];
       if (st_state[k] == DELETED) {
-        t.free_slots[sb + nfree++] = slot;
+        fstack[nfree++] = slot;
       } else {  // compaction in place (n <= k)
         if (n != k) { order[n] = slot; ord[n] = slot; st_state[n] = st_state[k]; st_tsu[n] = st_tsu[k]; }
         ++n;
@@ -686,7 +925,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
     int next_id = t.next_id[s];
     for (int j = 0; j < nU; ++j) {
       if (nfree == 0) { atomicOr(&t.overflow[s], 1); break; }
-      const int slot = t.free_slots[sb + --nfree];
+      const int slot = fstack[--nfree];
       order[n] = slot; ord[n] = slot; st_state[n] = TENTATIVE; st_tsu[n] = 0;
       ++n;
       Utmp[created++] = slot;
@@ -701,18 +940,17 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
     t.n_tracks[s] = n;
     s_nt = n;
     s_nL = created;
+    s_nfree1 = nfree;
   }
   __syncthreads();
+  // (the stack was worked on in shared memory: write every live entry back, at most T ints)
+  for (int k = tid; k < s_nfree1; k += ASSOC_THREADS) t.free_slots[sb + k] = fstack[k];
   for (int j = warp; j < s_nL; j += ASSOC_THREADS / 32) {
     const int d = U[j];
     const long long ts = sb + Utmp[j];
     const int row = io.has_feats ? io.crop_slot[static_cast<long long>(s) * io.stride_k + d] : -1;
     if (row >= 0) {
-      const long long go = ts * t.G * t.F, so = (static_cast<long long>(s) * Dm + d) * t.F;
-      for (int f = lane; f < t.F; f += 32) {
-        t.gallery[go + f] = t.featn[so + f];
-        if (t.gal_hi) { t.gal_hi[go + f] = t.featn_hi[so + f]; t.gal_lo[go + f] = t.featn_lo[so + f]; }
-      }
+      copy_feature_row(t, ts * t.G * t.F, (static_cast<long long>(s) * Dm + d) * t.F, lane);
       if (lane == 0) t.gal_count[ts] = 1;
     }
     if (lane == 0) {
@@ -726,6 +964,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
     }
   }
   __syncthreads();
+  ASSOC_STAMP(5);
   // -- output (deepsort_tracker.py:125-141): confirmed and updated this frame, track-list order
   if (tid == 0) {  // which positions are reported (shared memory only) ...
     int n = 0;
@@ -750,6 +989,10 @@ __global__ void __launch_bounds__(ASSOC_THREADS) assoc_kernel(Dev t, StepIO io) 
     o[5] = t.cls[ts];
     io.out_conf[sb + n] = t.conf[ts];
   }
+  __syncthreads();
+  ASSOC_STAMP(6);
+  if (io.trace && s == 0 && tid == 0) { io.trace[8] = nt; io.trace[9] = nd; }
+#undef ASSOC_STAMP
 }
 
 __global__ void reset_kernel(Dev t) {
@@ -768,8 +1011,10 @@ __global__ void lsap_kernel(const float* cost, int nr, int nc, int* col_for_row)
   extern __shared__ __align__(16) uint8_t smraw[];
   LsapMem m = lsap_carve(smraw, max(nr, nc));
   int* cfr = reinterpret_cast<int*>(smraw + lsap_bytes(max(nr, nc)));
-  lsap_warp(cost + static_cast<long long>(blockIdx.x) * nr * nc, nc, nr, nc, m, cfr, threadIdx.x);
-  for (int r = threadIdx.x; r < nr; r += 32) col_for_row[static_cast<long long>(blockIdx.x) * nr + r] = cfr[r];
+  const int nw = lsap_warps(nr, nc);
+  if (static_cast<int>(threadIdx.x) < 32 * nw) lsap_cta(cost + static_cast<long long>(blockIdx.x) * nr * nc, nc, nr, nc, m, cfr, threadIdx.x, nw);
+  __syncthreads();
+  for (int r = threadIdx.x; r < nr; r += blockDim.x) col_for_row[static_cast<long long>(blockIdx.x) * nr + r] = cfr[r];
 }
 
 __global__ void gating_kernel(const float* state, const float* meas, int n, int m, float* d2) {
@@ -814,7 +1059,7 @@ __global__ void __launch_bounds__(128) cost_probe_kernel(Dev t, const float* __r
 
 constexpr size_t CM_SMEM_LIMIT = 96 * 1024;  // cost matrices up to this size live in shared memory
 size_t assoc_smem(int T, int D, int* cm_in_smem = nullptr) {
-  const size_t base = sizeof(float) * 8 * D + sizeof(int) * (3 * D + 8 * T) + 16 + lsap_bytes(std::max(T, D));
+  const size_t base = sizeof(float) * 8 * D + sizeof(int) * (2 * D + std::max(T, D) + 10 * T) + 32 + 32 * static_cast<size_t>(T) + lsap_bytes(std::max(T, D));
   const size_t cm = sizeof(float) * T * D;
   const bool fits = cm <= CM_SMEM_LIMIT;
   if (cm_in_smem) *cm_in_smem = fits ? 1 : 0;
@@ -829,6 +1074,7 @@ struct aicam_tracker {
   aicam_tracker_config cfg;
   std::vector<void*> allocs;
   aicam::AppearanceTf32* tf = nullptr;  // tensor-core appearance path (frames with more than APP_GEMM_MIN detections)
+  long long* trace = nullptr;           // AICAM_ASSOC_TRACE: 16 clock64 slots, printed by aicam_tracker_destroy
 };
 
 using namespace aicam;
@@ -924,6 +1170,7 @@ int aicam_tracker_create(const aicam_tracker_config* cfg, aicam_tracker** out) {
   if (sm > 200 * 1024) { aicam_tracker_destroy(t); return fail(AICAM_ERR_CAPACITY, "tracker_create: max_tracks/max_dets need too much shared memory"); }
   // (the > 48 KB opt-ins are made per launch in aicam_tracker_step: a running maximum per device, so that trackers of
   //  different sizes - or on different GPUs - never lower each other's limit)
+  if (getenv("AICAM_ASSOC_TRACE")) { if (dev_alloc(t, &t->trace, 16)) { aicam_tracker_destroy(t); return AICAM_ERR_CUDA; } }
   if (int r2 = aicam_tracker_reset(t, nullptr)) { aicam_tracker_destroy(t); return r2; }
   AICAM_CUDA_OK(cudaDeviceSynchronize());
   *out = t;
@@ -933,6 +1180,14 @@ int aicam_tracker_create(const aicam_tracker_config* cfg, aicam_tracker** out) {
 void aicam_tracker_destroy(aicam_tracker* t) {
   if (!t) return;
   cudaSetDevice(t->cfg.device);
+  if (t->trace) {  // phase durations (cycles) of stream 0's CTA in the last step
+    long long h[16];
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(h, t->trace, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
+      fprintf(stderr, "assoc trace (stream 0, last step; cycles): predict+lists %lld cascade %lld iou %lld update %lld prune+initiate %lld "
+              "output %lld total %lld | tracks %lld dets %lld | lsap: %lld cycles in %lld solves (sum rows*1024+cols %lld)\n",
+              h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[6] - h[0], h[8], h[9], h[10], h[11], h[12]);
+  }
   for (void* p : t->allocs) cudaFree(p);
   if (t->tf) appearance_tf32_destroy(t->tf);
   delete t;
@@ -957,7 +1212,8 @@ int aicam_tracker_step(aicam_tracker* t, const float* boxes, const float* scores
   if (feats) {
     if (int rc = launch_appearance(d, t->tf, det_count, crop_slot, stride_k, feats, st)) return rc;
   }
-  StepIO io{boxes, scores, labels, stride_k, det_index, det_count, crop_slot, out_tracks, out_conf, out_count, 0, feats ? 1 : 0};
+  StepIO io{boxes, scores, labels, stride_k, det_index, det_count, crop_slot, out_tracks, out_conf, out_count, 0, t->trace, feats ? 1 : 0};
+  if (t->trace) cudaMemsetAsync(t->trace, 0, sizeof(long long) * 16, st);
   const size_t asm_bytes = assoc_smem(d.T, d.D, &io.cm_in_smem);
   if (int rc = ensure_dynamic_smem(assoc_kernel, asm_bytes)) return rc;
   assoc_kernel<<<d.S, ASSOC_THREADS, asm_bytes, st>>>(d, io);
@@ -1030,7 +1286,7 @@ int aicam_lsap(const float* cost, int count, int nr, int nc, int32_t* col_for_ro
   if (count == 0) return AICAM_OK;
   const size_t sm = lsap_bytes(std::max(nr, nc)) + sizeof(int) * nr + 16;
   if (int rc = ensure_dynamic_smem(lsap_kernel, sm)) return rc;
-  lsap_kernel<<<count, 32, sm, static_cast<cudaStream_t>(stream)>>>(cost, nr, nc, col_for_row);
+  lsap_kernel<<<count, 32 * LSAP_MAX_WARPS, sm, static_cast<cudaStream_t>(stream)>>>(cost, nr, nc, col_for_row);
   count_launch();
   return last_launch("lsap_kernel");
 }
