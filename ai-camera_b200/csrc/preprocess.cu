@@ -13,8 +13,8 @@
 // the reference's bit for bit.  Taps with a zero weight are not loaded: for 1080p (exact 3:1)
 // the kernel touches one source pixel per output pixel, 360 of the 1080 rows.
 //
-// Pure-decimation geometries (1080p -> 640 x 360 is exactly 3:1) take a row-staged path: 128-bit coalesced loads
-// of each touched source row into shared memory, byte picks from there (preprocess_rows_kernel).
+// Pure-decimation geometries (1080p -> 640 x 360 is exactly 3:1) take a row-staged path: bulk copies of each touched
+// source row into a shared-memory ring, byte picks from there (preprocess_pairs_kernel).
 //
 // HBM-bound.  Algorithmic bytes per 1080p frame: 360 rows x 5760 B read + 640*640*8 B written
 // (NHWC4 bf16) = 5 350 400 B   (format 0, fp32 NCHW: 2 073 600 + 4 915 200 B).
@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "frame_src.cuh"
+#include "tc_ptx.cuh"
 
 namespace aicam {
 
@@ -132,6 +133,17 @@ int get_geometry(int h, int w, Geometry* out) {
 
 constexpr int PIX = 4;  // output pixels per thread (consecutive x)
 
+// float(v) / 255.0f, correctly rounded, for an integer 0 <= v <= 255: q = v * RN(1/255), one exact remainder, one
+// correction (three instructions instead of the generic IEEE division sequence).  Equal to __fdiv_rn(v, 255.0f) for all
+// 256 inputs (checked exhaustively with exact rational arithmetic; tests/test_gpu_preprocess.py compares every value
+// with the oracle).  Explicit fmaf: this file is compiled with --fmad=false.
+__device__ __forceinline__ float byte_to_unit(int v) {
+  const float a = static_cast<float>(v);
+  const float rcp = 0x1.010102p-8f;  // RN(1 / 255)
+  const float q = a * rcp;
+  return fmaf(fmaf(-255.0f, q, a), rcp, q);
+}
+
 template <int FORMAT, int SRC>
 __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ frames, int h, int w, int mode,
                                                          int new_h, int new_w, int top, int left,
@@ -190,9 +202,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
       }
     }
     // BGR -> RGB, /255 in float32 exactly as ndarray.astype(float32) / 255.0
-    rgb[p][0] = __fdiv_rn(static_cast<float>(v[2]), 255.0f);
-    rgb[p][1] = __fdiv_rn(static_cast<float>(v[1]), 255.0f);
-    rgb[p][2] = __fdiv_rn(static_cast<float>(v[0]), 255.0f);
+    rgb[p][0] = byte_to_unit(v[2]);
+    rgb[p][1] = byte_to_unit(v[1]);
+    rgb[p][2] = byte_to_unit(v[0]);
   }
   if (FORMAT == 0) {
     float* o = static_cast<float*>(out) + static_cast<long long>(n) * 3 * S * S + static_cast<long long>(y) * S + xg * PIX;
@@ -222,83 +234,139 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
   }
 }
 
-// Row-staged fast path for pure decimation (Geometry::decimate): one CTA per output row.  The source row is
-// brought into shared memory with coalesced 128-bit loads (every byte of the row is fetched, one in `ratio`
-// pixels is used: that is the algorithmic traffic counted in the header), then each thread picks the three
-// bytes of its four pixels from shared memory.  Rows of the letterbox border issue no loads.
+// Row-staged fast path for pure decimation (Geometry::decimate).  Persistent CTAs, each walking output-row PAIRS
+// (y, y + 1 with y even: the two rows of a space-to-depth block row); the touched source rows of a pair are brought into
+// a K1_STAGES-deep shared-memory ring by bulk copies (cp.async.bulk, completion counted on an mbarrier) issued by one
+// thread up to K1_STAGES - 1 pairs ahead, so every SM keeps tens of KB of reads in flight without any thread waiting on
+// a load; every byte of a touched row is fetched, one pixel in `ratio` is used (the algorithmic traffic in the header).
+// Each thread then picks the bytes of its four pixels of both rows from shared memory and writes 64 contiguous bytes
+// (format 2: two whole 2x2 blocks) or 32 per row (format 1).  Rows of the letterbox border issue no loads.
+constexpr int K1_STAGES = 4;
 template <int FORMAT, int SRC>
-__global__ void __launch_bounds__(S / PIX) preprocess_rows_kernel(const uint8_t* __restrict__ frames, int h, int w, int new_h,
-                                                                  int new_w, int top, int left, const int* __restrict__ tab,
-                                                                  void* __restrict__ out) {
-  extern __shared__ __align__(16) uint8_t srow[];
-  const int y = blockIdx.x % S, n = blockIdx.x / S;
-  const int dy = y - top;
-  const bool row_in = dy >= 0 && dy < new_h;
-  if (row_in) {
-    const int sy = __ldg(tab + 4 * new_w + dy);
-    if (SRC == 0) {
-      const uint4* src = reinterpret_cast<const uint4*>(frames + (static_cast<long long>(n) * h + sy) * w * 3);
-      const int chunks = (w * 3) >> 4;
-      for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
-        uint4 v;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i));
-        reinterpret_cast<uint4*>(srow)[i] = v;
-      }
-    } else {  // NV12: the luma row, then the chroma row it shares with its neighbour: [w Y bytes][w UV bytes]
-      const uint8_t* fr = frames + n * FrameSrc<1>::frame_bytes(h, w);
-      const uint4* ysrc = reinterpret_cast<const uint4*>(fr + static_cast<long long>(sy) * w);
-      const uint4* csrc = reinterpret_cast<const uint4*>(fr + static_cast<long long>(h) * w + static_cast<long long>(sy >> 1) * w);
-      const int chunks = w >> 4;
-      for (int i = threadIdx.x; i < 2 * chunks; i += blockDim.x) {
-        const uint4* s = i < chunks ? ysrc + i : csrc + (i - chunks);
-        uint4 v;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(s));
-        reinterpret_cast<uint4*>(srow)[i] = v;
-      }
-    }
+__global__ void __launch_bounds__(S / PIX) preprocess_pairs_kernel(const uint8_t* __restrict__ frames, int h, int w, int new_h,
+                                                                   int new_w, int top, int left, const int* __restrict__ tab,
+                                                                   void* __restrict__ out, int n_pairs, int stages) {
+  extern __shared__ __align__(128) uint8_t sm_rows[];
+  __shared__ __align__(8) uint64_t full_bar[K1_STAGES];
+  const int row_bytes = SRC == 0 ? w * 3 : 2 * w;  // one staged source row: BGR, or the luma row followed by its chroma row
+  const int stage_bytes = 2 * row_bytes;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int k = 0; k < stages; ++k) ptx::mbar_init(smem_u32(&full_bar[k]), 1);
+    ptx::mbar_init_fence();
   }
   __syncthreads();
-  const int xg = threadIdx.x;
-  float rgb[PIX][3];
+  const int* ty = tab + 4 * new_w;
+  auto issue = [&](int pair, int stage) {  // thread 0: the source rows of one output-row pair -> ring stage
+    const int n = pair / (S / 2), y0 = (pair - n * (S / 2)) * 2;
+    const uint32_t bar = smem_u32(&full_bar[stage]);
+    int sy[2];
+    uint32_t bytes = 0;
+    for (int r = 0; r < 2; ++r) {
+      const int dy = y0 + r - top;
+      sy[r] = (dy >= 0 && dy < new_h) ? __ldg(ty + dy) : -1;
+      if (sy[r] >= 0) bytes += row_bytes;
+    }
+    ptx::mbar_arrive_expect_tx(bar, bytes);  // (a border pair completes the phase with no bytes)
+    for (int r = 0; r < 2; ++r) {
+      if (sy[r] < 0) continue;
+      const uint32_t dst = smem_u32(sm_rows + static_cast<size_t>(stage) * stage_bytes + r * row_bytes);
+      if (SRC == 0) {
+        ptx::bulk_g2s(dst, frames + (static_cast<long long>(n) * h + sy[r]) * w * 3, row_bytes, bar);
+      } else {
+        const uint8_t* fr = frames + n * FrameSrc<1>::frame_bytes(h, w);
+        ptx::bulk_g2s(dst, fr + static_cast<long long>(sy[r]) * w, w, bar);
+        ptx::bulk_g2s(dst + w, fr + static_cast<long long>(h) * w + static_cast<long long>(sy[r] >> 1) * w, w, bar);
+      }
+    }
+  };
+  if (tid == 0)
+    for (int k = 0; k < stages; ++k) {
+      const long long pair = blockIdx.x + static_cast<long long>(k) * gridDim.x;
+      if (pair < n_pairs) issue(static_cast<int>(pair), k);
+    }
+  // the four source columns of this thread never change
+  const int xg = tid;
+  int sx[PIX];
 #pragma unroll
   for (int p = 0; p < PIX; ++p) {
     const int dx = xg * PIX + p - left;
-    int v0 = 114, v1 = 114, v2 = 114;  // BGR pad colour (image_processing.py:10)
-    if (row_in && dx >= 0 && dx < new_w) {
-      const int sx = __ldg(tab + dx);
-      if (SRC == 0) {
-        const uint8_t* sp = srow + sx * 3;
-        v0 = sp[0]; v1 = sp[1]; v2 = sp[2];
+    sx[p] = (dx >= 0 && dx < new_w) ? __ldg(tab + dx) : -1;
+  }
+  for (int it = 0;; ++it) {
+    const long long pair_l = blockIdx.x + static_cast<long long>(it) * gridDim.x;
+    if (pair_l >= n_pairs) break;
+    const int pair = static_cast<int>(pair_l);
+    const int stage = it % stages;
+    const int n = pair / (S / 2), y0 = (pair - n * (S / 2)) * 2;
+    ptx::mbar_wait(smem_u32(&full_bar[stage]), (it / stages) & 1);
+    uint4 q[2][2];
+    float pl[2][PIX][3];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int dy = y0 + r - top;
+      const bool row_in = dy >= 0 && dy < new_h;
+      const uint8_t* srow = sm_rows + static_cast<size_t>(stage) * stage_bytes + r * row_bytes;
+      float rgb[PIX][3];
+#pragma unroll
+      for (int p = 0; p < PIX; ++p) {
+        int v0 = 114, v1 = 114, v2 = 114;  // BGR pad colour (image_processing.py:10)
+        if (row_in && sx[p] >= 0) {
+          if (SRC == 0) {
+            const uint8_t* sp = srow + sx[p] * 3;
+            v0 = sp[0]; v1 = sp[1]; v2 = sp[2];
+          } else {
+            int bgr[3];
+            yuv_to_bgr_601(srow[sx[p]], srow[w + (sx[p] & ~1)], srow[w + (sx[p] & ~1) + 1], bgr);
+            v0 = bgr[0]; v1 = bgr[1]; v2 = bgr[2];
+          }
+        }
+        // BGR -> RGB, /255 in float32 exactly as ndarray.astype(float32) / 255.0
+        rgb[p][0] = byte_to_unit(v2);
+        rgb[p][1] = byte_to_unit(v1);
+        rgb[p][2] = byte_to_unit(v0);
+      }
+      if (FORMAT == 0) {
+#pragma unroll
+        for (int p = 0; p < PIX; ++p)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) pl[r][p][c] = rgb[p][c];
       } else {
-        int bgr[3];
-        yuv_to_bgr_601(srow[sx], srow[w + (sx & ~1)], srow[w + (sx & ~1) + 1], bgr);
-        v0 = bgr[0]; v1 = bgr[1]; v2 = bgr[2];
+        q[r][0].x = pack_bf16x2(rgb[0][0], rgb[0][1]); q[r][0].y = pack_bf16x2(rgb[0][2], 0.0f);
+        q[r][0].z = pack_bf16x2(rgb[1][0], rgb[1][1]); q[r][0].w = pack_bf16x2(rgb[1][2], 0.0f);
+        q[r][1].x = pack_bf16x2(rgb[2][0], rgb[2][1]); q[r][1].y = pack_bf16x2(rgb[2][2], 0.0f);
+        q[r][1].z = pack_bf16x2(rgb[3][0], rgb[3][1]); q[r][1].w = pack_bf16x2(rgb[3][2], 0.0f);
       }
     }
-    rgb[p][0] = __fdiv_rn(static_cast<float>(v2), 255.0f);
-    rgb[p][1] = __fdiv_rn(static_cast<float>(v1), 255.0f);
-    rgb[p][2] = __fdiv_rn(static_cast<float>(v0), 255.0f);
-  }
-  if (FORMAT == 0) {
-    float* o = static_cast<float*>(out) + static_cast<long long>(n) * 3 * S * S + static_cast<long long>(y) * S + xg * PIX;
+    __syncthreads();  // the stage has been read by everyone: refill it
+    if (tid == 0) {
+      const long long next = pair_l + static_cast<long long>(stages) * gridDim.x;
+      if (next < n_pairs) issue(static_cast<int>(next), stage);
+    }
+    if (FORMAT == 0) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      *reinterpret_cast<float4*>(o + static_cast<long long>(c) * S * S) = make_float4(rgb[0][c], rgb[1][c], rgb[2][c], rgb[3][c]);
-  } else {
-    uint4 q0, q1;
-    q0.x = pack_bf16x2(rgb[0][0], rgb[0][1]); q0.y = pack_bf16x2(rgb[0][2], 0.0f);
-    q0.z = pack_bf16x2(rgb[1][0], rgb[1][1]); q0.w = pack_bf16x2(rgb[1][2], 0.0f);
-    q1.x = pack_bf16x2(rgb[2][0], rgb[2][1]); q1.y = pack_bf16x2(rgb[2][2], 0.0f);
-    q1.z = pack_bf16x2(rgb[3][0], rgb[3][1]); q1.w = pack_bf16x2(rgb[3][2], 0.0f);
-    if (FORMAT == 1) {
-      uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + ((static_cast<long long>(n) * S + y) * S + xg * PIX) * 4);
-      o[0] = q0;
-      o[1] = q1;
+      for (int r = 0; r < 2; ++r) {
+        float* o = static_cast<float*>(out) + static_cast<long long>(n) * 3 * S * S + static_cast<long long>(y0 + r) * S + xg * PIX;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          *reinterpret_cast<float4*>(o + static_cast<long long>(c) * S * S) = make_float4(pl[r][0][c], pl[r][1][c], pl[r][2][c], pl[r][3][c]);
+      }
+    } else if (FORMAT == 1) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + ((static_cast<long long>(n) * S + y0 + r) * S + xg * PIX) * 4);
+        o[0] = q[r][0];
+        o[1] = q[r][1];
+      }
     } else {
+      // space-to-depth: 2x2 pixel block (Y, X) = 16 channels [row parity][column parity][RGB0]; this thread holds
+      // columns 4 xg .. 4 xg + 3 of both rows = the whole blocks X = 2 xg and 2 xg + 1 of block row y0 / 2
       uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) +
-                                          ((static_cast<long long>(n) * (S / 2) + (y >> 1)) * (S / 2) + 2 * xg) * 16 + (y & 1) * 8);
-      o[0] = q0;
-      o[2] = q1;
+                                          ((static_cast<long long>(n) * (S / 2) + (y0 >> 1)) * (S / 2) + 2 * xg) * 16);
+      o[0] = q[0][0];
+      o[1] = q[1][0];
+      o[2] = q[0][1];
+      o[3] = q[1][1];
     }
   }
 }
@@ -349,18 +417,26 @@ int preprocess_impl(const uint8_t* frames, int batch, int h, int w, int format, 
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static const bool no_fast = getenv("AICAM_PREPROCESS_GENERIC") != nullptr;
-  const int row_bytes = SRC == 0 ? w * 3 : w;  // bytes of one staged source row (NV12: luma row; the chroma row has as many)
+  const int row_bytes = SRC == 0 ? w * 3 : w;  // bytes of one bulk copy (NV12: the luma row; its chroma row has as many)
+  const size_t stage_bytes = 2 * (SRC == 0 ? static_cast<size_t>(w) * 3 : static_cast<size_t>(w) * 2);
   if (g.decimate && !no_fast && row_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(frames) % 16 == 0 &&
-      FrameSrc<SRC>::frame_bytes(h, w) % 16 == 0 && (static_cast<long long>(h) * w) % 16 == 0 && w * 3 <= 96 * 1024) {
-    const unsigned rows = static_cast<unsigned>(batch) * S;
-    const size_t smem = SRC == 0 ? static_cast<size_t>(w) * 3 : static_cast<size_t>(w) * 2;
-    auto kernel = format == 0 ? preprocess_rows_kernel<0, SRC> : (format == 1 ? preprocess_rows_kernel<1, SRC> : preprocess_rows_kernel<2, SRC>);
+      FrameSrc<SRC>::frame_bytes(h, w) % 16 == 0 && (static_cast<long long>(h) * w) % 16 == 0 && 2 * stage_bytes <= 200 * 1024) {
+    const int n_pairs = batch * (S / 2);
+    static const int env_stages = getenv("AICAM_K1_STAGES") ? atoi(getenv("AICAM_K1_STAGES")) : 0;
+    static const int env_ctas = getenv("AICAM_K1_CTAS") ? atoi(getenv("AICAM_K1_CTAS")) : 0;
+    int stages = K1_STAGES * stage_bytes <= 100 * 1024 ? K1_STAGES : 2;
+    if (env_stages >= 2 && env_stages <= K1_STAGES && env_stages * stage_bytes <= 200 * 1024) stages = env_stages;
+    const size_t smem = stages * stage_bytes;
+    auto kernel = format == 0 ? preprocess_pairs_kernel<0, SRC> : (format == 1 ? preprocess_pairs_kernel<1, SRC> : preprocess_pairs_kernel<2, SRC>);
     if (smem > 48 * 1024) {
-      if (int rc = ensure_dynamic_smem(kernel, 96 * 1024)) return rc;
+      if (int rc = ensure_dynamic_smem(kernel, 200 * 1024)) return rc;
     }
-    kernel<<<rows, S / PIX, smem, st>>>(frames, h, w, g.new_h, g.new_w, g.top, g.left, g.tab, out);
+    int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024))));
+    if (env_ctas > 0) per_sm = std::min(per_sm, env_ctas);
+    const unsigned grid = static_cast<unsigned>(std::min<long long>(n_pairs, static_cast<long long>(current_num_sms()) * per_sm));
+    kernel<<<grid, S / PIX, smem, st>>>(frames, h, w, g.new_h, g.new_w, g.top, g.left, g.tab, out, n_pairs, stages);
     count_launch();
-    return last_launch("preprocess_rows_kernel");
+    return last_launch("preprocess_pairs_kernel");
   }
   auto kernel = format == 0 ? preprocess_kernel<0, SRC> : (format == 1 ? preprocess_kernel<1, SRC> : preprocess_kernel<2, SRC>);
   kernel<<<blocks, 256, 0, st>>>(frames, h, w, g.mode, g.new_h, g.new_w, g.top, g.left, g.tab, out, total);

@@ -134,71 +134,191 @@ __device__ __forceinline__ void axis_entry(int src, int dst, int d, bool horizon
   *w1 = __float2int_rn(__fmul_rn(f, 2048.0f));
 }
 
+// a / b correctly rounded, given rcp = RN(1 / b): quotient estimate, exact remainder, one correction - three
+// instructions instead of the generic IEEE division sequence.  Equal to __fdiv_rn(a, b) on every input this kernel can
+// produce: v / 255 for the 256 byte values and (v / 255 - mean) / std for the 3 x 256 (channel, value) pairs were checked
+// exhaustively with exact rational arithmetic, and tests/test_gpu_crops.py compares whole crops with the oracle bit for
+// bit.  Explicit fmaf: this file is compiled with --fmad=false.
+__device__ __forceinline__ float div_exact(float a, float b, float rcp) {
+  const float q = __fmul_rn(a, rcp);
+  return fmaf(fmaf(-b, q, a), rcp, q);
+}
+
+// One output pixel from its (up to) four source taps, normalised and stored.  tap(r, i, v): BGR of tap column i (0: sx0,
+// 1: sx1) of source row r (0: sy0, 1: sy1).
+template <int FORMAT, typename Tap>
+__device__ __forceinline__ void crop_pixel(int mode, int a0, int a1, int b0, int b1, Tap tap, void* __restrict__ out, int slot, int p) {
+  int v[3];
+  if (mode == 2) {
+    tap(0, 0, v);
+  } else if (mode == 1) {
+    int p00[3], p01[3], p10[3], p11[3];
+    tap(0, 0, p00); tap(0, 1, p01); tap(1, 0, p10); tap(1, 1, p11);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (p00[c] + p01[c] + p10[c] + p11[c] + 2) >> 2;
+  } else {
+    // taps with a zero weight are not fetched
+    int p00[3] = {0, 0, 0}, p01[3] = {0, 0, 0}, p10[3] = {0, 0, 0}, p11[3] = {0, 0, 0};
+    if (b0 != 0) {
+      tap(0, 0, p00);
+      if (a1 != 0) tap(0, 1, p01);
+    }
+    if (b1 != 0) {
+      tap(1, 0, p10);
+      if (a1 != 0) tap(1, 1, p11);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int h0 = p00[c] * a0 + p01[c] * a1, h1 = p10[c] * a0 + p11[c] * a1;
+      const int o = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      v[c] = min(max(o, 0), 255);
+    }
+  }
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  const float rstd[3] = {0x1.1779dap+2f, 0x1.1db6dap+2f, 0x1.1c71c8p+2f};  // RN(1 / std)
+  float rgb[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)  // BGR -> RGB, (x/255 - mean)/std in float32
+    rgb[c] = div_exact(__fsub_rn(div_exact(static_cast<float>(v[2 - c]), 255.0f, 0x1.010102p-8f), mean[c]), stdv[c], rstd[c]);
+  if (FORMAT == 0) {
+    float* o = static_cast<float*>(out) + static_cast<long long>(slot) * 3 * RH * RW + p;
+    o[0] = rgb[0]; o[RH * RW] = rgb[1]; o[2 * RH * RW] = rgb[2];
+  } else if (FORMAT == 1) {
+    uint2 q;
+    q.x = pack_bf16x2(rgb[0], rgb[1]);
+    q.y = pack_bf16x2(rgb[2], 0.0f);
+    reinterpret_cast<uint2*>(out)[static_cast<long long>(slot) * RH * RW + p] = q;
+  } else {  // NHWC8: one pixel = one 16-byte K chunk of the fused ReID stem (stem_pool.cu)
+    reinterpret_cast<uint4*>(out)[static_cast<long long>(slot) * RH * RW + p] =
+        make_uint4(pack_bf16x2(rgb[0], rgb[1]), pack_bf16x2(rgb[2], 0.0f), 0u, 0u);
+  }
+}
+
+// Crops up to CROP_STAGE_W pixels wide are resized from shared memory: one WARP per output row brings the row's two
+// source-row segments in with coalesced 32-bit loads (aligned words covering the segment), then every lane interpolates
+// two output pixels from there - the direct path issued up to twelve scattered byte loads per output pixel.  Wider crops
+// (and frames that are not 4-byte aligned) keep the direct path.
+constexpr int CROP_STAGE_W = 512;
+constexpr int CROP_SEG = CROP_STAGE_W * 3 + 16;  // bytes of one staged segment (BGR row; NV12: luma + chroma halves)
+constexpr int CROP_WARPS = 8;
+
+// NSEG byte segments [p[s], p[s] + n[s]) -> dst[s] (4-byte aligned shared memory) as the aligned words that cover them
+// (n[s] <= 0: segment not needed); shift[s] = p[s] & 3 is where the segment starts in dst[s].  All the loads of a pass -
+// WPP words per lane per segment - are issued before the first store, so a row costs one memory round trip.  The frame
+// batch is a multiple of 4 bytes long and 4-byte aligned (checked by the caller), so no word crosses its end.
+template <int NSEG, int WPP>
+__device__ __forceinline__ void stage_segments(const uint8_t* const (&p)[NSEG], const int (&n)[NSEG], uint8_t* const (&dst)[NSEG],
+                                               int (&shift)[NSEG], int lane) {
+  const uint32_t* pa[NSEG];
+  int nwords[NSEG], maxw = 0;
+#pragma unroll
+  for (int s = 0; s < NSEG; ++s) {
+    shift[s] = static_cast<int>(reinterpret_cast<uintptr_t>(p[s]) & 3);
+    pa[s] = reinterpret_cast<const uint32_t*>(p[s] - shift[s]);
+    nwords[s] = n[s] > 0 ? (shift[s] + n[s] + 3) >> 2 : 0;
+    maxw = max(maxw, nwords[s]);
+  }
+  for (int base = 0; base < maxw; base += 32 * WPP) {
+    uint32_t v[NSEG][WPP];
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s)
+#pragma unroll
+      for (int j = 0; j < WPP; ++j) {
+        const int i = base + lane + 32 * j;
+        v[s][j] = i < nwords[s] ? __ldg(pa[s] + i) : 0u;
+      }
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s)
+#pragma unroll
+      for (int j = 0; j < WPP; ++j) {
+        const int i = base + lane + 32 * j;
+        if (i < nwords[s]) reinterpret_cast<uint32_t*>(dst[s])[i] = v[s][j];
+      }
+  }
+}
+
 template <int FORMAT, int SRC>
-__global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ frames, int h, int w,
-                                                   const int* __restrict__ crop_rect,
-                                                   const int* __restrict__ crop_count, void* __restrict__ out) {
+__global__ void __launch_bounds__(32 * CROP_WARPS) crop_kernel(const uint8_t* __restrict__ frames, int batch, int h, int w,
+                                                               const int* __restrict__ crop_rect,
+                                                               const int* __restrict__ crop_count, void* __restrict__ out) {
   const int slot = blockIdx.x;
   if (slot >= *crop_count) return;
   __shared__ int tx[4][RW];
   __shared__ int ty[4][RH];
+  __shared__ __align__(16) uint8_t seg[CROP_WARPS][2][CROP_SEG];
   const int b = crop_rect[slot * 5], x1 = crop_rect[slot * 5 + 1], y1 = crop_rect[slot * 5 + 2];
   const int cw = crop_rect[slot * 5 + 3] - x1, ch = crop_rect[slot * 5 + 4] - y1;
   const int mode = (cw == RW && ch == RH) ? 2 : ((cw == 2 * RW && ch == 2 * RH) ? 1 : 0);
-  if (mode == 0) {
+  {
     const int t = threadIdx.x;
-    if (t < RW) axis_entry(cw, RW, t, true, &tx[0][t], &tx[1][t], &tx[2][t], &tx[3][t]);
-    else if (t < RW + RH) axis_entry(ch, RH, t - RW, false, &ty[0][t - RW], &ty[1][t - RW], &ty[2][t - RW], &ty[3][t - RW]);
+    if (mode == 0) {
+      if (t < RW) axis_entry(cw, RW, t, true, &tx[0][t], &tx[1][t], &tx[2][t], &tx[3][t]);
+      else if (t < RW + RH) axis_entry(ch, RH, t - RW, false, &ty[0][t - RW], &ty[1][t - RW], &ty[2][t - RW], &ty[3][t - RW]);
+    } else {  // exact 2x (box average of 2x2) / copy: the taps as tables too
+      const int f = mode == 1 ? 2 : 1;
+      if (t < RW) { tx[0][t] = f * t; tx[1][t] = f * t + (f - 1); tx[2][t] = 0; tx[3][t] = 0; }
+      else if (t < RW + RH) { const int u = t - RW; ty[0][u] = f * u; ty[1][u] = f * u + (f - 1); ty[2][u] = 0; ty[3][u] = 0; }
+    }
   }
   __syncthreads();
   const FrameSrc<SRC> src{frames + b * FrameSrc<SRC>::frame_bytes(h, w), h, w};
-  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
-  for (int p = threadIdx.x; p < RH * RW; p += blockDim.x) {
-    const int oy = p / RW, ox = p - oy * RW;
-    int v[3];
-    if (mode == 2) {
-      src.pix(y1 + oy, x1 + ox, v);
-    } else if (mode == 1) {
-      int p00[3], p01[3], p10[3], p11[3];
-      src.pix(y1 + 2 * oy, x1 + 2 * ox, p00); src.pix(y1 + 2 * oy, x1 + 2 * ox + 1, p01);
-      src.pix(y1 + 2 * oy + 1, x1 + 2 * ox, p10); src.pix(y1 + 2 * oy + 1, x1 + 2 * ox + 1, p11);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) v[c] = (p00[c] + p01[c] + p10[c] + p11[c] + 2) >> 2;
-    } else {
-      const int sx0 = x1 + tx[0][ox], sx1 = x1 + tx[1][ox], a0 = tx[2][ox], a1 = tx[3][ox];
-      const int sy0 = y1 + ty[0][oy], sy1 = y1 + ty[1][oy], b0 = ty[2][oy], b1 = ty[3][oy];
-      // taps with a zero weight are not fetched
-      int p00[3] = {0, 0, 0}, p01[3] = {0, 0, 0}, p10[3] = {0, 0, 0}, p11[3] = {0, 0, 0};
-      if (b0 != 0) {
-        src.pix(sy0, sx0, p00);
-        if (a1 != 0) src.pix(sy0, sx1, p01);
-      }
-      if (b1 != 0) {
-        src.pix(sy1, sx0, p10);
-        if (a1 != 0) src.pix(sy1, sx1, p11);
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int h0 = p00[c] * a0 + p01[c] * a1, h1 = p10[c] * a0 + p11[c] * a1;
-        const int o = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-        v[c] = min(max(o, 0), 255);
-      }
+  const bool staged = cw <= CROP_STAGE_W && (reinterpret_cast<uintptr_t>(frames) & 3) == 0 &&
+                      ((static_cast<long long>(batch) * FrameSrc<SRC>::frame_bytes(h, w)) & 3) == 0;
+  if (!staged) {
+    for (int p = threadIdx.x; p < RH * RW; p += blockDim.x) {
+      const int oy = p / RW, ox = p - oy * RW;
+      const int sx[2] = {x1 + tx[0][ox], x1 + tx[1][ox]}, sy[2] = {y1 + ty[0][oy], y1 + ty[1][oy]};
+      crop_pixel<FORMAT>(mode, tx[2][ox], tx[3][ox], ty[2][oy], ty[3][oy],
+                         [&](int r, int i, int (&v)[3]) { src.pix(sy[r], sx[i], v); }, out, slot, p);
     }
-    float rgb[3];
+    return;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int lsx[RW / 32][2], la[RW / 32][2];  // this lane's columns never change: taps (relative to the crop) and weights
 #pragma unroll
-    for (int c = 0; c < 3; ++c)  // BGR -> RGB, (x/255 - mean)/std in float32
-      rgb[c] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v[2 - c]), 255.0f), mean[c]), stdv[c]);
-    if (FORMAT == 0) {
-      float* o = static_cast<float*>(out) + static_cast<long long>(slot) * 3 * RH * RW + p;
-      o[0] = rgb[0]; o[RH * RW] = rgb[1]; o[2 * RH * RW] = rgb[2];
-    } else if (FORMAT == 1) {
-      uint2 q;
-      q.x = pack_bf16x2(rgb[0], rgb[1]);
-      q.y = pack_bf16x2(rgb[2], 0.0f);
-      reinterpret_cast<uint2*>(out)[static_cast<long long>(slot) * RH * RW + p] = q;
-    } else {  // NHWC8: one pixel = one 16-byte K chunk of the fused ReID stem (stem_pool.cu)
-      reinterpret_cast<uint4*>(out)[static_cast<long long>(slot) * RH * RW + p] =
-          make_uint4(pack_bf16x2(rgb[0], rgb[1]), pack_bf16x2(rgb[2], 0.0f), 0u, 0u);
+  for (int k = 0; k < RW / 32; ++k) {
+    lsx[k][0] = tx[0][lane + 32 * k]; lsx[k][1] = tx[1][lane + 32 * k];
+    la[k][0] = tx[2][lane + 32 * k]; la[k][1] = tx[3][lane + 32 * k];
+  }
+  for (int oy = warp; oy < RH; oy += CROP_WARPS) {
+    const int sy[2] = {y1 + ty[0][oy], y1 + ty[1][oy]};
+    const int b0 = ty[2][oy], b1 = ty[3][oy];
+    // which of the two source rows the row's pixels read (crop_pixel skips taps with a zero weight)
+    const bool need[2] = {mode != 0 || b0 != 0, mode == 1 || (mode == 0 && b1 != 0)};
+    int shift[2] = {0, 0}, cshift[2] = {0, 0};
+    __syncwarp();  // the previous row's taps have been read
+    if (SRC == 0) {
+      const uint8_t* const ps[2] = {src.f + (static_cast<long long>(sy[0]) * w + x1) * 3, src.f + (static_cast<long long>(sy[1]) * w + x1) * 3};
+      const int ns[2] = {need[0] ? cw * 3 : 0, need[1] ? cw * 3 : 0};
+      uint8_t* const ds[2] = {seg[warp][0], seg[warp][1]};
+      stage_segments<2, 4>(ps, ns, ds, shift, lane);
+    } else {  // luma segments, then the chroma pairs of columns x1 & ~1 .. (even start: U first)
+      const uint8_t* chroma = src.f + static_cast<long long>(h) * w + (x1 & ~1);
+      const int cn = ((x1 + cw + 1) & ~1) - (x1 & ~1);
+      const uint8_t* const ps[4] = {src.f + static_cast<long long>(sy[0]) * w + x1, src.f + static_cast<long long>(sy[1]) * w + x1,
+                                    chroma + static_cast<long long>(sy[0] >> 1) * w, chroma + static_cast<long long>(sy[1] >> 1) * w};
+      const int ns[4] = {need[0] ? cw : 0, need[1] ? cw : 0, need[0] ? cn : 0, need[1] ? cn : 0};
+      uint8_t* const ds[4] = {seg[warp][0], seg[warp][1], seg[warp][0] + CROP_SEG / 2, seg[warp][1] + CROP_SEG / 2};
+      int sh[4];
+      stage_segments<4, 2>(ps, ns, ds, sh, lane);
+      shift[0] = sh[0]; shift[1] = sh[1]; cshift[0] = sh[2]; cshift[1] = sh[3];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < RW / 32; ++k) {
+      const int ox = lane + 32 * k;
+      const int sx[2] = {lsx[k][0], lsx[k][1]};
+      crop_pixel<FORMAT>(mode, la[k][0], la[k][1], b0, b1,
+                         [&](int r, int i, int (&v)[3]) {
+                           if (SRC == 0) {
+                             const uint8_t* q = seg[warp][r] + shift[r] + sx[i] * 3;
+                             v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
+                           } else {
+                             const uint8_t* c = seg[warp][r] + CROP_SEG / 2 + cshift[r] + (((x1 + sx[i]) & ~1) - (x1 & ~1));
+                             yuv_to_bgr_601(seg[warp][r][shift[r] + sx[i]], c[0], c[1], v);
+                           }
+                         },
+                         out, slot, oy * RW + ox);
     }
   }
 }
@@ -229,11 +349,11 @@ int reid_crops_impl(const uint8_t* frames, int batch, int h, int w, const float*
   if (int rc = last_launch("filter_kernel")) return rc;
   if (max_crops == 0 || !frames || !crops) return AICAM_OK;  // filter only
   if (format == 0)
-    crop_kernel<0, SRC><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
+    crop_kernel<0, SRC><<<max_crops, 32 * CROP_WARPS, 0, st>>>(frames, batch, h, w, crop_rect, crop_count, crops);
   else if (format == 1)
-    crop_kernel<1, SRC><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
+    crop_kernel<1, SRC><<<max_crops, 32 * CROP_WARPS, 0, st>>>(frames, batch, h, w, crop_rect, crop_count, crops);
   else
-    crop_kernel<2, SRC><<<max_crops, 256, 0, st>>>(frames, h, w, crop_rect, crop_count, crops);
+    crop_kernel<2, SRC><<<max_crops, 32 * CROP_WARPS, 0, st>>>(frames, batch, h, w, crop_rect, crop_count, crops);
   count_launch();
   return last_launch("crop_kernel");
 }
