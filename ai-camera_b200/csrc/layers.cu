@@ -92,20 +92,25 @@ __global__ void __launch_bounds__(256) sppf_pool3_kernel(__nv_bfloat16* __restri
   }
 }
 
-__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, long long in_img_stride, int in_cstride,
-                                  int in_coff, int h, int w, int c8, __nv_bfloat16* __restrict__ out,
-                                  long long out_img_stride, int out_cstride, int out_coff, long long total) {
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+// nearest-neighbour 2x: one thread per INPUT 16-byte chunk (8 channels of one pixel): one load, four stores
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, long long in_img_stride, int in_cstride,
+                                                         int in_coff, int h, int w, int c8, __nv_bfloat16* __restrict__ out,
+                                                         long long out_img_stride, int out_cstride, int out_coff, unsigned total) {
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int g = static_cast<int>(idx % c8);
-  long long p = idx / c8;
-  const int ox = static_cast<int>(p % (2 * w)); p /= (2 * w);
-  const int oy = static_cast<int>(p % (2 * h));
-  const int n = static_cast<int>(p / (2 * h));
+  const unsigned g = idx % c8;
+  unsigned p = idx / c8;
+  const unsigned x = p % w; p /= w;
+  const unsigned y = p % h;
+  const unsigned n = p / h;
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(
-      in + n * in_img_stride + (static_cast<long long>(oy >> 1) * w + (ox >> 1)) * in_cstride + in_coff + g * 8));
-  *reinterpret_cast<uint4*>(out + n * out_img_stride + (static_cast<long long>(oy) * 2 * w + ox) * out_cstride +
-                            out_coff + g * 8) = v;
+      in + n * in_img_stride + (static_cast<long long>(y) * w + x) * in_cstride + in_coff + g * 8));
+  __nv_bfloat16* o = out + n * out_img_stride + (static_cast<long long>(2 * y) * 2 * w + 2 * x) * out_cstride + out_coff + g * 8;
+  const long long row = static_cast<long long>(2 * w) * out_cstride;
+  *reinterpret_cast<uint4*>(o) = v;
+  *reinterpret_cast<uint4*>(o + out_cstride) = v;
+  *reinterpret_cast<uint4*>(o + row) = v;
+  *reinterpret_cast<uint4*>(o + row + out_cstride) = v;
 }
 
 // One block per image: mean over hw pixels of each of c channels, then x / ||x||_2 (fp32).  Thread t owns the
@@ -226,10 +231,11 @@ int launch_upsample2x(const __nv_bfloat16* in, long long in_img_stride, int in_c
                       cudaStream_t stream) {
   if (c % 8 || in_cstride % 8 || in_coff % 8 || out_cstride % 8 || out_coff % 8)
     return fail(AICAM_ERR_INVALID_ARG, "upsample: channel counts/offsets must be multiples of 8");
-  const long long total = static_cast<long long>(batch) * 4 * h * w * (c / 8);
+  const long long total = static_cast<long long>(batch) * h * w * (c / 8);  // input chunks
   if (total == 0) return AICAM_OK;
+  if (total >= (1ll << 32)) return fail(AICAM_ERR_CAPACITY, "upsample: tensor too large");
   upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      in, in_img_stride, in_cstride, in_coff, h, w, c / 8, out, out_img_stride, out_cstride, out_coff, total);
+      in, in_img_stride, in_cstride, in_coff, h, w, c / 8, out, out_img_stride, out_cstride, out_coff, static_cast<unsigned>(total));
   count_launch();
   return last_launch("upsample2x_kernel");
 }
