@@ -52,6 +52,10 @@ class TrackerConfig(C.Structure):
                 ("nn_budget", C.c_int), ("device", C.c_int)]
 
 
+class OverlayItem(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("type", "x1", "y1", "x2", "y2", "color", "slot", "reserved")]
+
+
 class TensorInfo(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("dtype", C.c_int), ("ndim", C.c_int), ("shape", C.c_int * 4),
                 ("is_dynamic", C.c_int)]
@@ -66,6 +70,7 @@ SIGNATURES = {
     "aicam_launch_count": (C.c_uint64, []),
     "aicam_profile_enable": (_I, [_I]),
     "aicam_profile_conv": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "aicam_debug_timeline": (_I, [_I, C.POINTER(C.c_longlong), _I]),
     "aicam_engine_create": (_I, [C.c_char_p, _I, _I, C.POINTER(_P)]),
     "aicam_engine_destroy": (None, [_P]),
     "aicam_engine_kind": (_I, [_P]),
@@ -114,6 +119,7 @@ SIGNATURES = {
     "aicam_tracker_overflow": (_I, [_P, _P]),
     "aicam_lsap": (_I, [_P, _I, _I, _I, _P, _P]),
     "aicam_kf_gating": (_I, [_P, _P, _I, _I, _P, _P]),
+    "aicam_overlay_draw": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
 }
 
 _lib = None

@@ -13,10 +13,10 @@ Differences, all in the direction of the hardware:
   * ``--streams N`` (new) runs N sources through ONE batched ``TrackingPipeline`` step per time
     step (the multi-camera form of the loop: per-stream order is kept, the N frames of a time
     step travel together; N = 1 keeps the reference-shaped facades);
-  * drawing / encoding (visualization.py, cv2.VideoWriter) are outside the hot path and are not
-    rebuilt (DESIGN.md "out of scope"): instead of an annotated video, ``--no_save`` absent
-    writes the track tuples of every frame as JSON lines (same name stem as the reference's
-    output video, ``.tracks.jsonl``).
+  * the annotated video the reference writes (:211-236) is drawn ON THE DEVICE (visualization.py: box outlines,
+    labels, status panel on a device copy of the frame the detector already uploaded) and only then copied back for
+    ``cv2.VideoWriter`` (this image has no NVENC: the encode stays on the host); next to it the track tuples of every
+    frame go to ``<stem>.tracks.jsonl``.  Batched mode writes videos only with ``--save_video`` (one per stream).
 """
 import argparse
 import json
@@ -39,7 +39,8 @@ def parse_arguments(argv=None) -> argparse.Namespace:
     parser.add_argument("--output_filename", type=str, default=None,
                         help="Name of the output file. If None, generated from input name or timestamp.")
     parser.add_argument("--show_display", action="store_true", help="Accepted for compatibility; no window is opened.")
-    parser.add_argument("--no_save", action="store_true", help="Do not save the track tables.")
+    parser.add_argument("--no_save", action="store_true", help="Do not save the output video / track tables.")
+    parser.add_argument("--save_video", action="store_true", help="Batched mode: also write one annotated video per stream.")
     parser.add_argument("--yolo_engine", type=str, default=str(config.YOLO_ENGINE_PATH),
                         help="Path to the YOLO weight blob (.aicw; replaces the TensorRT engine file).")
     parser.add_argument("--reid_engine", type=str, default=str(config.REID_ENGINE_PATH),
@@ -85,11 +86,13 @@ class LoopStats:
                 "p50_ms": self.percentile(50), "p99_ms": self.percentile(99)}
 
 
-def run_single_stream(frames: Iterable[np.ndarray], detector, tracker, on_frame=None, share_upload=True) -> LoopStats:
+def run_single_stream(frames: Iterable[np.ndarray], detector, tracker, on_frame=None, share_upload=True, stats_out=None) -> LoopStats:
     """The reference's while-loop body (:169-207) for one stream.  ``on_frame(idx, frame, dets, tracks)``
     receives what the loop would draw.  share_upload: hand ``update`` the frame ``detect`` already
     uploaded (one H2D per frame instead of two)."""
     stats = LoopStats()
+    if stats_out is not None:
+        stats_out.append(stats)  # (callbacks read the running fps from it)
     for idx, frame_bgr in enumerate(frames):
         t0 = time.time()
         det_bboxes, det_scores, det_class_ids, _ = detector.detect(frame_bgr)
@@ -101,7 +104,7 @@ def run_single_stream(frames: Iterable[np.ndarray], detector, tracker, on_frame=
     return stats
 
 
-def run_batched(sources: List[Iterable[np.ndarray]], pipeline, on_step=None, max_steps=0) -> LoopStats:
+def run_batched(sources: List[Iterable[np.ndarray]], pipeline, on_step=None, max_steps=0, stats_out=None) -> LoopStats:
     """N streams, one ``TrackingPipeline.step`` per time step.  Frames are read on the host (cv2), staged in two
     pinned buffers and uploaded on a copy stream while the previous step computes; per-stream frame order is kept.
     Stops when the first source ends.  Time per step = wall time from "frames of the step are on the host" to
@@ -111,6 +114,8 @@ def run_batched(sources: List[Iterable[np.ndarray]], pipeline, on_step=None, max
     S = pipeline.n_streams
     assert len(its) == S
     stats = LoopStats()
+    if stats_out is not None:
+        stats_out.append(stats)
     host = dev_buf = None
     T = pipeline.tracker.T
     out_host = [torch.empty((S, T, 6), dtype=torch.int32).pin_memory(), torch.empty((S, T), dtype=torch.float32).pin_memory(),
@@ -164,6 +169,37 @@ def video_frames(path_or_id, max_frames=0):
         cap.release()
 
 
+class AnnotatedWriter:
+    """The reference's visualisation + save step (:211-236) with the drawing on the device: ``write(frame_dev, tracks,
+    lines)`` draws the tracks and the status panel on a device COPY of the frame (the reference draws on
+    ``frame_bgr.copy()``), copies it back and hands it to cv2.VideoWriter (mp4v, as the reference :150-157)."""
+
+    def __init__(self, path, device, fps=config.DEFAULT_OUTPUT_FPS):
+        from .visualization import Overlay
+        self.path, self.fps, self.device = str(path), fps, device
+        self.overlay = Overlay(device)
+        self.writer = None
+
+    def write(self, frame_dev, tracked, info_lines):
+        import cv2
+        from .visualization import Overlay
+        vis = frame_dev.reshape(frame_dev.shape[-3:]).clone()
+        H, W = int(vis.shape[0]), int(vis.shape[1])
+        lines = list(info_lines)
+        self.overlay.draw(vis, [self.overlay.track_items(tracked, (H, W))],
+                          panels=[(lambda img: Overlay._draw_info_panel(img, lines)) if lines else None])
+        if self.writer is None:
+            self.writer = cv2.VideoWriter(self.path, cv2.VideoWriter_fourcc(*"mp4v"), self.fps, (W, H))
+            if not self.writer.isOpened():
+                raise RuntimeError("Could not open video writer for %s" % self.path)
+        self.writer.write(vis.cpu().numpy())
+
+    def close(self):
+        if self.writer is not None:
+            self.writer.release()
+            self.writer = None
+
+
 def tracks_to_rows(table_host, s):
     ot, oc, on = table_host
     return [tuple(int(v) for v in ot[s, k, :5]) + (config.CLASSES[int(ot[s, k, 5])], float(oc[s, k])) for k in range(int(on[s]))]
@@ -186,6 +222,8 @@ def main(argv=None):
         stem = Path(args.output_filename).stem if args.output_filename else "%s_tracked_%s" % (names[0], time.strftime("%Y%m%d-%H%M%S"))
         writer = open(out_dir / (stem + ".tracks.jsonl"), "w")
         print(f"Track tables will be saved to: {writer.name}")
+    videos = []
+    source_name = Path(inputs[0]).name if inputs else f"webcam_{args.webcam_id}"
     try:
         if args.streams > 0:
             from .pipeline import TrackingPipeline
@@ -194,14 +232,29 @@ def main(argv=None):
                                     conf_threshold=args.conf_thresh)
             srcs = [video_frames(sources_spec[s % len(sources_spec)], args.max_frames) for s in range(args.streams)]
 
+            if writer and args.save_video:
+                videos = [AnnotatedWriter(out_dir / ("%s_s%02d.mp4" % (stem, s)), device) for s in range(args.streams)]
+            dev_frames = {}
+            pipe_step = pipe.step
+
+            def step_and_keep(frames_dev, *a, **k):  # (the step's device frames, for the overlay)
+                dev_frames["f"] = frames_dev
+                return pipe_step(frames_dev, *a, **k)
+            pipe.step = step_and_keep
+            stats_ref = []
+
             def on_step(step, batch, table):
                 if writer:
+                    tabs = [t.numpy() for t in table]
+                    fps = stats_ref[0].fps() * args.streams if stats_ref else 0.0
                     for s in range(args.streams):
-                        writer.write(json.dumps({"frame": step, "stream": s, "tracks": tracks_to_rows(
-                            [t.numpy() for t in table], s)}) + "\n")
+                        rows = tracks_to_rows(tabs, s)
+                        writer.write(json.dumps({"frame": step, "stream": s, "tracks": rows}) + "\n")
+                        if videos:
+                            videos[s].write(dev_frames["f"][s], rows, ["AICamera: YOLOv8 + DeepSORT", f"Input: {source_name}", "FPS: %.2f" % fps])
                 if (step + 1) % 100 == 0:
                     print(f"Processed {step + 1} steps.")
-            stats = run_batched(srcs, pipe, on_step)
+            stats = run_batched(srcs, pipe, on_step, stats_out=stats_ref)
             frames = stats.frames * args.streams
         else:
             from .deepsort_tracker import DeepSORT
@@ -211,16 +264,25 @@ def main(argv=None):
             print("Initializing DeepSORT Tracker...")
             trk = DeepSORT(reid_model_path=args.reid_engine, device=device)
 
+            if writer:
+                videos = [AnnotatedWriter(out_dir / (stem + ".mp4"), device)]
+                print(f"Output video will be saved to: {videos[0].path}")
+            loop_stats = []
+
             def on_frame(idx, frame, dets, tracks):
                 if writer:
                     writer.write(json.dumps({"frame": idx, "stream": 0, "tracks": tracks}) + "\n")
+                    fps = loop_stats[0].fps() if loop_stats else 0.0  # frames / sum of detect + update time, as the reference (:204-207)
+                    videos[0].write(det.device_frame, tracks, ["AICamera: YOLOv8 + DeepSORT", f"Input: {source_name}", "FPS: %.2f" % fps])
                 if (idx + 1) % 100 == 0:
                     print(f"Processed {idx + 1} frames.")
-            stats = run_single_stream(video_frames(sources_spec[0], args.max_frames), det, trk, on_frame)
+            stats = run_single_stream(video_frames(sources_spec[0], args.max_frames), det, trk, on_frame, stats_out=loop_stats)
             frames = stats.frames
     finally:
         if writer:
             writer.close()
+        for v in videos:
+            v.close()
     print("\n--- Processing Summary ---")
     print(f"Total frames processed: {frames}")
     print(f"Total time: {stats.total_s:.2f} seconds")

@@ -51,3 +51,29 @@ def tracked_class_mask():
             else:
                 hi |= 1 << (i - 64)
     return lo, hi
+
+
+# ---- visualisation (src/config.py:55-85) ----------------------------------------------------------------------------
+# The reference draws one random BGR colour per class name, re-drawn at every start (its seed line is commented out,
+# src/config.py:57); here the table is drawn once from a fixed seed so that runs - and overlay parity tests - agree.
+def _class_colors():
+    import random
+    rng = random.Random(42)
+    return {name: [rng.randint(0, 255) for _ in range(3)] for name in CLASSES}
+
+
+CLASS_COLORS = _class_colors()
+DEFAULT_TRACK_COLOR = (0, 255, 0)
+FONT = 0                 # cv2.FONT_HERSHEY_SIMPLEX
+FONT_SCALE_ID = 0.7
+FONT_SCALE_INFO = 0.9
+FONT_THICKNESS = 2
+DEFAULT_OUTPUT_FPS = 30
+
+
+def get_track_color(class_name):
+    return CLASS_COLORS.get(class_name, DEFAULT_TRACK_COLOR)
+
+
+def get_class_color(class_name):
+    return CLASS_COLORS.get(class_name, (200, 200, 200))

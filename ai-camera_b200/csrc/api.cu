@@ -65,6 +65,19 @@ bool profile_begin(cudaStream_t st, size_t* slot) {
   return true;
 }
 bool profile_enabled() { return g_profile; }
+
+// Step timeline (debug): while enabled, every conv_win launch is handed the next 4-slot record of a device buffer and
+// its CTA 0 stamps %globaltimer there at entry, when its dependency on the previous kernel has resolved, and at exit;
+// slot 3 holds a host-written tag (cout, cin, height).  A CUDA-graph capture made while the timeline is on keeps the
+// records, so replays give the IN-GRAPH timing of every layer (aicam_debug_timeline).
+static long long* g_tl_dev = nullptr;
+static int g_tl_cap = 0, g_tl_next = 0;
+static std::vector<long long> g_tl_tags;
+long long* timeline_slot(long long tag) {
+  if (!g_tl_dev || g_tl_next >= g_tl_cap) return nullptr;
+  g_tl_tags.push_back(tag);
+  return g_tl_dev + 4 * static_cast<size_t>(g_tl_next++);
+}
 void profile_end(cudaStream_t st, size_t slot) { cudaEventRecord(g_events[slot].second, st); }
 
 }  // namespace aicam
@@ -74,6 +87,32 @@ extern "C" {
 int aicam_version(void) { return 100; }
 const char* aicam_last_error(void) { return aicam::g_error.c_str(); }
 uint64_t aicam_launch_count(void) { return aicam::g_launches.load(); }
+
+int aicam_debug_timeline(int op, long long* host_out, int capacity) {
+  // op 1: start (allocate `capacity` records, restart numbering), op 2: copy the records to host_out ([n][4]: entry ns,
+  // dependency-resolved ns, exit ns, tag), returns their number; op 0: stop and free
+  using namespace aicam;
+  if (op == 1) {
+    if (g_tl_dev) cudaFree(g_tl_dev);
+    g_tl_dev = nullptr; g_tl_next = 0; g_tl_tags.clear();
+    if (capacity <= 0 || cudaMalloc(&g_tl_dev, sizeof(long long) * 4 * capacity) != cudaSuccess) return fail(AICAM_ERR_CUDA, "debug_timeline: allocation failed");
+    cudaMemset(g_tl_dev, 0, sizeof(long long) * 4 * capacity);
+    g_tl_cap = capacity;
+    return AICAM_OK;
+  }
+  if (op == 2) {
+    if (!g_tl_dev || !host_out) return fail(AICAM_ERR_INVALID_ARG, "debug_timeline: not started");
+    const int n = std::min(g_tl_next, capacity);
+    if (cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(host_out, g_tl_dev, sizeof(long long) * 4 * n, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return fail(AICAM_ERR_CUDA, "debug_timeline: copy failed");
+    for (int i = 0; i < n; ++i) host_out[4 * i + 3] = g_tl_tags[i];
+    return n;
+  }
+  if (g_tl_dev) cudaFree(g_tl_dev);
+  g_tl_dev = nullptr; g_tl_cap = 0; g_tl_next = 0; g_tl_tags.clear();
+  return AICAM_OK;
+}
 
 int aicam_profile_enable(int on) {
   aicam::g_profile = on != 0;

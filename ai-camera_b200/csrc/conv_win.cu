@@ -73,6 +73,7 @@ struct WinArgs {
   int nres;               // residual staging buffers (TMA-loaded one or two tiles ahead)
   int nstage;             // output staging buffers (2: the store of tile i overlaps the staging of tile i + 1)
   long long* trace;       // debug: clock64 stamps of CTA 0 (AICAM_CONV_TRACE in aicam_conv2d_bench)
+  long long* tl;          // debug (aicam_debug_timeline): %globaltimer of CTA 0 at entry / dependency resolved / exit
   int res_direct;  // residual read straight from global in the finish phase (no staging): deep, streamed layers
   int out_s2d;  // window modes: the output is stored space-to-depth: [h/2][w/2][2x2 sub-pixel][out_cstride]
   int flat;  // 1x1 mode: output and residual are dense, pixel p of the batch sits at p * cstride
@@ -112,6 +113,12 @@ struct WinArgs {
   uint32_t off_w, off_b, off_stage, off_res, stage_pitch, res_pitch;
   float4 bias4[128];  // TMA epilogue: the bias (<= 512 channels) read from the constant bank, not from shared memory
 };
+
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ float silu_fast(float x) {
   // x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU instead of two
@@ -305,6 +312,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
   else m_tiles = (static_cast<long long>(batch) * a.hw + TM - 1) / TM;
   const int total_tiles = static_cast<int>(m_tiles) * a.n_tiles;
   pdl_trigger();  // the next layer's CTAs may take over each SM as soon as the CTA here exits
+  if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) a.tl[0] = global_timer_ns();
   if (static_cast<int>(blockIdx.x) >= total_tiles) return;
 
   if (threadIdx.x == 0) {
@@ -698,6 +706,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
     // ================================================================== patch (A) producer
     if (lane == 0) {
       pdl_wait();  // the patches are the previous layer's output
+      if (a.tl && blockIdx.x == 0) a.tl[1] = global_timer_ns();
       const uint32_t a_ring = sbase + OFF_RING_A;
       uint32_t sa = 0, pa = 1;
       const uint32_t n_sa = a.sa;
@@ -877,6 +886,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
     if (lane == 0) bulk_wait_all();
   }
   __syncthreads();
+  if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) a.tl[2] = global_timer_ns();
   if (warp == 4 * NWG) {
     tc_fence_after();
     tc_dealloc(tmem_base, a.tmem_cols);
@@ -967,6 +977,7 @@ struct WinPlan {
 // Returns 1 when the layer was launched on the window kernel, 0 when the shape is not eligible
 // (the caller falls back to conv_tc_kernel), negative on error.
 int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream);
+long long* timeline_slot(long long tag);  // api.cu
 
 int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream) {
   if (mode_is_flatwin(pc, L) && pc.w_pair) {  // 64 / 128-channel 3x3 layers of a zero-bordered trunk: CTA pairs (conv_pair.cu)
@@ -1245,6 +1256,7 @@ plan:
   a.res = L.res; a.res_img_stride = L.res_img_stride; a.res_cstride = L.res_cstride; a.res_coff = L.res_coff; a.res_mode = res_mode;
   a.act = L.act;
   a.trace = L.trace;
+  a.tl = timeline_slot(pc.cout * 1000000ll + pc.cin_pad * 1000ll + L.h);
   a.out_s2d = (window && L.out_s2d) ? 1 : 0;
   a.s2d_store = (epi && s2d_store) ? 1 : 0;
   a.batch = L.batch; a.batch_dev = L.batch_dev;

@@ -52,6 +52,11 @@ uint64_t aicam_launch_count(void);
  * Not for use under CUDA-graph capture. */
 int aicam_profile_enable(int on);
 int aicam_profile_conv(double* total_ms, uint64_t* launches);
+/* Debug: in-graph timeline of the window-convolution launches.  op 1: start with room for `capacity` launches (each
+ * later launch - also inside a CUDA-graph capture - gets a record its CTA 0 stamps with the GPU's global timer at entry,
+ * when its dependency on the previous kernel has resolved, and at exit); op 2: copy the records to host_out
+ * ([n][4] int64: entry ns, dependency ns, exit ns, tag = cout * 1e6 + cin * 1e3 + input height), returns n; op 0: stop. */
+int aicam_debug_timeline(int op, long long* host_out, int capacity);
 
 /* ------------------------------------------------------------------------------------------
  * Engine: replaces TRTEngine (src/trt_utils/trt_engine.py:15-216): __init__/_init_engine
@@ -342,6 +347,26 @@ int aicam_lsap(const float* cost, int count, int nr, int nc, int32_t* col_for_ro
 /* KalmanFilter.gating_distance (kalman_filter.py:206-249): state fp32 [n][24] (mean8+cov16),
  * meas fp32 [n][m][4] -> d2 fp32 [n][m]. */
 int aicam_kf_gating(const float* state, const float* meas, int n, int m, float* d2, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Overlay: replaces the drawing loop of src/utils/visualization.py (draw_tracks :72-124,
+ * draw_detections :9-69, draw_fps :127-167, draw_info_panel :170-227: cv2.rectangle / cv2.putText on a host
+ * copy of every frame, called from src/aicamera_tracker.py:211-225) on frames that stay in device memory.
+ * frames_bgr u8 [batch][h][w][3], drawn in place.  Frame n's items are items[item_start[n] .. item_start[n + 1])
+ * (both device arrays), drawn IN ORDER like the sequential cv2 calls:
+ *   type 0  cv2.rectangle(.., (x1, y1), (x2, y2), color, 2): the 3-pixel band around the rectangle minus its
+ *           four outer corner pixels (what OpenCV's thick-line rasteriser fills), clipped to the frame
+ *   type 1  cv2.rectangle(.., color, -1): the inclusive filled rectangle
+ *   type 2  decal `slot` of the atlas (u8 [slots][slot_h][slot_w][8]: B0 B1 B2 0 A0 A1 A2 0 per pixel), its
+ *           first pixel at (x1, y1), (x2, y2) = the used (width, height): frame = B + (frame * A + 127) / 255 per
+ *           channel; (B, A) = (0, 255) leaves a pixel untouched.  ai-camera_b200/visualization.py builds decals
+ *           of anti-aliased text by running cv2.putText itself on a black and a white canvas.
+ * color = b | g << 8 | r << 16. */
+typedef struct {
+  int32_t type, x1, y1, x2, y2, color, slot, reserved;
+} aicam_overlay_item;
+int aicam_overlay_draw(uint8_t* frames_bgr, int batch, int h, int w, const aicam_overlay_item* items,
+                       const int32_t* item_start, const uint8_t* atlas, int slot_w, int slot_h, void* stream);
 
 #ifdef __cplusplus
 }

@@ -124,3 +124,45 @@ def test_frame_loop_single_upload_equals_double_upload(blobs):
         run_single_stream(frames, det, trk, on_frame=lambda i, f, d, tr: res.append(tr), share_upload=share)
         outs.append(res)
     assert outs[0] == outs[1] and sum(len(r) for r in outs[0]) > 0
+
+
+def test_frame_loop_writes_device_drawn_video(blobs, tmp_path):
+    """The loop's save step (src/aicamera_tracker.py:211-236): the frames the AnnotatedWriter hands cv2.VideoWriter are
+    the reference's draw_tracks + draw_info_panel of the same frame and tracks (drawn on the device copy of the frame the
+    detector uploaded), and the file it writes decodes to as many frames."""
+    import cv2
+    from ai_camera_b200 import synth
+    from ai_camera_b200.aicamera_tracker import AnnotatedWriter, run_single_stream
+    from ai_camera_b200.deepsort_tracker import DeepSORT
+    from ai_camera_b200.yolo_detector import YOLODetector
+    import test_overlay as T
+    rv = T.reference_visualization()
+    yolo, reid = blobs
+    frames = _clip_frames(10)
+    det = YOLODetector(yolo)
+    synth.apply_class_bias(det.trt_engine, synth.shifted_class_bias(yolo, synth.CLIP_LOGIT_SHIFT))
+    trk = DeepSORT(reid, n_init=2)
+    out = AnnotatedWriter(tmp_path / "clip_tracked.mp4", det.device)
+    written, drawn = [], 0
+    real_write = None
+
+    def on_frame(idx, frame, dets, tracks):
+        nonlocal real_write, drawn
+        lines = ["AICamera: YOLOv8 + DeepSORT", "Input: clip", "FPS: %.2f" % (10.0 + idx)]
+        out.write(det.device_frame, tracks, lines)
+        if real_write is None:  # (after the first call the cv2 writer exists: tap what it is given)
+            real_write = out.writer.write
+            out.writer = type("Tap", (), {"write": lambda self, img: (written.append(img.copy()), real_write(img))[1],
+                                          "release": out.writer.release})()
+        else:
+            ref = rv.draw_info_panel(rv.draw_tracks(frame.copy(), tracks), lines)
+            T.check_close(written[-1], ref, max_diff=6)
+            drawn += len(tracks)
+    run_single_stream(frames, det, trk, on_frame=on_frame)
+    out.close()
+    assert drawn > 0, "no track was drawn on the clip frames"
+    cap = cv2.VideoCapture(str(tmp_path / "clip_tracked.mp4"))
+    n = 0
+    while cap.read()[0]:
+        n += 1
+    assert n == len(frames)
