@@ -8,7 +8,11 @@ Everything between the arguments and the returned list runs on the device: class
 filter, crops, ReID network, Kalman predict, gated appearance cascade, IoU matching, LSAP,
 updates, initiation, pruning and output formatting.  The tracker state lives in HBM; each
 instance has its own id counter starting at 1 (the reference uses a process-global counter
-reset by every TrackerCore, tracker_core.py:42)."""
+reset by every TrackerCore, tracker_core.py:42).
+
+Like ``YOLODetector.detect``, the device side of ``update`` is captured in a CUDA graph after two eager calls and
+replayed per frame (keyed by the frame buffer it reads); ``AICAM_NO_FACADE_GRAPH=1`` keeps the calls eager."""
+import os
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -49,18 +53,62 @@ class DeepSORT:
         self._out_dev = torch.zeros(1 + 7 * T, dtype=torch.int32, device=self.device)
         self._frame_host = None
         self._frame_dev = None
+        self._graphs = {}    # (frame buffer address, shape) -> CUDAGraph of _run(); False: capture failed
+        self._calls = {}
+        self._no_graph = bool(os.environ.get("AICAM_NO_FACADE_GRAPH"))
         print("DeepSORT Tracker initialized.")
 
-    def _upload(self, frame_bgr):
+    def _stage(self, frame_bgr):
+        """(device frame [1, H, W, 3], from_host): a CUDA tensor is used where it lies; a numpy frame goes into the pinned
+        buffer and is uploaded by _run()."""
         if isinstance(frame_bgr, torch.Tensor):
-            return frame_bgr if frame_bgr.dim() == 4 else frame_bgr.unsqueeze(0)
+            return (frame_bgr if frame_bgr.dim() == 4 else frame_bgr.unsqueeze(0)), False
         shape = tuple(frame_bgr.shape)
         if self._frame_host is None or tuple(self._frame_host.shape[1:]) != shape:
             self._frame_host = torch.empty((1,) + shape, dtype=torch.uint8).pin_memory()
             self._frame_dev = torch.empty((1,) + shape, dtype=torch.uint8, device=self.device)
         self._frame_host[0].numpy()[...] = frame_bgr
-        self._frame_dev.copy_(self._frame_host, non_blocking=True)
-        return self._frame_dev
+        return self._frame_dev, True
+
+    def _run(self, frames, from_host):
+        """Device side of update(): detections (and, for a numpy frame, the frame) from pinned memory, K5-K12, packed result
+        -> pinned host.  Asynchronous; fixed addresses: capturable."""
+        K, T = self.K, self.T
+        if from_host:
+            self._frame_dev.copy_(self._frame_host, non_blocking=True)
+        d = self._in_dev
+        d.copy_(self._in_host, non_blocking=True)
+        num = d[0:1]
+        boxes = d[4:4 + 4 * K].view(torch.float32).view(1, K, 4)
+        scores = d[4 + 4 * K:4 + 5 * K].view(torch.float32).view(1, K)
+        labels = d[4 + 5 * K:4 + 6 * K].view(1, K)
+        out_tracks, out_conf, out_count = self._trk.update(frames, num, boxes, scores, labels)
+        o = self._out_dev
+        o[0:1].copy_(out_count)
+        o[1:1 + 6 * T].copy_(out_tracks.reshape(-1))
+        o[1 + 6 * T:].view(torch.float32).copy_(out_conf.reshape(-1))
+        self._out_host.copy_(o, non_blocking=True)
+
+    def _run_graphed(self, frames, from_host):
+        key = (frames.data_ptr(), tuple(frames.shape), from_host)
+        g = False if self._no_graph else self._graphs.get(key)
+        if len(self._calls) > 64:  # (callers that hand in a fresh tensor per frame: nothing to replay, keep the table small)
+            self._calls.clear()
+        n = self._calls[key] = self._calls.get(key, 0) + 1
+        if g is None and n > 2 and len(self._graphs) < 8:
+            try:
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run(frames, from_host)
+            except Exception as e:  # (stay eager for this buffer)
+                print(f"DeepSORT: CUDA graph capture failed ({e}); running eager")
+                g = False
+            self._graphs[key] = g
+        if g:
+            g.replay()
+        else:
+            self._run(frames, from_host)
 
     def update(self, yolo_bboxes_xyxy: np.ndarray, yolo_confidences: np.ndarray, yolo_class_ids: np.ndarray,
                original_frame_bgr) -> List[Tuple[int, int, int, int, int, str, float]]:
@@ -75,19 +123,9 @@ class DeepSORT:
             h[4:4 + 4 * n].view(np.float32)[:] = np.asarray(yolo_bboxes_xyxy, dtype=np.float32).reshape(-1)
             h[4 + 4 * K:4 + 4 * K + n].view(np.float32)[:] = np.asarray(yolo_confidences, dtype=np.float32)
             h[4 + 5 * K:4 + 5 * K + n] = np.asarray(yolo_class_ids).astype(np.int32)
-        frames = self._upload(original_frame_bgr)
-        d = self._in_dev
-        d.copy_(self._in_host, non_blocking=True)
-        num = d[0:1]
-        boxes = d[4:4 + 4 * K].view(torch.float32).view(1, K, 4)
-        scores = d[4 + 4 * K:4 + 5 * K].view(torch.float32).view(1, K)
-        labels = d[4 + 5 * K:4 + 6 * K].view(1, K)
-        out_tracks, out_conf, out_count = self._trk.update(frames, num, boxes, scores, labels)
-        o = self._out_dev
-        o[0:1].copy_(out_count)
-        o[1:1 + 6 * T].copy_(out_tracks.reshape(-1))
-        o[1 + 6 * T:].view(torch.float32).copy_(out_conf.reshape(-1))
-        self._out_host.copy_(o, non_blocking=True)
+        frames, from_host = self._stage(original_frame_bgr)
+        with torch.cuda.device(self.device):
+            self._run_graphed(frames, from_host)
         torch.cuda.current_stream(self.device).synchronize()
         r = self._out_host.numpy()
         m = int(r[0])
