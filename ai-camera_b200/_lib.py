@@ -86,6 +86,8 @@ SIGNATURES = {
     "aicam_yolo_forward": (_I, [_P, _P, _I, _P, _P]),
     "aicam_yolo_forward_s2d": (_I, [_P, _P, _I, _P, _P]),
     "aicam_engine_accepts_s2d": (_I, [_P]),
+    "aicam_yolo_detect": (_I, [_P, _P, _I, _I, C.POINTER(NmsParams), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "aicam_engine_fused_decode": (_I, [_P]),
     "aicam_reid_forward": (_I, [_P, _P, _I, _P, _P, _P]),
     "aicam_reid_forward_nhwc8": (_I, [_P, _P, _I, _P, _P, _P]),
     "aicam_engine_accepts_nhwc8": (_I, [_P]),

@@ -69,6 +69,7 @@ struct PairArgs {
   uint32_t res_tx_bytes;
   float4 bias4[128];  // the bias, read from the constant bank
   long long* trace;  // debug: clock64 stamps of CTA 0 (AICAM_CONV_TRACE in aicam_conv2d_bench), same slots as conv_win.cu
+  int warp_arrive;   // one elected lane per epilogue warp arrives on the mbarriers (default) instead of every thread (conv_win.cu)
 };
 
 #define PAIR_TRACE(it, who) do { if (a.trace && blockIdx.x == 0 && (it) < 32) a.trace[(it) * 16 + (who)] = clock64(); } while (0)
@@ -205,9 +206,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) conv_pair_kernel(const __grid
       mbar_init(bar_peer_a + 8 * s, 1); mbar_init(bar_peer_b + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 128 * NWG);
+      mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, a.warp_arrive ? 4 * NWG : 128 * NWG);
       mbar_init(bar_peer_acc + 8 * s, 1);
-      mbar_init(bar_res_full + 8 * s, 1); mbar_init(bar_res_empty + 8 * s, 128 * NWG);
+      mbar_init(bar_res_full + 8 * s, 1); mbar_init(bar_res_empty + 8 * s, a.warp_arrive ? 4 * NWG : 128 * NWG);
       mbar_init(bar_stage_free + 8 * s, 1);
     }
     mbar_init(bar_w_full, 1);
@@ -289,8 +290,16 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) conv_pair_kernel(const __grid
       }
       if (!stage_ok) mbar_wait(bar_stage_free + 8 * sbuf, spar ^ 1);
       tc_fence_before();
-      mbar_arrive(bar_acc_empty + 8 * buf);
-      if (a.res_mode) mbar_arrive(bar_res_empty + 8 * sbuf);
+      if (a.warp_arrive) {
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_acc_empty + 8 * buf);
+          if (a.res_mode) mbar_arrive(bar_res_empty + 8 * sbuf);
+        }
+      } else {
+        mbar_arrive(bar_acc_empty + 8 * buf);
+        if (a.res_mode) mbar_arrive(bar_res_empty + 8 * sbuf);
+      }
       if (threadIdx.x == 0) PAIR_TRACE(it, 12);
       fence_proxy_async();
       asm volatile("bar.arrive %0, %1;" ::"r"(2 + (it & 1)), "n"(128 * NWG + 32) : "memory");
@@ -609,6 +618,8 @@ int try_launch_conv_pair(const PackedConv& pc, const ConvLaunch& L, cudaStream_t
   const int mt = best_mt, tm = 128 * mt;
   PairArgs a;
   std::memset(&a, 0, sizeof(a));
+  static const bool thread_arrive = getenv("AICAM_WIN_THREAD_ARRIVE") != nullptr;
+  a.warp_arrive = thread_arrive ? 0 : 1;
   a.h = L.h; a.w = L.w; a.hw = hp * wp; a.rw = wp; a.lo = pad_lo(L.in_pad);
   a.slabs = slabs; a.cin_pad = pc.cin_pad;
   a.sa = best_sa; a.sb = best_sb; a.resident = resident ? 1 : 0;

@@ -780,6 +780,7 @@ int launch_conv(const PackedConv& pc, const ConvLaunch& L, cudaStream_t stream) 
     if (wrc < 0) return wrc;
     if (wrc == 1) return AICAM_OK;
     if (L.out_s2d) return fail(AICAM_ERR_UNSUPPORTED, "launch_conv: space-to-depth output needs the window kernel");
+    if (L.decode) return fail(AICAM_ERR_UNSUPPORTED, "launch_conv: the fused Detect decode needs the window kernel");
   }
   // TMA im2col path: whole 128-pixel x slab-channel tiles per instruction (all layers but the stems)
   alignas(64) CUtensorMap tmap;

@@ -55,6 +55,14 @@ struct ConvLaunch {
   //            Same flat-raster arithmetic, fewer wasted positions: h w / ((h + 1)(w + 1)) useful instead of
   //            h w / ((h + 2)(w + 2)) - 71 % instead of 53 % on the 8 x 4 maps of ReID layer 4.
   int in_pad = 0, out_pad = 0;
+  // Detect-head 1x1 layers (window kernel, generic epilogue): instead of storing the fp32 head rows, the epilogue decodes them
+  // where they are staged in shared memory (same arithmetic as decode_kernel, detect_post.cu) and writes the dense per-anchor
+  // arrays the NMS kernel reads.  1: box branch (64 DFL logits -> xyxy), 2: class branch (nc logits -> score, label).
+  int decode = 0;
+  int dec_anchor_base = 0, dec_anchors = 0;  // first anchor of this Detect level inside an image's anchors, anchors per image
+  float* dec_boxes = nullptr;                // [batch][anchors][4]
+  float* dec_scores = nullptr;               // [batch][anchors]
+  int* dec_labels = nullptr;                 // [batch][anchors]
 };
 
 inline int pad_lo(int pad) { return pad == 1 ? 1 : 0; }                    // interior offset (rows and columns)

@@ -88,6 +88,14 @@ struct WinArgs {
                     // for its latency chain (TMEM read -> finish -> staging -> store hand-off)
   int res_inplace;  // TMA epilogue: the residual tile is loaded INTO the output staging buffer and finished in place
                     // (no residual ring): the store of tile i is followed by the residual load of tile i + nstage
+  int warp_arrive;  // epilogue -> MMA / I/O hand-offs: one elected lane per warp arrives on the mbarriers (default) instead of every
+                    // thread: 32 same-address arrives serialise on the shared-memory port the tensor core reads its operands through
+  int decode;       // generic epilogue of a Detect-head 1x1 layer: decode the staged fp32 rows instead of storing them (ConvLaunch::decode)
+  int dec_anchor_base, dec_anchors;
+  float dec_stride;
+  float* dec_boxes;
+  float* dec_scores;
+  int* dec_labels;
   int direct_out;  // generic epilogue: every thread stores its finished 32-byte groups straight to global (whole
                    // sectors, no staging tile): deep streamed layers spend the shared memory on operand rings instead
   int mt, tm;
@@ -259,6 +267,41 @@ __device__ __forceinline__ void finish_group_b(const uint32_t (&v)[16], const fl
   *reinterpret_cast<uint4*>(dst_hi) = o1;
 }
 
+// Detect-head decode inside the generic epilogue (ConvLaunch::decode) - the arithmetic of decode_kernel (detect_post.cu,
+// compiled without FMA contraction: the multiply-add of the DFL expectation is spelled out here).  A 16-column accumulator
+// group of the box branch IS one DFL side: the thread that holds it in registers reduces it to the side's expected distance.
+__device__ __forceinline__ float dfl_side(const uint32_t (&v)[16], const float* bias) {
+  float x[16];
+  const float4* bp = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 b4 = bp[i];
+    x[4 * i] = __uint_as_float(v[4 * i]) + b4.x;
+    x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+    x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+    x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+  }
+  float m = x[0];
+#pragma unroll
+  for (int i = 1; i < 16; ++i) m = fmaxf(m, x[i]);
+  float s = 0.0f, ws = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float e = expf(x[i] - m);
+    s = __fadd_rn(s, e);
+    ws = __fadd_rn(ws, __fmul_rn(e, static_cast<float>(i)));
+  }
+  return __fdiv_rn(ws, s);
+}
+// class branch: running best logit of an ascending column scan (strict compare: the lowest class index wins ties)
+__device__ __forceinline__ void cls_scan(const uint32_t (&v)[16], const float* bias, int c0, int ncols, float& best, int& bi) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float x = __uint_as_float(v[i]) + bias[i];
+    if (c0 + i < ncols && x > best) { best = x; bi = c0 + i; }
+  }
+}
+
 // Tile index -> image, column strip and first raster position (window mode)
 struct TilePos {
   int n_img, strip, q0;
@@ -324,12 +367,12 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);
-      mbar_init(bar_acc_empty + 8 * s, a.epi_alt ? 64 * NWG : 128 * NWG);
+      mbar_init(bar_acc_empty + 8 * s, (a.epi_alt ? 64 * NWG : 128 * NWG) >> (a.warp_arrive ? 5 : 0));
     }
     mbar_init(bar_w_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_res_full + 8 * s, 1);
-      mbar_init(bar_res_empty + 8 * s, a.epi_alt ? 64 * NWG : 128 * NWG);
+      mbar_init(bar_res_empty + 8 * s, (a.epi_alt ? 64 * NWG : 128 * NWG) >> (a.warp_arrive ? 5 : 0));
     }
     mbar_init(bar_stage_free, 1);
     mbar_init(bar_stage_free + 8, 1);
@@ -448,8 +491,16 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
       }
       if (!stage_ok) mbar_wait(sfree_bar, sfree_par);  // (no column group: keep the phases in step)
       tc_fence_before();
-      mbar_arrive(bar_acc_empty + 8 * buf);
-      if (a.res_mode) mbar_arrive(bar_res_empty + 8 * rslot);
+      if (a.warp_arrive) {
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_acc_empty + 8 * buf);
+          if (a.res_mode) mbar_arrive(bar_res_empty + 8 * rslot);
+        }
+      } else {
+        mbar_arrive(bar_acc_empty + 8 * buf);
+        if (a.res_mode) mbar_arrive(bar_res_empty + 8 * rslot);
+      }
       if (threadIdx.x == 0) WIN_TRACE(it, 12);
       fence_proxy_async();  // my staging writes -> visible to the TMA unit
       // hand the tile to the I/O warp: arrive without waiting (it syncs on the same barrier).  Two barrier ids
@@ -525,6 +576,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
       ro[lane] = valid ? img * a.out_img_stride + static_cast<long long>(pix) * a.out_cstride + a.out_coff + n0 : -1;
       if (a.res_mode)
         ro[8 * 32 + lane] = valid ? img * a.res_img_stride + static_cast<long long>(pix) * a.res_cstride + a.res_coff + n0 : -1;
+      if (a.decode)  // (never together with a residual) the anchor row the decode phase writes
+        ro[8 * 32 + lane] = valid ? (static_cast<long long>(pix) << 32) | static_cast<long long>(img * a.dec_anchors + a.dec_anchor_base + pix) : -1;  // (pixel of the level, anchor row of the batch)
     };
     // per-n-tile constants: column range of the TMEM phase, chunks per row of the copy phases.  With a
     // single n-tile (most layers) they are computed once; otherwise again for every tile.
@@ -583,6 +636,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
       if (a.res_direct && valid) res_row = reinterpret_cast<const uint8_t*>(a.res + ro[8 * 32 + lane]);
       // ---- TMEM -> registers -> bias / residual / activation -> my staging row (32 columns in flight)
       const uint32_t taddr = taddr_lane + buf * acc_cols + my_j * a.n_tile;
+      float dec_best = -INFINITY;
+      int dec_bi = 0x7fffffff;
       for (int c0 = c.c_lo; c0 < c.c_hi; c0 += 32) {
         uint32_t v0[16], v1[16];
         const bool two = c0 + 16 < c.c_hi;  // warp-uniform
@@ -590,7 +645,13 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
         tc_ld16_nowait(taddr + c0, v0);
         if (two) tc_ld16_nowait(taddr + c0 + 16, v1);
         tc_ld_wait();
-        if (valid) {
+        if (a.decode == 1) {  // box branch: my 16-column groups are DFL sides -> expected distances, slot `side` of my staging row
+          reinterpret_cast<float*>(my_stage)[c0 >> 4] = dfl_side(v0, bias_s + c0);
+          if (two) reinterpret_cast<float*>(my_stage)[(c0 >> 4) + 1] = dfl_side(v1, bias_s + c0 + 16);
+        } else if (a.decode == 2) {
+          cls_scan(v0, bias_s + c0, c0, c.ncols, dec_best, dec_bi);
+          if (two) cls_scan(v1, bias_s + c0 + 16, c0 + 16, c.ncols, dec_best, dec_bi);
+        } else if (valid) {
           uint8_t* dst = a.direct_out ? out_bytes + ro[lane] * esize : my_stage;
           finish_group<ACT>(v0, bias_s + c.n0 + c0, res_row + c0 * 2, a.res_mode, a.out_f32, dst + c0 * esize);
           if (two)
@@ -598,9 +659,18 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
                               dst + (c0 + 16) * esize);
         }
       }
+      if (a.decode == 2) {  // my columns' best class -> slot `part` of my staging row
+        reinterpret_cast<float*>(my_stage)[2 * part] = dec_best;
+        reinterpret_cast<int*>(my_stage)[2 * part + 1] = dec_bi;
+      }
       // my part of the accumulator buffer has been read: the MMA thread may reuse it for tile it + 2
       tc_fence_before();
-      mbar_arrive(bar_acc_empty + 8 * buf);
+      if (a.warp_arrive) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+      } else {
+        mbar_arrive(bar_acc_empty + 8 * buf);
+      }
       if (threadIdx.x == 0) WIN_TRACE(it, 12);
       const int next = tile + static_cast<int>(gridDim.x);
       const bool more = next < total_tiles;
@@ -611,7 +681,31 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
       if (threadIdx.x == 0) WIN_TRACE(it, 13);
       if (res_staged && more) prefetch_res(cc, buf ^ 1);
       // ---- staging -> global, rows [ROWS_PER_WARP * part, +ROWS_PER_WARP): whole rows per instruction
-      if (c.cpr > 0 && !a.direct_out) {
+      if (a.decode) {
+        // the team's part-0 warp (lane = row) gathers what the column teams left in the row's staging slots
+        const long long packed = ro[8 * 32 + lane];
+        if (part == 0 && packed >= 0) {
+          const int gw = static_cast<int>(packed & 0x7fffffff), idx = static_cast<int>(packed >> 32);
+          if (a.decode == 1) {
+            const float4 d = *reinterpret_cast<const float4*>(my_stage);  // l, t, r, b
+            const int gy = idx / a.w, gx = idx - gy * a.w;
+            const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f, st = a.dec_stride;
+            reinterpret_cast<float4*>(a.dec_boxes)[gw] =
+                make_float4(__fmul_rn(ax - d.x, st), __fmul_rn(ay - d.y, st), __fmul_rn(ax + d.z, st), __fmul_rn(ay + d.w, st));
+          } else {
+            float best = -INFINITY;
+            int bi = 0x7fffffff;
+#pragma unroll
+            for (int q = 0; q < PARTS; ++q) {  // ascending column ranges: a strict compare keeps the lowest index on ties
+              const float ov = reinterpret_cast<const float*>(my_stage)[2 * q];
+              const int oi = reinterpret_cast<const int*>(my_stage)[2 * q + 1];
+              if (ov > best) { best = ov; bi = oi; }
+            }
+            a.dec_scores[gw] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-best)));
+            a.dec_labels[gw] = bi;
+          }
+        }
+      } else if (c.cpr > 0 && !a.direct_out) {
         const int ch = lane & ((1 << c.cpr_sh) - 1);
         for (int rr = lane >> c.cpr_sh; rr < ROWS_PER_WARP; rr += 32 >> c.cpr_sh) {
           const int r = part * ROWS_PER_WARP + rr;
@@ -1295,6 +1389,18 @@ plan:
   a.res_direct = (!epi && res_mode != 0 && !res_staged) ? 1 : 0;
   a.res_inplace = (epi && mode == 4) ? 1 : 0;
   static const bool no_alt = getenv("AICAM_WIN_NO_EPI_ALT") != nullptr;
+  if (L.decode) {
+    // the decode phase reads whole fp32 rows of ONE n-tile from the generic epilogue's staging rows
+    if (mode != 1 || epi || direct_out || n_tiles != 1 || !L.out_f32 || res_mode || (pc.cout & 3) || (L.decode == 1 && pc.cout != AICAM_HEAD_DFL) ||
+        (L.decode == 1 && !L.dec_boxes) || (L.decode == 2 && (!L.dec_scores || !L.dec_labels)) || L.dec_anchors <= 0)
+      return fail(AICAM_ERR_UNSUPPORTED, "conv_win: this layer cannot take the fused Detect decode");
+    a.decode = L.decode; a.dec_anchor_base = L.dec_anchor_base; a.dec_anchors = L.dec_anchors;
+    a.dec_stride = static_cast<float>(AICAM_YOLO_INPUT / L.w);
+    a.dec_boxes = L.dec_boxes; a.dec_scores = L.dec_scores; a.dec_labels = L.dec_labels;
+    a.flat = 0;  // (image, pixel) per row
+  }
+  static const bool thread_arrive = getenv("AICAM_WIN_THREAD_ARRIVE") != nullptr;
+  a.warp_arrive = thread_arrive ? 0 : 1;
   a.epi_alt = (!no_alt && epi && best.mt == 2 && n_tile <= 32 && best.nstage == 2 && (!res_mode || best.nres == 2) && !a.res_inplace) ? 1 : 0;
   const size_t smem = epi ? a.off_stage + static_cast<size_t>(best.stage_buf) * (best.nstage + (a.res_inplace ? 0 : best.nres))
                           : a.off_stage + (direct_out ? 0 : static_cast<size_t>(a.tm) * (stage_pitch + (res_staged ? res_pitch : 0)));

@@ -437,8 +437,16 @@ struct Builder {
   }
 };
 
+// Dense per-anchor arrays of the fused Detect decode (aicam_yolo_detect): when given, the six 1x1 head layers decode their
+// rows in the epilogue and the fp32 head tensor is never written
+struct DecodeTarget {
+  float* boxes;
+  float* scores;
+  int* labels;
+};
+
 int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStream_t stream,
-            const int* n_dev = nullptr, bool input_is_s2d = false) {
+            const int* n_dev = nullptr, bool input_is_s2d = false, const DecodeTarget* dec = nullptr) {
   const void* input_s2d = input;
   if (e->s2d_in >= 0 && !input_is_s2d) {
     __nv_bfloat16* dst = e->buffers[e->s2d_in].ptr;
@@ -524,12 +532,20 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
         L.out_pad = op.out.buf >= 0 ? e->buffers[op.out.buf].pad : 0;
         if (op.res_mode && op.res.buf >= 0 && e->buffers[op.res.buf].pad != L.out_pad)
           return fail(AICAM_ERR_INVALID_ARG, "engine: residual and output layouts differ");
+        if (dec && op.out.buf == -2) {  // a Detect-head 1x1 layer: decode in the epilogue, nothing is stored through L.out
+          L.decode = op.out.coff == 0 ? 1 : 2;
+          L.dec_anchor_base = static_cast<int>(op.out.eoff / e->out_cstride);
+          L.dec_anchors = e->num_anchors;
+          L.dec_boxes = dec->boxes; L.dec_scores = dec->scores; L.dec_labels = dec->labels;
+          L.out = dec->boxes;  // (any aligned address: the planner checks it, the kernel does not use it)
+        }
         rc = launch_conv(pc, L, stream);
         break;
       }
       case Op::CHAIN: {
         const ChainOp& c = e->chains[op.chain];
         if (n_dev) break;  // (device-side batch counts: single layers)
+        if (dec && op.out.buf == -2) break;  // (fused decode: the single layers carry it)
         geom(op.out, 0, &op_, &os, &oc);
         ChainSpec sp;
         sp.nstages = c.nstages;
@@ -777,6 +793,43 @@ int aicam_yolo_forward(aicam_engine* e, const void* in_nhwc4, int batch, float* 
   if (!in_nhwc4 || !head) return fail(AICAM_ERR_INVALID_ARG, "yolo_forward: null tensor");
   if (batch < 0 || batch > e->max_batch) return fail(AICAM_ERR_CAPACITY, "yolo_forward: batch exceeds max_batch");
   return run_ops(e, in_nhwc4, batch, head, static_cast<cudaStream_t>(stream));
+}
+
+int aicam_engine_fused_decode(const aicam_engine* e) {
+  static const bool off = getenv("AICAM_NO_DECODE_FUSION") != nullptr;
+  if (!e || e->kind != AICAM_KIND_YOLOV8 || off) return 0;
+  const int nc = static_cast<int>(e->params[7]);
+  return (nc % 16 == 0 && nc <= 80 && e->num_anchors == 8400) ? 1 : 0;  // one n-tile of whole 16-column groups per branch
+}
+
+int aicam_yolo_detect(aicam_engine* e, const void* in, int in_is_s2d, int batch, const aicam_nms_params* p, float* head,
+                      int32_t* num_dets, float* boxes_lb, float* boxes_orig, float* scores, int32_t* labels, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (!e || e->kind != AICAM_KIND_YOLOV8) return fail(AICAM_ERR_INVALID_ARG, "yolo_detect: not a yolov8 engine");
+  if (batch < 0 || batch > e->max_batch) return fail(AICAM_ERR_CAPACITY, "yolo_detect: batch exceeds max_batch");
+  if (in_is_s2d && e->s2d_in < 0) return fail(AICAM_ERR_UNSUPPORTED, "yolo_detect: this engine was built without the space-to-depth stem");
+  if (!in || !p || !num_dets || !boxes_lb || !scores || !labels) return fail(AICAM_ERR_INVALID_ARG, "yolo_detect: null argument");
+  const int anchors = e->num_anchors, nc = static_cast<int>(e->params[7]);
+  if (batch == 0) return AICAM_OK;
+  if (!aicam_engine_fused_decode(e)) {
+    if (!head) return fail(AICAM_ERR_INVALID_ARG, "yolo_detect: this engine needs the fp32 head tensor (no fused decode)");
+    if (int rc = run_ops(e, in, batch, head, static_cast<cudaStream_t>(stream), nullptr, in_is_s2d != 0)) return rc;
+    return aicam_decode_nms(head, batch, anchors, nc, p, num_dets, boxes_lb, boxes_orig, scores, labels, workspace, workspace_bytes,
+                            stream);
+  }
+  const size_t need = aicam_decode_nms_workspace(batch, anchors, p);
+  if (need == 0 || !workspace || workspace_bytes < need) return fail(AICAM_ERR_CAPACITY, "yolo_detect: workspace too small");
+  // the workspace layout of aicam_decode_nms: dense boxes, scores, labels, then (256-aligned) the suppression masks
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const size_t dense = static_cast<size_t>(batch) * anchors * 24;
+  DecodeTarget dec;
+  dec.boxes = reinterpret_cast<float*>(ws);
+  dec.scores = reinterpret_cast<float*>(ws + static_cast<size_t>(batch) * anchors * 16);
+  dec.labels = reinterpret_cast<int*>(ws + static_cast<size_t>(batch) * anchors * 20);
+  uint8_t* mask = ws + (dense + 255) / 256 * 256;
+  if (int rc = run_ops(e, in, batch, nullptr, static_cast<cudaStream_t>(stream), nullptr, in_is_s2d != 0, &dec)) return rc;
+  return aicam_nms(dec.boxes, dec.scores, dec.labels, batch, anchors, p, num_dets, boxes_lb, boxes_orig, scores, labels, nullptr,
+                   mask, workspace_bytes - static_cast<size_t>(mask - ws), stream);
 }
 
 int aicam_yolo_forward_s2d(aicam_engine* e, const void* in_s2d16, int batch, float* head, void* stream) {

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(THREADS, 1) reid_stem_pool_kernel(const StemAr
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);
-      mbar_init(bar_acc_empty + 8 * s, EPI_WARPS * 32 / 2);  // one group of 8 epilogue warps per accumulator buffer
+      mbar_init(bar_acc_empty + 8 * s, EPI_WARPS / 2);  // one group of 8 epilogue warps per accumulator buffer, one elected arrive per warp
     }
     mbar_init(bar_w_full, 1);
     mbar_init_fence();
@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(THREADS, 1) reid_stem_pool_kernel(const StemAr
       tc_ld16_nowait(taddr_lane + 48, v3);
       tc_ld_wait();
       tc_fence_before();
-      mbar_arrive(bar_acc_empty + 8 * g);  // accumulator read: the MMA warp may reuse the buffer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * g);  // accumulator read: the MMA warp may reuse the buffer
       if (q < NPOS) {
         // raw accumulators as bf16; positions outside the crop lose every max (-inf)
         uint8_t* my_row = conv_s + my_row_off;

@@ -62,15 +62,13 @@ class BatchDetector:
             raise _lib.AicamError(-4, "detect: %d frames exceed the detector's batch %d" % (n, self.batch))
         e, st = self.engine, _lib.stream_ptr(self.device)
         with torch.cuda.device(self.device):
-            if self._s2d:  # same bytes, 2x2 pixel blocks: the stride-2 stem runs as a stride-1 window
-                _lib.check(pre(_lib.ptr(frames), n, h, w, 2, _lib.ptr(e._nhwc), st))
-                _lib.check(self.lib.aicam_yolo_forward_s2d(e.handle, _lib.ptr(e._nhwc), n, _lib.ptr(e._head), st))
-            else:
-                _lib.check(pre(_lib.ptr(frames), n, h, w, 1, _lib.ptr(e._nhwc), st))
-                _lib.check(self.lib.aicam_yolo_forward(e.handle, _lib.ptr(e._nhwc), n, _lib.ptr(e._head), st))
+            # same bytes, 2x2 pixel blocks (format 2): the stride-2 stem runs as a stride-1 window
+            _lib.check(pre(_lib.ptr(frames), n, h, w, 2 if self._s2d else 1, _lib.ptr(e._nhwc), st))
             self._nms.frame_h, self._nms.frame_w = h, w
-            _lib.check(self.lib.aicam_decode_nms(
-                _lib.ptr(e._head), n, e.anchors, e.nc, C.byref(self._nms), _lib.ptr(self.num_dets),
+            # network + decode (fused into the Detect-head epilogues) + NMS + un-letterboxing: one entry
+            _lib.check(self.lib.aicam_yolo_detect(
+                e.handle, _lib.ptr(e._nhwc), 1 if self._s2d else 0, n, C.byref(self._nms),
+                _lib.ptr(e._head) if e._head is not None else None, _lib.ptr(self.num_dets),
                 _lib.ptr(self.boxes_lb), _lib.ptr(self.boxes), _lib.ptr(self.scores), _lib.ptr(self.labels),
                 _lib.ptr(e._ws), e._ws.numel(), st))
         return self.num_dets[:n], self.boxes[:n], self.scores[:n], self.labels[:n]

@@ -60,7 +60,10 @@ class TRTEngine(torch.nn.Module):
             self._nms = _lib.NmsParams(self.score_threshold, self.nms_threshold, self.topk, self.max_candidates, 0, 0)
             ws = self._lib.aicam_decode_nms_workspace(self.max_batch, self.anchors, C.byref(self._nms))
             self._ws = torch.empty(ws, dtype=torch.uint8, device=self.device)
-            self._head = torch.empty((self.max_batch, self.anchors, 64 + self.nc), dtype=torch.float32, device=self.device)
+            # the fp32 head tensor exists only when the engine cannot decode inside its Detect-head epilogues
+            self.fused_decode = bool(self._lib.aicam_engine_fused_decode(self._h))
+            self._head = None if self.fused_decode else torch.empty((self.max_batch, self.anchors, 64 + self.nc),
+                                                                    dtype=torch.float32, device=self.device)
             self._nhwc = torch.empty((self.max_batch, h, w, 4), dtype=torch.bfloat16, device=self.device)
         else:
             self.feature_dim = self._lib.aicam_engine_num_classes(self._h)
@@ -135,14 +138,13 @@ class TRTEngine(torch.nn.Module):
                 if n > self.max_batch:
                     raise RuntimeError(f"execute failed for engine {self.engine_path.name}: batch {n} > {self.max_batch}")
                 _lib.check(self._lib.aicam_nchw_to_nhwc4(_lib.ptr(x), n, x.shape[2], x.shape[3], _lib.ptr(self._nhwc), st))
-                _lib.check(self._lib.aicam_yolo_forward(self._h, _lib.ptr(self._nhwc), n, _lib.ptr(self._head), st))
                 outs['num_dets'] = torch.empty((n, 1), dtype=torch.int32, device=self.device)
                 outs['bboxes'] = torch.empty((n, self.topk, 4), dtype=torch.float32, device=self.device)
                 outs['scores'] = torch.empty((n, self.topk), dtype=torch.float32, device=self.device)
                 outs['labels'] = torch.empty((n, self.topk), dtype=torch.int32, device=self.device)
-                _lib.check(self._lib.aicam_decode_nms(
-                    _lib.ptr(self._head), n, self.anchors, self.nc, C.byref(self._nms), _lib.ptr(outs['num_dets']),
-                    _lib.ptr(outs['bboxes']), None, _lib.ptr(outs['scores']), _lib.ptr(outs['labels']),
+                _lib.check(self._lib.aicam_yolo_detect(
+                    self._h, _lib.ptr(self._nhwc), 0, n, C.byref(self._nms), _lib.ptr(self._head) if self._head is not None else None,
+                    _lib.ptr(outs['num_dets']), _lib.ptr(outs['bboxes']), None, _lib.ptr(outs['scores']), _lib.ptr(outs['labels']),
                     _lib.ptr(self._ws), self._ws.numel(), st))
             else:
                 outs['output'] = torch.empty((n, self.feature_dim), dtype=torch.float32, device=self.device)

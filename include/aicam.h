@@ -243,6 +243,16 @@ int aicam_nms(const float* boxes, const float* scores, const int32_t* labels, in
               const aicam_nms_params* p, int32_t* num_dets, float* boxes_lb, float* boxes_orig,
               float* out_scores, int32_t* out_labels, int32_t* keep_index, void* workspace,
               size_t workspace_bytes, void* stream);
+/* The whole engine call of YOLODetector.detect (yolo_detector.py:97: network + embedded decode + NMS) in one
+ * entry: aicam_yolo_forward[_s2d] + aicam_decode_nms, with the decode FUSED into the epilogues of the six 1x1
+ * Detect-head layers when aicam_engine_fused_decode(e) is 1 - the fp32 head tensor (310 MB per 64 frames,
+ * written once and read once) then never exists and `head` may be NULL; otherwise `head` is the scratch
+ * tensor [batch][anchors][64 + nc].  in: the aicam_preprocess output, format 2 when in_is_s2d, else format 1.
+ * workspace: aicam_decode_nms_workspace bytes.  Results as aicam_decode_nms (same arithmetic, same order). */
+int aicam_yolo_detect(aicam_engine* e, const void* in, int in_is_s2d, int batch, const aicam_nms_params* p,
+                      float* head, int32_t* num_dets, float* boxes_lb, float* boxes_orig, float* scores,
+                      int32_t* labels, void* workspace, size_t workspace_bytes, void* stream);
+int aicam_engine_fused_decode(const aicam_engine* e);
 
 /* ------------------------------------------------------------------------------------------
  * ReID crops: replaces DeepSORT.update steps 1-2 (class/confidence filter,

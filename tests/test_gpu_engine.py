@@ -100,6 +100,50 @@ def test_yolov8_s_m_head_matches_oracle(blobs, scale, gflop):
     assert np.abs(gs[top] - ws[top]).max() < 3e-2
 
 
+@pytest.mark.parametrize("name,batch", [("yolov8n", 3), ("yolov8s", 1)])
+def test_fused_decode_equals_decode_kernel(blobs, name, batch):
+    """aicam_yolo_detect decodes inside the Detect-head epilogues (no fp32 head tensor); the dense per-anchor arrays it
+    hands to the NMS kernel and the final detections must be bit-identical with forward -> decode_kernel -> NMS."""
+    import gpu_util as G
+    rng = np.random.default_rng(7)
+    frames = np.stack([synth_image(rng, 540, 960) for _ in range(batch)])
+    frames[-1] = rng.integers(0, 256, (540, 960, 3), dtype=np.uint8)
+    x = G.preprocess(torch.from_numpy(frames).to(G.DEV), 1)
+    lib = G.lib()
+    e = _engine(blobs[name], batch)
+    try:
+        assert lib.aicam_engine_fused_decode(e) == 1
+        p = G.NmsParams(0.05, 0.5, 100, 1024, 540, 960)
+        nws = lib.aicam_decode_nms_workspace(batch, 8400, C.byref(p))
+
+        def outs():
+            return (torch.zeros(batch, dtype=torch.int32, device=G.DEV), torch.zeros((batch, 100, 4), device=G.DEV),
+                    torch.zeros((batch, 100, 4), device=G.DEV), torch.zeros((batch, 100), device=G.DEV),
+                    torch.zeros((batch, 100), dtype=torch.int32, device=G.DEV))
+        head = torch.empty((batch, 8400, 144), dtype=torch.float32, device=G.DEV)
+        G.check(lib.aicam_yolo_forward(e, G.ptr(x), batch, G.ptr(head), None))
+        db, ds, dl = G.decode(head)
+        ws1 = torch.zeros(nws, dtype=torch.uint8, device=G.DEV)
+        o1 = outs()
+        G.check(lib.aicam_decode_nms(G.ptr(head), batch, 8400, 80, C.byref(p), *[G.ptr(t) for t in o1], G.ptr(ws1), nws, None))
+        ws2 = torch.zeros(nws, dtype=torch.uint8, device=G.DEV)
+        o2 = outs()
+        G.check(lib.aicam_yolo_detect(e, G.ptr(x), 0, batch, C.byref(p), None, *[G.ptr(t) for t in o2], G.ptr(ws2), nws, None))
+        G.sync()
+    finally:
+        lib.aicam_engine_destroy(e)
+    n = batch * 8400
+    fb = ws2[:n * 16].view(torch.float32).reshape(batch, 8400, 4)
+    fs = ws2[n * 16:n * 20].view(torch.float32).reshape(batch, 8400)
+    fl = ws2[n * 20:n * 24].view(torch.int32).reshape(batch, 8400)
+    assert torch.equal(fl, dl), "labels differ"
+    assert torch.equal(fs, ds), "scores differ: max %g" % (fs - ds).abs().max().item()
+    assert torch.equal(fb, db), "boxes differ: max %g" % (fb - db).abs().max().item()
+    assert int(o1[0].sum()) > 0
+    for a, b in zip(o1, o2):
+        assert torch.equal(a, b)
+
+
 def test_reid_embeddings_match_oracle(blobs):
     import gpu_util as G
     from oracle import image_ops, nets
