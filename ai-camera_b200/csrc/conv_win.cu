@@ -48,6 +48,7 @@ constexpr int MAX_RING = 8;
 constexpr uint32_t OFF_BIAS = 512;      // fp32 bias, <= 512 channels
 constexpr uint32_t OFF_ROWOFF = 2560;   // 2 tile parities x (output, residual) x 8 teams x 32 rows x int64 element offsets
 constexpr uint32_t OFF_RING_A = 11264;   // 1024-byte aligned: swizzle patterns repeat every 1024 B
+constexpr uint32_t OFF_RING_A_EPI = 3072;  // TMA epilogue: no row-offset tables, the operand ring starts right after the bias
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 constexpr size_t RESIDENT_LIMIT = 120 * 1024;
 
@@ -90,6 +91,7 @@ struct WinArgs {
                     // (no residual ring): the store of tile i is followed by the residual load of tile i + nstage
   int warp_arrive;  // epilogue -> MMA / I/O hand-offs: one elected lane per warp arrives on the mbarriers (default) instead of every
                     // thread: 32 same-address arrives serialise on the shared-memory port the tensor core reads its operands through
+  int ws;           // MMA issue in the weight-stationary form (tcgen05.mma.ws, collector buffers for B)
   int decode;       // generic epilogue of a Detect-head 1x1 layer: decode the staged fp32 rows instead of storing them (ConvLaunch::decode)
   int dec_anchor_base, dec_anchors;
   float dec_stride;
@@ -150,6 +152,35 @@ __device__ __forceinline__ void mma_issue(bool leader, uint32_t tmem_d, uint32_t
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(leader))
       : "memory");
+}
+// Weight-stationary form (tcgen05.mma.ws): the B block (weights of one tap / K step) is kept in collector buffer BUF - COP 0: fill
+// (fetch from shared memory and keep), 1: lastuse (take it from the collector: no shared-memory fetch), 2: discard (fetch, do not keep).
+// Consecutive MMAs of the accumulators of one tile share their weights, so only the first of them reads B through the port.
+template <int COP>
+__device__ __forceinline__ void mma_issue_ws(int BUF, bool leader, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                             uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+#define AICAM_WS_ASM(BUFS, OPS)                                                                                        \
+  asm volatile(                                                                                                        \
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"                                                               \
+      "setp.ne.b32 p, %6, 0;\n\t"                                                                                      \
+      "setp.ne.b32 q, %7, 0;\n\t"                                                                                      \
+      "mov.b64 da, {%1, %2};\n\t"                                                                                      \
+      "mov.b64 db, {%3, %4};\n\t"                                                                                      \
+      "@q tcgen05.mma.ws.cta_group::1.kind::f16.collector::" BUFS "::" OPS " [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d), \
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(leader))      \
+      : "memory")
+#define AICAM_WS_BUF(BUFS)                         \
+  do {                                             \
+    if (COP == 0) AICAM_WS_ASM(BUFS, "fill");      \
+    else if (COP == 1) AICAM_WS_ASM(BUFS, "lastuse"); \
+    else AICAM_WS_ASM(BUFS, "discard");            \
+  } while (0)
+  if (BUF == 0) AICAM_WS_BUF("b0");
+  else if (BUF == 1) AICAM_WS_BUF("b1");
+  else if (BUF == 2) AICAM_WS_BUF("b2");
+  else AICAM_WS_BUF("b3");
+#undef AICAM_WS_BUF
+#undef AICAM_WS_ASM
 }
 __device__ __forceinline__ void tc_commit_if(bool leader, uint32_t bar) {
   asm volatile(
@@ -318,8 +349,11 @@ __device__ __forceinline__ TilePos tile_pos(const WinArgs& a, int mt_idx) {
 // trace slot layout: [tile < 32][16 stamps]; who: 0-3 MMA warp, 4-5 producer, 8-13 epilogue thread 0
 #define WIN_TRACE(it, who) do { if (a.trace && blockIdx.x == 0 && (it) < 32) a.trace[(it) * 16 + (who)] = clock64(); } while (0)
 
-template <int SLAB, int AMODE, int MT, int ACT, int EPI>
+// EPIW: bit 0 = TMA epilogue, bit 1 = MMAs issued in the weight-stationary form (64-column tiles of the window modes)
+template <int SLAB, int AMODE, int MT, int ACT, int EPIW>
 __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_constant__ WinArgs a, const __grid_constant__ WinMaps maps) {
+  constexpr int EPI = EPIW & 1;
+  constexpr bool WS = (EPIW & 2) != 0;
   constexpr uint32_t ROW_BYTES = SLAB * 2;
   constexpr int K16S = SLAB / 16;
   constexpr uint32_t LTYPE = SLAB == 64 ? 2u : (SLAB == 32 ? 4u : 6u);
@@ -725,7 +759,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
       const bool leader = elect_one();
       const uint32_t a_hi = ((8 * ROW_BYTES) >> 4) | (1u << 14) | (LTYPE << 29);  // SBO | version | swizzle
       const uint32_t b_hi = (128u >> 4) | (1u << 14);                           // SBO = 128 B, no swizzle
-      const uint32_t a_ring = sbase + OFF_RING_A, b_ring = sbase + a.off_b, w_base = sbase + a.off_w;
+      const uint32_t a_ring = sbase + (EPI ? OFF_RING_A_EPI : OFF_RING_A), b_ring = sbase + a.off_b, w_base = sbase + a.off_w;
       const uint32_t rw_units = static_cast<uint32_t>(a.rw) * (ROW_BYTES >> 4);  // one raster row, in 16-byte units
       const uint32_t lbo = static_cast<uint32_t>(a.resident ? a.cout_pad : a.n_tile);  // K-chunk stride, 16-byte units
       const uint32_t b_k16 = 2 * lbo;
@@ -776,12 +810,26 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
               tc_fence_after();
               b_lo = ((b_ring + sbi * a.bstage_bytes) >> 4) | b_lo_flags;
             }
+            if (WS) {  // weight-stationary: K step outermost, the tile's accumulators share the collected weight block
 #pragma unroll
-            for (int j = 0; j < MT; ++j) {
+              for (int k = 0; k < K16S; ++k) {
 #pragma unroll
-              for (int k = 0; k < K16S; ++k)
-                mma_issue(leader, d_tmem + j * n_tile, a_lo + j * (128 * ROW_BYTES >> 4) + k * 2, a_hi, b_lo + k * b_k16, b_hi,
-                          idesc, (s | t | k) != 0 ? 1u : 0u);
+                for (int j = 0; j < MT; ++j) {
+                  const uint32_t acc = (s | t | k) != 0 ? 1u : 0u;
+                  const uint32_t al = a_lo + j * (128 * ROW_BYTES >> 4) + k * 2, bl = b_lo + k * b_k16;
+                  if (MT == 1) mma_issue_ws<2>(k & 3, leader, d_tmem, al, a_hi, bl, b_hi, idesc, acc);
+                  else if (j == 0) mma_issue_ws<0>(k & 3, leader, d_tmem, al, a_hi, bl, b_hi, idesc, acc);
+                  else mma_issue_ws<1>(k & 3, leader, d_tmem + j * n_tile, al, a_hi, bl, b_hi, idesc, acc);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < MT; ++j) {
+#pragma unroll
+                for (int k = 0; k < K16S; ++k)
+                  mma_issue(leader, d_tmem + j * n_tile, a_lo + j * (128 * ROW_BYTES >> 4) + k * 2, a_hi, b_lo + k * b_k16, b_hi,
+                            idesc, (s | t | k) != 0 ? 1u : 0u);
+              }
             }
             if (!a.resident) {
               tc_commit_if(leader, bar_b_empty + 8 * sbi);
@@ -801,7 +849,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
     if (lane == 0) {
       pdl_wait();  // the patches are the previous layer's output
       if (a.tl && blockIdx.x == 0) a.tl[1] = global_timer_ns();
-      const uint32_t a_ring = sbase + OFF_RING_A;
+      const uint32_t a_ring = sbase + (EPI ? OFF_RING_A_EPI : OFF_RING_A);
       uint32_t sa = 0, pa = 1;
       const uint32_t n_sa = a.sa;
       const long long total_pix = static_cast<long long>(batch) * a.hw;
@@ -1001,6 +1049,11 @@ WinKernelFn pick_mt(int mt, int act) {
 }
 template <int SLAB>
 WinKernelFn pick_mode(int mode, int mt, int act, int epi) {
+  if (SLAB == 64 && epi == 3) {  // weight-stationary variants exist for the 64-channel-slab window modes only
+    if (mode == 0) return pick_mt<64, 0, 3>(mt, act);
+    if (mode == 4) return pick_mt<64, 4, 3>(mt, act);
+  }
+  epi &= 1;
   if (mode == 0) return epi ? pick_mt<SLAB, 0, 1>(mt, act) : pick_mt<SLAB, 0, 0>(mt, act);
   if (mode == 3) return epi ? pick_mt<SLAB, 3, 1>(mt, act) : pick_mt<SLAB, 3, 0>(mt, act);
   if (mode == 4) return epi ? pick_mt<SLAB, 4, 1>(mt, act) : pick_mt<SLAB, 4, 0>(mt, act);
@@ -1160,7 +1213,7 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   // streamed (deep-K) layers: the epilogue is a small share of a tile, read the residual from global there
   // instead of spending 70 KB of shared memory that the 256-row tiling needs
   const bool res_staged = res_mode != 0 && resident;
-  const size_t fixed_base = OFF_RING_A + (resident ? (wbytes + 1023) / 1024 * 1024 : static_cast<size_t>(sb) * bstage_bytes);
+  const size_t fixed_tail = (resident ? (wbytes + 1023) / 1024 * 1024 : static_cast<size_t>(sb) * bstage_bytes);
 
   // ---- TMA epilogue (window modes, bf16, natural layout): the n-tile splits into one or two channel pieces
   // of 64 / 32 / 16 channels, each a swizzled staging tile with its own output / residual tensor map
@@ -1184,6 +1237,7 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   const int k16_total = taps * pc.cin_pad / 16;
 plan:
   best = WinPlan();
+  size_t fixed_base = 0;  // set below, once this pass's epilogue flavour is known
   window = mode == 0 || mode == 3;
   // flat / im2col tiles are runs of consecutive output pixels: the store is a 2-D box when pixel p of the batch
   // sits at p * cstride in the output (and residual) tensor
@@ -1198,6 +1252,11 @@ plan:
   if (!window && !(epi_everywhere && flat_io) && !epi_flat) epi = false;
   if (mode == 4) epi = epi4 && piece_ch[0] != 0;  // flat TMA epilogue: border positions are stored as zeros
   else if (opd) epi = false;                        // (un-padded raster -> padded image: row-by-row offsets, generic epilogue)
+  fixed_base = (epi ? OFF_RING_A_EPI : OFF_RING_A) + fixed_tail;
+  // 64-column tiles are bound by the shared-memory port (4 KB of A + 2 KB of B per 32-cycle MMA): the weight-stationary MMA form
+  // keeps a tile's B block in a collector buffer across the accumulators of the tile
+  static const bool no_ws = getenv("AICAM_WIN_NO_WS") != nullptr;
+  const bool ws_ok = !no_ws && epi && slab == 64 && n_tile == 64 && (mode == 0 || mode == 4);
   for (int mt = 1; mt <= 2; ++mt) {
     if (force_mt && mt != force_mt) continue;
     const int tm = 128 * mt;
@@ -1294,7 +1353,10 @@ plan:
         p.smem = fixed + static_cast<size_t>(p.sa) * p.patch_bytes;
         // estimated cycles per tile: tensor pipe vs L2->SM traffic vs epilogue, plus a fixed hand-off cost
         // one 128 x n_tile x 16 MMA: tensor pipe n_tile / 2 cycles, operand fetch (4 KB + n_tile * 32 B) at 128 B/clk
-        const double mma = static_cast<double>(mt) * k16_total * std::max(n_tile / 2.0, 32.0 + n_tile / 4.0);
+        // (weight-stationary issue, two accumulators per tile: the second MMA of a pair takes B from the collector - measured on
+        //  ReID layer 1: 57 cycles per 128 x 64 x 16 MMA instead of 68, tile of 256 rows 4 500 cycles instead of 2 x 2 790)
+        const bool ws_pair = ws_ok && mode == 4 && mt == 2;
+        const double mma = static_cast<double>(mt) * k16_total * std::max(n_tile / 2.0, 32.0 + n_tile / (ws_pair ? 8.0 : 4.0));
         const double l2 = (static_cast<double>(p.box_bytes) * slabs * (mode == 2 ? taps : 1) +
                            (resident ? 0.0 : static_cast<double>(wbytes) / n_tiles)) / 48.0;
         const int groups = (n_tile + 15) / 16;
@@ -1304,7 +1366,7 @@ plan:
                                    : (static_cast<double>(mt) * groups / active) * 1000.0 + 1700.0;
         double per_tile = std::max(mma, std::max(l2, epi_cyc)) + 250.0;
         // shallow rings serialise producer, MMA and epilogue
-        if ((window || (mode == 4 && slabs == 1)) && p.sa < 3) per_tile *= 1.6;
+        if ((window || (mode == 4 && slabs == 1)) && p.sa < 3 && !(ws_pair && p.sa == 2 && p.nstage == 2)) per_tile *= 1.6;
         if (epi && mode != 4 && res_mode && p.nres < 2) per_tile *= 2.0;  // (mode 4 finishes the residual in place)
         p.cost = static_cast<double>(p.tiles) * n_tiles * per_tile;
         p.ok = true;
@@ -1358,7 +1420,7 @@ plan:
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(2 * best.mt * n_tile)) cols <<= 1;
   a.tmem_cols = cols;
-  const uint32_t ring_a_end = OFF_RING_A + static_cast<uint32_t>(best.sa) * best.patch_bytes;
+  const uint32_t ring_a_end = (epi ? OFF_RING_A_EPI : OFF_RING_A) + static_cast<uint32_t>(best.sa) * best.patch_bytes;
   a.off_w = ring_a_end;
   a.off_b = ring_a_end;
   a.off_stage = ring_a_end + static_cast<uint32_t>(resident ? (wbytes + 1023) / 1024 * 1024 : static_cast<size_t>(sb) * bstage_bytes);
@@ -1399,6 +1461,7 @@ plan:
     a.dec_boxes = L.dec_boxes; a.dec_scores = L.dec_scores; a.dec_labels = L.dec_labels;
     a.flat = 0;  // (image, pixel) per row
   }
+  a.ws = (ws_ok && best.mt == 2) ? 1 : 0;
   static const bool thread_arrive = getenv("AICAM_WIN_THREAD_ARRIVE") != nullptr;
   a.warp_arrive = thread_arrive ? 0 : 1;
   a.epi_alt = (!no_alt && epi && best.mt == 2 && n_tile <= 32 && best.nstage == 2 && (!res_mode || best.nres == 2) && !a.res_inplace) ? 1 : 0;
@@ -1507,7 +1570,7 @@ plan:
     fprintf(stderr, "conv_win: %dx%d c%d->%d k%d s%d mode %d mt %d n_tile %d x%d slab %d x%d resident %d sa %d sb %d patch %u bstage %u "
             "epi %d direct %d tiles %lld smem %zu\n", L.h, L.w, pc.cin_pad, pc.cout, pc.ksize, pc.stride, mode, best.mt, n_tile, n_tiles,
             slab, slabs, resident ? 1 : 0, a.sa, a.sb, a.patch_bytes, a.bstage_bytes, epi ? 1 : 0, a.direct_out, best.tiles * n_tiles, smem);
-  WinKernelFn kernel = pick_kernel(slab, mode, best.mt, L.act, epi ? 1 : 0);
+  WinKernelFn kernel = pick_kernel(slab, mode, best.mt, L.act, (epi ? 1 : 0) | (a.ws ? 2 : 0));
   if (int rc = ensure_dynamic_smem(kernel, SMEM_LIMIT)) return rc;  // per (device, instantiation)
   const int num_sms = current_num_sms();
   const long long total_tiles = best.tiles * n_tiles;
