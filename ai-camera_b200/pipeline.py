@@ -74,7 +74,8 @@ class BatchDetector:
         return self.num_dets[:n], self.boxes[:n], self.scores[:n], self.labels[:n]
 
     def launches_per_step(self):
-        return 1 + self.engine.launches_per_forward() + 2
+        # K1 + network + NMS (+ the decode kernel when the engine cannot decode inside its Detect-head epilogues)
+        return 1 + self.engine.launches_per_forward() + (1 if self.engine.fused_decode else 2)
 
 
 class BatchTracker:
