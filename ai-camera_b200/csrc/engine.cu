@@ -69,6 +69,7 @@ struct Op {
   int act = 0, res_mode = 0, out_f32 = 0;
   int s2d_c0 = 0;   // conv reads its input space-to-depth (h, w are the space-to-depth sizes), c0 channels per pixel
   int out_s2d = 0;  // conv stores its output space-to-depth (for the next stride-2 layer)
+  int only_fmt = 0; // 0: always; 2: only when the input is NOT format 3; 3: only when the input is format 3 (the two stems of yolov8n)
   int lane = 0;     // 0: the caller's stream; 1, 2: the engine's side streams (independent tail chains, joined at the end)
 };
 
@@ -83,6 +84,7 @@ struct aicam_engine {
   aicam::StemPool stem;            // reid: fused conv.0 + ReLU + maxpool
   int stem_in8 = -1;               // reid: NHWC8 copy of the input crops
   int s2d_in = -1;                 // yolov8: space-to-depth copy of an NHWC4 input (callers may pass it directly)
+  int stem4 = -1;                  // yolov8n: index (in convs) of the stem re-expressed over 4x4 pixel blocks (input format 3), or -1
   std::map<std::string, int> conv_by_name;
   std::vector<aicam::Buffer> buffers;
   std::vector<aicam::Op> ops;
@@ -160,6 +162,49 @@ struct Builder {
   }
 
   // 3x3 stride-2 layer over a space-to-depth input of (h2 x w2) 2x2 blocks with c0 channels per pixel
+  // The yolov8n stem once more space-to-depth: the 3x3 stride-2 layer over the 640 grid is a 2x2 window over the 320 grid of
+  // 2x2 blocks (format 2, 16 channels); computing the 2x2 OUTPUT pixels of an output block together makes it a 3x3
+  // stride-2 layer over that 320 grid with 16 input and 4 x 16 output channels [(oy, ox)][co] - exactly the layer type
+  // pack_conv_weights_s2d packs (model.1), now reading 4x4 pixel blocks of 64 channels (format 3) and storing plain 64-channel
+  // pixels = the space-to-depth tensor model.1 reads.  Why: a 16-channel pixel is a 32-byte TMA request and the window kernel
+  // is bound by the request rate there (6.5 M loads + 3.3 M stores per 64 frames); 64-channel blocks need a quarter of them.
+  int stem_4x4(const std::string& name, View in, int h4, int w4, View out, int c1) {
+    if (err) return err;
+    auto wi = tensors->find(name + ".weight");
+    auto bi = tensors->find(name + ".bias");
+    if (wi == tensors->end() || bi == tensors->end()) return err = fail(AICAM_ERR_IO, "engine: blob has no tensor " + name);
+    const float* w = wi->second.data;  // [c1][3][3][3]
+    const int cout = 4 * c1;
+    std::vector<float> w2(static_cast<size_t>(cout) * 16 * 9, 0.0f), b2(cout);
+    // image row 4Y + 2 oy + dy - 1 = 2 u + py with u = 2Y + e - 1 (e: tap of the 320-grid layer), py: row parity inside the block
+    for (int oy = 0; oy < 2; ++oy)
+      for (int ox = 0; ox < 2; ++ox)
+        for (int co = 0; co < c1; ++co) {
+          const int o = (oy * 2 + ox) * c1 + co;
+          b2[o] = bi->second.data[co];
+          for (int dy = 0; dy < 3; ++dy)
+            for (int dx = 0; dx < 3; ++dx) {
+              const int ry = 2 * oy + dy - 1, rx = 2 * ox + dx - 1;  // -1 .. 3
+              const int e = (ry + 2) / 2, f = (rx + 2) / 2;           // floor(r / 2) + 1
+              const int py = (ry + 2) & 1, px = (rx + 2) & 1;
+              for (int c = 0; c < 3; ++c)
+                w2[(static_cast<size_t>(o) * 16 + (py * 2 + px) * 4 + c) * 9 + e * 3 + f] = w[(static_cast<size_t>(co) * 3 + c) * 9 + dy * 3 + dx];
+            }
+        }
+    PackedConv pc;
+    if (int rc = pack_conv_weights_s2d(w2.data(), b2.data(), cout, 16, 16, &pc)) return err = rc;
+    e->convs.push_back(pc);
+    e->stem4 = static_cast<int>(e->convs.size()) - 1;
+    Op op;
+    op.type = Op::CONV;
+    op.conv = e->stem4;
+    op.in = in; op.out = out;
+    op.h = h4; op.w = w4; op.k = 2; op.stride = 1;
+    op.act = 1; op.s2d_c0 = 16; op.out_s2d = 0; op.only_fmt = 3;
+    e->ops.push_back(op);
+    return AICAM_OK;
+  }
+
   int conv_s2d(const std::string& name, View in, int h2, int w2, View out, int cin, int cout, int c0, int act, int out_s2d) {
     if (err) return err;
     auto wi = tensors->find(name + ".weight");
@@ -302,6 +347,11 @@ struct Builder {
     if (s2d0) {
       e->s2d_in = buf(h2, h2, 16);
       conv_s2d("model.0.conv", V(-1), h2, h2, V(a0), 3, c1, 4, 1, s2d1 ? 1 : 0);
+      static const bool no_stem4 = getenv("AICAM_NO_STEM4") != nullptr;
+      if (s2d1 && !no_stem4) {  // the same layer over format-3 input; run_ops picks one of the two by the input's format
+        e->ops.back().only_fmt = 2;
+        stem_4x4("model.0.conv", V(-1), h4, h4, V(a0), c1);
+      }
     } else {
       conv("model.0.conv", V(-1), S, S, V(a0), 3, c1, 3, 2, 1);
     }
@@ -446,7 +496,10 @@ struct DecodeTarget {
 };
 
 int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStream_t stream,
-            const int* n_dev = nullptr, bool input_is_s2d = false, const DecodeTarget* dec = nullptr) {
+            const int* n_dev = nullptr, int input_is_s2d = 0, const DecodeTarget* dec = nullptr) {
+  // input_is_s2d: 0: NHWC4 (yolov8) / NHWC4 crops (reid); 1: the engine's space-to-depth / NHWC8 input format; 2: yolov8n,
+  // 4x4 pixel blocks (aicam_preprocess format 3)
+  if (input_is_s2d == 2 && e->stem4 < 0) return fail(AICAM_ERR_UNSUPPORTED, "engine: this engine has no 4x4-block stem (input format 3)");
   const void* input_s2d = input;
   if (e->s2d_in >= 0 && !input_is_s2d) {
     __nv_bfloat16* dst = e->buffers[e->s2d_in].ptr;
@@ -470,6 +523,8 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
   int skip = 0;  // single-layer ops covered by a chain that has just been launched
   for (const Op& op : e->ops) {
     if (skip > 0) { --skip; continue; }
+    if (op.only_fmt == 3 && input_is_s2d != 2) continue;
+    if (op.only_fmt == 2 && input_is_s2d == 2) continue;
     stream = main_stream;
     if (op.lane > 0 && e->side[op.lane - 1] && !profile_enabled()) {  // (per-launch timing: one kernel at a time)
       if (!forked) {
@@ -521,6 +576,7 @@ int run_ops(aicam_engine* e, const void* input, int batch, void* output, cudaStr
           L.out = const_cast<__nv_bfloat16*>(op_) + op.out.eoff;
         }
         L.out_img_stride = os; L.out_cstride = oc; L.out_coff = op.out.coff; L.out_f32 = op.out_f32;
+        if (op.only_fmt == 3) L.out_cstride = pc.cout;  // 4x4-block stem: (h x w) pixels of 4 c1 channels = the same bytes as the buffer's 2x2 blocks
         L.res = nullptr; L.res_img_stride = 0; L.res_cstride = 0; L.res_coff = 0; L.res_mode = 0;
         if (op.res_mode) {
           geom(op.res, 0, &rp, &rs, &rc_);
@@ -774,6 +830,13 @@ int aicam_engine_set_bias(aicam_engine* e, const char* name, const float* host, 
   AICAM_CUDA_OK(cudaSetDevice(e->device));
   AICAM_CUDA_OK(cudaMemcpy(pc.bias, host, sizeof(float) * n, cudaMemcpyHostToDevice));
   if (pc.bias_host) std::memcpy(pc.bias_host, host, sizeof(float) * n);  // (kernel-argument copy: takes effect at the next launch / capture)
+  if (e->stem4 >= 0 && std::string(name) == "model.0.conv") {  // the 4x4-block form of the stem repeats the bias per output sub-pixel
+    PackedConv& p4 = e->convs[e->stem4];
+    std::vector<float> b4(p4.cout);
+    for (int i = 0; i < p4.cout; ++i) b4[i] = host[i % n];
+    AICAM_CUDA_OK(cudaMemcpy(p4.bias, b4.data(), sizeof(float) * p4.cout, cudaMemcpyHostToDevice));
+    if (p4.bias_host) std::memcpy(p4.bias_host, b4.data(), sizeof(float) * p4.cout);
+  }
   return AICAM_OK;
 }
 
@@ -807,13 +870,14 @@ int aicam_yolo_detect(aicam_engine* e, const void* in, int in_is_s2d, int batch,
                       size_t workspace_bytes, void* stream) {
   if (!e || e->kind != AICAM_KIND_YOLOV8) return fail(AICAM_ERR_INVALID_ARG, "yolo_detect: not a yolov8 engine");
   if (batch < 0 || batch > e->max_batch) return fail(AICAM_ERR_CAPACITY, "yolo_detect: batch exceeds max_batch");
+  if (in_is_s2d < 0 || in_is_s2d > 2) return fail(AICAM_ERR_INVALID_ARG, "yolo_detect: in_is_s2d must be 0, 1 or 2");
   if (in_is_s2d && e->s2d_in < 0) return fail(AICAM_ERR_UNSUPPORTED, "yolo_detect: this engine was built without the space-to-depth stem");
   if (!in || !p || !num_dets || !boxes_lb || !scores || !labels) return fail(AICAM_ERR_INVALID_ARG, "yolo_detect: null argument");
   const int anchors = e->num_anchors, nc = static_cast<int>(e->params[7]);
   if (batch == 0) return AICAM_OK;
   if (!aicam_engine_fused_decode(e)) {
     if (!head) return fail(AICAM_ERR_INVALID_ARG, "yolo_detect: this engine needs the fp32 head tensor (no fused decode)");
-    if (int rc = run_ops(e, in, batch, head, static_cast<cudaStream_t>(stream), nullptr, in_is_s2d != 0)) return rc;
+    if (int rc = run_ops(e, in, batch, head, static_cast<cudaStream_t>(stream), nullptr, in_is_s2d)) return rc;
     return aicam_decode_nms(head, batch, anchors, nc, p, num_dets, boxes_lb, boxes_orig, scores, labels, workspace, workspace_bytes,
                             stream);
   }
@@ -827,7 +891,7 @@ int aicam_yolo_detect(aicam_engine* e, const void* in, int in_is_s2d, int batch,
   dec.scores = reinterpret_cast<float*>(ws + static_cast<size_t>(batch) * anchors * 16);
   dec.labels = reinterpret_cast<int*>(ws + static_cast<size_t>(batch) * anchors * 20);
   uint8_t* mask = ws + (dense + 255) / 256 * 256;
-  if (int rc = run_ops(e, in, batch, nullptr, static_cast<cudaStream_t>(stream), nullptr, in_is_s2d != 0, &dec)) return rc;
+  if (int rc = run_ops(e, in, batch, nullptr, static_cast<cudaStream_t>(stream), nullptr, in_is_s2d, &dec)) return rc;
   return aicam_nms(dec.boxes, dec.scores, dec.labels, batch, anchors, p, num_dets, boxes_lb, boxes_orig, scores, labels, nullptr,
                    mask, workspace_bytes - static_cast<size_t>(mask - ws), stream);
 }
@@ -839,7 +903,7 @@ int aicam_yolo_forward_s2d(aicam_engine* e, const void* in_s2d16, int batch, flo
   return run_ops(e, in_s2d16, batch, head, static_cast<cudaStream_t>(stream), nullptr, true);
 }
 
-int aicam_engine_accepts_s2d(const aicam_engine* e) { return e && e->s2d_in >= 0 ? 1 : 0; }
+int aicam_engine_accepts_s2d(const aicam_engine* e) { return e && e->s2d_in >= 0 ? (e->stem4 >= 0 ? 2 : 1) : 0; }
 
 int aicam_engine_accepts_nhwc8(const aicam_engine* e) { return e && e->kind == AICAM_KIND_REID && e->stem_in8 >= 0 ? 1 : 0; }
 

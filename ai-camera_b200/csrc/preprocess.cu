@@ -223,13 +223,21 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
                                           ((static_cast<long long>(n) * S + y) * S + xg * PIX) * 4);
       o[0] = q0;
       o[1] = q1;
-    } else {
+    } else if (FORMAT == 2) {
       // space-to-depth: 2x2 pixel block (Y, X) = 16 channels [row parity][column parity][RGB0]; this thread
       // holds columns 4 xg .. 4 xg + 3 of row y = blocks X = 2 xg, 2 xg + 1, row parity y & 1
       uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) +
                                           ((static_cast<long long>(n) * (S / 2) + (y >> 1)) * (S / 2) + 2 * xg) * 16 + (y & 1) * 8);
       o[0] = q0;
       o[2] = q1;
+    } else {
+      // two levels of space-to-depth: 4x4 pixel block (Y, X) = 64 channels [2x2 sub-block (by, bx)][row parity][column
+      // parity][RGB0] - the format-2 blocks grouped 2x2 once more; this thread holds row y of block X = xg
+      uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) +
+                                          ((static_cast<long long>(n) * (S / 4) + (y >> 2)) * (S / 4) + xg) * 64);
+      const int by = (y >> 1) & 1, py = y & 1;
+      o[by * 4 + py] = q0;
+      o[by * 4 + 2 + py] = q1;
     }
   }
 }
@@ -358,11 +366,19 @@ __global__ void __launch_bounds__(S / PIX) preprocess_pairs_kernel(const uint8_t
         o[0] = q[r][0];
         o[1] = q[r][1];
       }
-    } else {
+    } else if (FORMAT == 2) {
       // space-to-depth: 2x2 pixel block (Y, X) = 16 channels [row parity][column parity][RGB0]; this thread holds
       // columns 4 xg .. 4 xg + 3 of both rows = the whole blocks X = 2 xg and 2 xg + 1 of block row y0 / 2
       uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) +
                                           ((static_cast<long long>(n) * (S / 2) + (y0 >> 1)) * (S / 2) + 2 * xg) * 16);
+      o[0] = q[0][0];
+      o[1] = q[1][0];
+      o[2] = q[0][1];
+      o[3] = q[1][1];
+    } else {
+      // 4x4 pixel blocks of 64 channels (format 3): the same 64 bytes = sub-block row by of block (y0 / 4, xg)
+      uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) +
+                                          ((static_cast<long long>(n) * (S / 4) + (y0 >> 2)) * (S / 4) + xg) * 64) + ((y0 >> 1) & 1) * 4;
       o[0] = q[0][0];
       o[1] = q[1][0];
       o[2] = q[0][1];
@@ -409,7 +425,7 @@ namespace {
 template <int SRC>
 int preprocess_impl(const uint8_t* frames, int batch, int h, int w, int format, void* out, void* stream) {
   if (!frames || !out || batch < 0 || h <= 0 || w <= 0) return fail(AICAM_ERR_INVALID_ARG, "preprocess: bad arguments");
-  if (format < 0 || format > 2) return fail(AICAM_ERR_INVALID_ARG, "preprocess: format must be 0, 1 or 2");
+  if (format < 0 || format > 3) return fail(AICAM_ERR_INVALID_ARG, "preprocess: format must be 0, 1, 2 or 3");
   if (batch == 0) return AICAM_OK;
   Geometry g;
   if (int rc = get_geometry(h, w, &g)) return rc;
@@ -427,7 +443,8 @@ int preprocess_impl(const uint8_t* frames, int batch, int h, int w, int format, 
     int stages = K1_STAGES * stage_bytes <= 100 * 1024 ? K1_STAGES : 2;
     if (env_stages >= 2 && env_stages <= K1_STAGES && env_stages * stage_bytes <= 200 * 1024) stages = env_stages;
     const size_t smem = stages * stage_bytes;
-    auto kernel = format == 0 ? preprocess_pairs_kernel<0, SRC> : (format == 1 ? preprocess_pairs_kernel<1, SRC> : preprocess_pairs_kernel<2, SRC>);
+    auto kernel = format == 0 ? preprocess_pairs_kernel<0, SRC>
+                              : (format == 1 ? preprocess_pairs_kernel<1, SRC> : (format == 2 ? preprocess_pairs_kernel<2, SRC> : preprocess_pairs_kernel<3, SRC>));
     if (smem > 48 * 1024) {
       if (int rc = ensure_dynamic_smem(kernel, 200 * 1024)) return rc;
     }
@@ -438,7 +455,8 @@ int preprocess_impl(const uint8_t* frames, int batch, int h, int w, int format, 
     count_launch();
     return last_launch("preprocess_pairs_kernel");
   }
-  auto kernel = format == 0 ? preprocess_kernel<0, SRC> : (format == 1 ? preprocess_kernel<1, SRC> : preprocess_kernel<2, SRC>);
+  auto kernel = format == 0 ? preprocess_kernel<0, SRC>
+                            : (format == 1 ? preprocess_kernel<1, SRC> : (format == 2 ? preprocess_kernel<2, SRC> : preprocess_kernel<3, SRC>));
   kernel<<<blocks, 256, 0, st>>>(frames, h, w, g.mode, g.new_h, g.new_w, g.top, g.left, g.tab, out, total);
   count_launch();
   return last_launch("preprocess_kernel");

@@ -49,7 +49,8 @@ class BatchDetector:
         self.scores = torch.zeros((batch, topk), dtype=torch.float32, device=dev)
         self.labels = torch.zeros((batch, topk), dtype=torch.int32, device=dev)
         self._nms = _lib.NmsParams(e.score_threshold, e.nms_threshold, topk, e.max_candidates, 0, 0)
-        self._s2d = bool(self.lib.aicam_engine_accepts_s2d(e.handle))
+        # 0: NHWC4 input (aicam_preprocess format 1), 1: 2x2 pixel blocks (format 2), 2: 4x4 pixel blocks (format 3, yolov8n)
+        self._s2d = int(self.lib.aicam_engine_accepts_s2d(e.handle))
 
     def detect(self, frames: torch.Tensor):
         """frames: uint8 cuda [n<=batch, H, W, 3] BGR, or [n, H*3/2, W] NV12 (Y plane + interleaved UV plane, the
@@ -62,12 +63,12 @@ class BatchDetector:
             raise _lib.AicamError(-4, "detect: %d frames exceed the detector's batch %d" % (n, self.batch))
         e, st = self.engine, _lib.stream_ptr(self.device)
         with torch.cuda.device(self.device):
-            # same bytes, 2x2 pixel blocks (format 2): the stride-2 stem runs as a stride-1 window
-            _lib.check(pre(_lib.ptr(frames), n, h, w, 2 if self._s2d else 1, _lib.ptr(e._nhwc), st))
+            # same bytes in 2x2 / 4x4 pixel blocks (formats 2 / 3): the stride-2 stem runs as a stride-1 window over the blocks
+            _lib.check(pre(_lib.ptr(frames), n, h, w, 1 + self._s2d, _lib.ptr(e._nhwc), st))
             self._nms.frame_h, self._nms.frame_w = h, w
             # network + decode (fused into the Detect-head epilogues) + NMS + un-letterboxing: one entry
             _lib.check(self.lib.aicam_yolo_detect(
-                e.handle, _lib.ptr(e._nhwc), 1 if self._s2d else 0, n, C.byref(self._nms),
+                e.handle, _lib.ptr(e._nhwc), self._s2d, n, C.byref(self._nms),
                 _lib.ptr(e._head) if e._head is not None else None, _lib.ptr(self.num_dets),
                 _lib.ptr(self.boxes_lb), _lib.ptr(self.boxes), _lib.ptr(self.scores), _lib.ptr(self.labels),
                 _lib.ptr(e._ws), e._ws.numel(), st))

@@ -102,7 +102,8 @@ int aicam_yolo_forward(aicam_engine* e, const void* in_nhwc4, int batch, float* 
 /* Same network, input already space-to-depth as aicam_preprocess format 2 writes it:
  * bf16 [batch][320][320][16] = 2x2 pixel blocks [row parity][column parity][R, G, B, 0].  The 3x3 stride-2
  * stem runs as a 2x2 window over these blocks; aicam_yolo_forward repacks an NHWC4 input into this
- * layout first.  aicam_engine_accepts_s2d: 1 when the engine was built with that stem. */
+ * layout first.  aicam_engine_accepts_s2d: 1 when the engine was built with that stem, 2 when it also has the
+ * stem over 4x4 pixel blocks (yolov8n; aicam_preprocess format 3, taken by aicam_yolo_detect with in_is_s2d = 2). */
 int aicam_yolo_forward_s2d(aicam_engine* e, const void* in_s2d16, int batch, float* head, void* stream);
 int aicam_engine_accepts_s2d(const aicam_engine* e);
 
@@ -195,6 +196,10 @@ int aicam_reid_stem_pool(const void* in_nhwc4, int n, int h, int w, const float*
  *   format 1: out = bf16 [batch][640][640][4] (what aicam_yolo_forward consumes)
  *   format 2: out = bf16 [batch][320][320][16], the same values space-to-depth: 2x2 pixel blocks
  *             [row parity][column parity][R, G, B, 0] (what aicam_yolo_forward_s2d consumes)
+ *   format 3: out = bf16 [batch][160][160][64], the format-2 blocks grouped 2x2 once more: 4x4 pixel blocks
+ *             [block row parity][block column parity][row parity][column parity][R, G, B, 0] (aicam_yolo_detect
+ *             with in_is_s2d = 2, engines for which aicam_engine_accepts_s2d returns 2: a 64-channel block is one
+ *             128-byte tensor-copy request where four 16-channel blocks are four)
  * meta (host out, may be NULL): ratio, pad_w, pad_h as the reference returns them. */
 typedef struct {
   double ratio, pad_w, pad_h;
@@ -247,7 +252,8 @@ int aicam_nms(const float* boxes, const float* scores, const int32_t* labels, in
  * entry: aicam_yolo_forward[_s2d] + aicam_decode_nms, with the decode FUSED into the epilogues of the six 1x1
  * Detect-head layers when aicam_engine_fused_decode(e) is 1 - the fp32 head tensor (310 MB per 64 frames,
  * written once and read once) then never exists and `head` may be NULL; otherwise `head` is the scratch
- * tensor [batch][anchors][64 + nc].  in: the aicam_preprocess output, format 2 when in_is_s2d, else format 1.
+ * tensor [batch][anchors][64 + nc].  in: the aicam_preprocess output of format 1 + in_is_s2d (0: NHWC4, 1: 2x2 blocks,
+ * 2: 4x4 blocks - only when aicam_engine_accepts_s2d(e) returns 2).
  * workspace: aicam_decode_nms_workspace bytes.  Results as aicam_decode_nms (same arithmetic, same order). */
 int aicam_yolo_detect(aicam_engine* e, const void* in, int in_is_s2d, int batch, const aicam_nms_params* p,
                       float* head, int32_t* num_dets, float* boxes_lb, float* boxes_orig, float* scores,

@@ -42,8 +42,10 @@ def preprocess(frames_u8, fmt):
         out = torch.empty((B, 3, 640, 640), dtype=torch.float32, device=DEV)
     elif fmt == 1:
         out = torch.empty((B, 640, 640, 4), dtype=torch.bfloat16, device=DEV)
-    else:
+    elif fmt == 2:
         out = torch.empty((B, 320, 320, 16), dtype=torch.bfloat16, device=DEV)
+    else:
+        out = torch.empty((B, 160, 160, 64), dtype=torch.bfloat16, device=DEV)
     check(lib().aicam_preprocess(ptr(frames_u8), B, H, W, fmt, ptr(out), None))
     sync()
     return out

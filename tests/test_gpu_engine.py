@@ -144,6 +144,43 @@ def test_fused_decode_equals_decode_kernel(blobs, name, batch):
         assert torch.equal(a, b)
 
 
+def test_4x4_block_stem_matches_2x2_block_stem(blobs):
+    """yolov8n runs its stem over 4x4 pixel blocks (aicam_preprocess format 3, in_is_s2d = 2): the same products summed in
+    another order.  The stem's bf16 output may differ in the last bit; the detections must agree with the format-2 path
+    far inside the 1e-2 box bar, and with the oracle exactly as the format-2 path does (test_yolov8n_head_matches_oracle)."""
+    import gpu_util as G
+    rng = np.random.default_rng(11)
+    frames = np.stack([synth_image(rng, 540, 960) for _ in range(2)])
+    fd = torch.from_numpy(frames).to(G.DEV)
+    lib = G.lib()
+    e = _engine(blobs["yolov8n"], 2)
+    try:
+        assert lib.aicam_engine_accepts_s2d(e) == 2
+        p = G.NmsParams(0.05, 0.5, 100, 1024, 540, 960)
+        nws = lib.aicam_decode_nms_workspace(2, 8400, C.byref(p))
+        res = []
+        for s2d in (1, 2):
+            x = G.preprocess(fd, 1 + s2d)
+            ws = torch.zeros(nws, dtype=torch.uint8, device=G.DEV)
+            o = (torch.zeros(2, dtype=torch.int32, device=G.DEV), torch.zeros((2, 100, 4), device=G.DEV), torch.zeros((2, 100, 4), device=G.DEV),
+                 torch.zeros((2, 100), device=G.DEV), torch.zeros((2, 100), dtype=torch.int32, device=G.DEV))
+            G.check(lib.aicam_yolo_detect(e, G.ptr(x), s2d, 2, C.byref(p), None, *[G.ptr(t) for t in o], G.ptr(ws), nws, None))
+            G.sync()
+            n = 2 * 8400
+            res.append((ws[:n * 16].view(torch.float32).reshape(2, 8400, 4).cpu().numpy().copy(),
+                        ws[n * 16:n * 20].view(torch.float32).reshape(2, 8400).cpu().numpy().copy(), [t.cpu().numpy() for t in o]))
+    finally:
+        lib.aicam_engine_destroy(e)
+    (b2, s2, o2), (b3, s3, o3) = res
+    assert o2[0].sum() > 0
+    size = np.maximum(np.maximum(b2[..., 2] - b2[..., 0], b2[..., 3] - b2[..., 1]), 1.0)[..., None]
+    strong = s2 > 0.05
+    print("4x4 vs 2x2 stem: max box diff / size %.2e, max score diff %.2e" % ((np.abs(b3 - b2) / size)[strong].max(), np.abs(s3 - s2).max()))
+    assert (np.abs(b3 - b2) / size)[strong].max() < 2e-3
+    assert np.abs(s3 - s2).max() < 5e-3
+    assert np.array_equal(o2[0], o3[0])  # the same number of detections per frame
+
+
 def test_reid_embeddings_match_oracle(blobs):
     import gpu_util as G
     from oracle import image_ops, nets

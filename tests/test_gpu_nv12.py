@@ -40,7 +40,7 @@ def test_nv12_conversion_and_preprocess_bit_exact(hw):
     bgr = _to_bgr(nd, h, w)
     for i in range(2):  # device conversion == oracle restatement (== cv2, tests/test_oracle_imageops.py)
         assert np.array_equal(bgr[i].cpu().numpy(), image_ops.nv12_to_bgr(nv[i], h, w)), "nv12_to_bgr differs"
-    for fmt in (0, 1, 2):
+    for fmt in (0, 1, 2, 3):
         want = G.preprocess(bgr, fmt)
         got = torch.empty_like(want)
         G.check(G.lib().aicam_preprocess_nv12(G.ptr(nd), 2, h, w, fmt, G.ptr(got), None))

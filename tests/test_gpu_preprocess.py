@@ -51,3 +51,17 @@ def test_space_to_depth_format_is_a_pure_permutation():
     b = G.preprocess(frames, 2).view(torch.int16).cpu().numpy()           # [B,320,320,16]
     want = a.reshape(2, 320, 2, 320, 2, 4).transpose(0, 1, 3, 2, 4, 5).reshape(2, 320, 320, 16)
     assert np.array_equal(b, want)
+
+
+@pytest.mark.parametrize("hw", [(1080, 1920), (540, 960), (333, 517)])
+def test_4x4_block_format_is_a_pure_permutation(hw):
+    """Format 3 (what the 4x4-block stem of yolov8n consumes) = the format-2 blocks grouped 2x2 once more:
+    block (Y, X) channel ((by*2 + bx)*4 + (py*2 + px))*4 + c  ==  pixel (4Y + 2by + py, 4X + 2bx + px) channel c.
+    1080p runs the row-staged decimation kernel, the other sizes the generic one."""
+    import gpu_util as G
+    rng = np.random.default_rng(8)
+    frames = torch.from_numpy(rng.integers(0, 256, (2,) + hw + (3,), dtype=np.uint8)).to(G.DEV)
+    a = G.preprocess(frames, 1).view(torch.int16).cpu().numpy()           # [B,640,640,4]
+    b = G.preprocess(frames, 3).view(torch.int16).cpu().numpy()           # [B,160,160,64]
+    want = a.reshape(2, 160, 2, 2, 160, 2, 2, 4).transpose(0, 1, 4, 2, 5, 3, 6, 7).reshape(2, 160, 160, 64)
+    assert np.array_equal(b, want)
