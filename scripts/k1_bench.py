@@ -48,7 +48,7 @@ def timed(fn):
 
 
 print("K1 / K5 micro-benchmark: %d frames %dx%d, %d launches each, peak %.0f GB/s (MEASURED_PEAKS.json hbm_gbs)" % (B, H, W, iters, peak))
-for fmt, name, out_bytes in ((2, "space-to-depth bf16 (engine input)", 640 * 640 * 8), (1, "NHWC4 bf16", 640 * 640 * 8),
+for fmt, name, out_bytes in ((3, "4x4 pixel blocks bf16 (engine input)", 640 * 640 * 8), (2, "2x2 pixel blocks bf16", 640 * 640 * 8), (1, "NHWC4 bf16", 640 * 640 * 8),
                              (0, "NCHW fp32 (reference layout)", 640 * 640 * 12)):
     out = torch.empty(B * out_bytes, dtype=torch.uint8, device=dev)
     for src, frames, fn, row_bytes in (("BGR", bgr, lib.aicam_preprocess, W * 3), ("NV12", nv12, lib.aicam_preprocess_nv12, W * 2)):
