@@ -786,7 +786,10 @@ double aicam_engine_flops_per_item(const aicam_engine* e) { return e ? 2.0 * e->
 int aicam_engine_num_launches(const aicam_engine* e) {
   if (!e) return 0;
   int n = 0;
-  for (const auto& op : e->ops) n += op.type == aicam::Op::STEMPOOL ? 2 : (op.type == aicam::Op::CHAIN ? 0 : 1);  // upper bound: NHWC8 repack + fused stem; chains replace layers
+  for (const auto& op : e->ops) {
+    if (op.only_fmt == 2) continue;  // (the stem exists twice, one of the two runs)
+    n += op.type == aicam::Op::STEMPOOL ? 2 : (op.type == aicam::Op::CHAIN ? 0 : 1);
+  }  // upper bound: NHWC8 repack + fused stem; chains replace layers
   return n;
 }
 

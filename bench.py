@@ -431,6 +431,11 @@ def run_streams(args):
                    "weights": "seeded synthetic (no checkpoints offline)",
                    "e2e_input": "NV12 host surfaces (decoder output format, 199 MB per step); e2e_bgr: packed BGR host frames (398 MB per step)"},
         "p50_latency_ms": statistics.median(per_step),
+        "step_ms_distribution": {"min": min(per_step), "p10": sorted(per_step)[len(per_step) // 10], "p50": statistics.median(per_step),
+                                 "p90": sorted(per_step)[(9 * len(per_step)) // 10], "max": max(per_step),
+                                 "first_8": [round(x, 3) for x in per_step[:8]],
+                                 **({"all": [round(x, 2) for x in per_step]} if os.environ.get("AICAM_BENCH_DUMP_STEPS") else {}),
+                                 "note": "rank 0, per-step CUDA events inside the timed region; value uses the whole region (mean)"},
         "clocks": clocks,
         "e2e": {"value": world * S * e2e_steps / max_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "h2d_gbs": h2d * e2e_steps / max_e2e / 1e9, "input": "nv12",
@@ -713,7 +718,12 @@ def run_crowded(args):
                    "mean_gallery_size": gal, "tracker_overflow": bool(overflow.any()),
                    "detections": "planted person boxes riding on the moving texture; the detector runs and is timed, its output is not used",
                    "reid_ms_per_step": reid_ms, "appearance_probe_ms": t0.elapsed_time(t1)},
-        "p50_latency_ms": statistics.median(per_step), "clocks": clocks,
+        "p50_latency_ms": statistics.median(per_step),
+        "step_ms_distribution": {"min": min(per_step), "p10": sorted(per_step)[len(per_step) // 10], "p50": statistics.median(per_step),
+                                 "p90": sorted(per_step)[(9 * len(per_step)) // 10], "max": max(per_step),
+                                 "first_8": [round(x, 3) for x in per_step[:8]],
+                                 **({"all": [round(x, 2) for x in per_step]} if os.environ.get("AICAM_BENCH_DUMP_STEPS") else {}),
+                                 "note": "rank 0, per-step CUDA events inside the timed region; value uses the whole region (mean)"}, "clocks": clocks,
         "e2e": {"value": frames_total / (total_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": "device-resident frames (the host-fed leg is measured in --config streams64)"},
         "gpu_launches": int(launches),
