@@ -62,8 +62,8 @@ int aicam_debug_timeline(int op, long long* host_out, int capacity);
  * Engine: replaces TRTEngine (src/trt_utils/trt_engine.py:15-216): __init__/_init_engine
  * (deserialize_cuda_engine, :45-60) -> aicam_engine_create on a flat ".aicw" weight blob;
  * get_input_details/get_output_details (:212-216) -> aicam_engine_io_count / aicam_engine_io_info;
- * infer (:151-203) -> aicam_nchw_to_nhwc4 + aicam_yolo_forward + aicam_decode_nms for the detector
- * engine (whose ONNX embeds the NMS), aicam_nchw_to_nhwc4 + aicam_reid_forward for the ReID engine.
+ * infer (:151-203) -> aicam_nchw_to_nhwc4 + aicam_yolo_detect (network, decode and NMS; the pieces
+ * aicam_yolo_forward + aicam_decode_nms remain) for the detector engine (whose ONNX embeds the NMS), aicam_nchw_to_nhwc4 + aicam_reid_forward for the ReID engine.
  * ---------------------------------------------------------------------------------------- */
 int aicam_engine_create(const char* blob_path, int device, int max_batch, aicam_engine** out);
 void aicam_engine_destroy(aicam_engine* e);
