@@ -91,6 +91,8 @@ struct WinArgs {
                     // (no residual ring): the store of tile i is followed by the residual load of tile i + nstage
   int warp_arrive;  // epilogue -> MMA / I/O hand-offs: one elected lane per warp arrives on the mbarriers (default) instead of every
                     // thread: 32 same-address arrives serialise on the shared-memory port the tensor core reads its operands through
+  int pad_store;    // im2col mode, TMA epilogue, zero-bordered output: a tile is whole rows of one image or whole images, stored as ONE 4-D box
+                    // (channels, wo, rows, images) into the interiors - the generic epilogue's row-by-row copy-out was half of its tile time
   int ws;           // MMA issue in the weight-stationary form (tcgen05.mma.ws, collector buffers for B)
   int decode;       // generic epilogue of a Detect-head 1x1 layer: decode the staged fp32 rows instead of storing them (ConvLaunch::decode)
   int dec_anchor_base, dec_anchors;
@@ -961,6 +963,11 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
         cx = tp.strip * a.tw; cy = tp.q0 / a.rw; cn = tp.n_img;
       } else {
         cx = mt_idx * TM; cy = 0; cn = 0;
+        if (MODE == 2 && a.pad_store) {  // first pixel of the tile -> (image, row); tiles are whole rows / whole images
+          cn = cx / a.hw;
+          cy = (cx - cn * a.hw) / a.wo;
+          cx = 0;
+        }
       }
     };
     auto load_res = [&](int tile, uint32_t slot, uint32_t phase) {
@@ -1009,7 +1016,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
         } else {
           int pc0 = 0;
           for (int q = 0; q < a.pieces && n0 + pc0 < a.cout; ++q) {
-            tma_store_2d(&maps.out[q ? 1 : 0], src + a.piece_off[q], n0 + pc0, cx);
+            if (MODE == 2 && a.pad_store) tma_store_4d(&maps.out[q ? 1 : 0], src + a.piece_off[q], n0 + pc0, 0, cy, cn);
+            else tma_store_2d(&maps.out[q ? 1 : 0], src + a.piece_off[q], n0 + pc0, cx);
             pc0 += a.piece_ch[q];
           }
         }
@@ -1235,6 +1243,8 @@ int try_launch_conv_win(const PackedConv& pc, const ConvLaunch& L, cudaStream_t 
   // ---- choose the tiling: strips x (linear | row-aligned) x mt, cheapest estimated time
   WinPlan best;
   const int k16_total = taps * pc.cin_pad / 16;
+  bool pad2_failed = false;
+  const bool epi_pad2_ok = epi;  // (the static conditions of the TMA epilogue: bf16, channel pieces, cout % 8)
 plan:
   best = WinPlan();
   size_t fixed_base = 0;  // set below, once this pass's epilogue flavour is known
@@ -1249,9 +1259,15 @@ plan:
   // (1x1 layers with few input channels are all epilogue: measured 70 -> 50 us on 32 -> 32 @160x160)
   static const int epi_flat_cin = getenv("AICAM_WIN_EPI_FLAT_CIN") ? atoi(getenv("AICAM_WIN_EPI_FLAT_CIN")) : 128;
   const bool epi_flat = mode == 1 && flat_io && resident && pc.cin_pad <= epi_flat_cin;
-  if (!window && !(epi_everywhere && flat_io) && !epi_flat) epi = false;
+  // im2col layers storing into zero-bordered images (the stride-2 entry layers of the ReID trunk and their 1x1 partners): TMA epilogue
+  // when the tiles can be whole rows of an image or whole images (checked per tile height below)
+  static const bool no_pad_store = getenv("AICAM_WIN_NO_PAD_STORE") != nullptr;
+  // (measured in the step: the 1x1 stride-2 partners 59 / 38 / 23 -> 58 / 33 / 19 us; the 3x3 entry layers are bound by operand ingest and
+  //  lose a little to the smaller operand ring, so they keep the generic epilogue)
+  const bool epi_pad2 = mode == 2 && opd && !res_mode && pc.ksize == 1 && !no_pad_store && !pad2_failed && epi_pad2_ok;
+  if (!window && !(epi_everywhere && flat_io) && !epi_flat && !epi_pad2) epi = false;
   if (mode == 4) epi = epi4 && piece_ch[0] != 0;  // flat TMA epilogue: border positions are stored as zeros
-  else if (opd) epi = false;                        // (un-padded raster -> padded image: row-by-row offsets, generic epilogue)
+  else if (opd && !epi_pad2) epi = false;           // (un-padded raster -> padded image: row-by-row offsets, generic epilogue)
   fixed_base = (epi ? OFF_RING_A_EPI : OFF_RING_A) + fixed_tail;
   // 64-column tiles are bound by the shared-memory port (4 KB of A + 2 KB of B per 32-cycle MMA): the weight-stationary MMA form
   // keeps a tile's B block in a collector buffer across the accumulators of the tile
@@ -1261,6 +1277,10 @@ plan:
     if (force_mt && mt != force_mt) continue;
     const int tm = 128 * mt;
     if (2 * mt * n_tile > 512) continue;
+    if (epi && epi_pad2) {  // tiles = whole output rows of one image, or whole images
+      const int hwo = L.ho * L.wo;
+      if (!((hwo % tm == 0 && tm % L.wo == 0) || tm % hwo == 0)) continue;
+    }
     for (int strips = 1; strips <= (window ? 8 : 1); ++strips) {
       for (int aligned = (epi && window) ? 1 : 0; aligned <= (window ? 1 : 0); ++aligned) {
         WinPlan p;
@@ -1387,6 +1407,11 @@ plan:
       goto plan;
     }
   }
+  if (!best.ok && epi && epi_pad2) {  // no tile height fits the image: generic epilogue
+    pad2_failed = true;
+    epi = false;
+    goto plan;
+  }
   if (!best.ok) return 0;
 
   WinArgs a;
@@ -1462,6 +1487,7 @@ plan:
     a.flat = 0;  // (image, pixel) per row
   }
   a.ws = (ws_ok && best.mt == 2) ? 1 : 0;
+  a.pad_store = (epi && epi_pad2) ? 1 : 0;
   static const bool thread_arrive = getenv("AICAM_WIN_THREAD_ARRIVE") != nullptr;
   a.warp_arrive = thread_arrive ? 0 : 1;
   a.epi_alt = (!no_alt && epi && best.mt == 2 && n_tile <= 32 && best.nstage == 2 && (!res_mode || best.nres == 2) && !a.res_inplace) ? 1 : 0;
@@ -1516,6 +1542,21 @@ plan:
     for (int q = 0; q < std::min(a.pieces, 2) && cr == CUDA_SUCCESS; ++q) {  // (pieces beyond the second reuse map 1)
       const int pb = piece_ch[q] * 2;
       const CUtensorMapSwizzle psw = pb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (pb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+      if (a.pad_store) {
+        // interiors of the zero-bordered output images: (channels, wo, ho, batch), rows (wo + border) pixels apart
+        const int hwo = L.ho * L.wo;
+        const cuuint64_t pd[4] = {static_cast<cuuint64_t>(pc.cout), static_cast<cuuint64_t>(L.wo), static_cast<cuuint64_t>(L.ho),
+                                  static_cast<cuuint64_t>(L.batch)};
+        const cuuint64_t ps[3] = {static_cast<cuuint64_t>(L.out_cstride) * 2, static_cast<cuuint64_t>(L.wo + oext) * L.out_cstride * 2,
+                                  static_cast<cuuint64_t>(L.out_img_stride) * 2};
+        const cuuint32_t pbx[4] = {static_cast<cuuint32_t>(piece_ch[q]), static_cast<cuuint32_t>(L.wo),
+                                   static_cast<cuuint32_t>(a.tm <= hwo ? a.tm / L.wo : L.ho), static_cast<cuuint32_t>(a.tm <= hwo ? 1 : a.tm / hwo)};
+        const cuuint32_t pe[4] = {1, 1, 1, 1};
+        __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(L.out) + L.out_coff + static_cast<long long>(olo) * (L.wo + oext + 1) * L.out_cstride;
+        cr = get_encode_tiled()(&maps.out[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, obase, pd, ps, pbx, pe, CU_TENSOR_MAP_INTERLEAVE_NONE, psw,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        continue;
+      }
       if (!window) {
         // flat: [piece channels][128 MT pixels] of the [pixels][cstride] matrix
         const cuuint64_t fd[2] = {static_cast<cuuint64_t>(pc.cout), static_cast<cuuint64_t>(mode == 4 ? padded_pixels : pixels)};
