@@ -93,6 +93,9 @@ struct WinArgs {
                     // thread: 32 same-address arrives serialise on the shared-memory port the tensor core reads its operands through
   int pad_store;    // im2col mode, TMA epilogue, zero-bordered output: a tile is whole rows of one image or whole images, stored as ONE 4-D box
                     // (channels, wo, rows, images) into the interiors - the generic epilogue's row-by-row copy-out was half of its tile time
+  int img_tile;     // mode 4 on 8-pixel-wide maps of 128 pixels (ReID layer 3): a tile is ONE image's interior - accumulator row 8 y + x - read
+                    // through a descriptor whose 8-row groups are a raster row (RW pixels) apart, so the border column and row cost no MMA
+                    // rows (84 % -> 100 % useful); stored / residual-loaded as one 4-D box like pad_store
   int ws;           // MMA issue in the weight-stationary form (tcgen05.mma.ws, collector buffers for B)
   int decode;       // generic epilogue of a Detect-head 1x1 layer: decode the staged fp32 rows instead of storing them (ConvLaunch::decode)
   int dec_anchor_base, dec_anchors;
@@ -388,6 +391,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
   if (a.batch_dev) batch = min(batch, __ldg(a.batch_dev));
   long long m_tiles;
   if (MODE == 0) m_tiles = static_cast<long long>(batch) * a.tiles_per_img;
+  else if (FLATWIN && a.img_tile) m_tiles = batch;
   else m_tiles = (static_cast<long long>(batch) * a.hw + TM - 1) / TM;
   const int total_tiles = static_cast<int>(m_tiles) * a.n_tiles;
   pdl_trigger();  // the next layer's CTAs may take over each SM as soon as the CTA here exits
@@ -483,7 +487,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
       uint8_t* stage = stage0 + sbuf * a.stage_buf_bytes;
       bool stage_ok = false;
       bool zero_row = false;
-      if (FLATWIN) {  // my raster position of this tile: border positions are stored as zeros (the border stays zero)
+      if (FLATWIN && !a.img_tile) {  // my raster position of this tile: border positions are stored as zeros (the border stays zero)
         // (32-bit unsigned arithmetic: the host guarantees fewer than 2^31 padded pixels; the 64-bit modulo was 9 % of
         //  the kernel's instructions)
         const uint32_t p = static_cast<uint32_t>(mt_idx) * TM + r;
@@ -759,7 +763,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
     // only the tcgen05.mma / tcgen05.commit instructions are predicated on one elected lane.
     {
       const bool leader = elect_one();
-      const uint32_t a_hi = ((8 * ROW_BYTES) >> 4) | (1u << 14) | (LTYPE << 29);  // SBO | version | swizzle
+      // SBO | version | swizzle; image tiles: consecutive 8-row groups are one raster row apart (the swizzle follows the address bits)
+      const uint32_t a_hi = ((((FLATWIN && a.img_tile) ? a.rw : 8) * ROW_BYTES) >> 4) | (1u << 14) | (LTYPE << 29);
       const uint32_t b_hi = (128u >> 4) | (1u << 14);                           // SBO = 128 B, no swizzle
       const uint32_t a_ring = sbase + (EPI ? OFF_RING_A_EPI : OFF_RING_A), b_ring = sbase + a.off_b, w_base = sbase + a.off_w;
       const uint32_t rw_units = static_cast<uint32_t>(a.rw) * (ROW_BYTES >> 4);  // one raster row, in 16-byte units
@@ -893,7 +898,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
           if (MODE == 0) {
             tma_load_4d(dst, &maps.in, bar, s * SLAB, x_start, y_start, n_img);
           } else if (FLATWIN) {
-            const int row0 = mt_idx * TM - (a.rw + 1);  // negative / past-the-end rows are zero-filled
+            // negative / past-the-end rows are zero-filled; image tiles start RW + 1 positions before the image's first interior pixel
+            const int row0 = a.img_tile ? mt_idx * a.hw + (a.in_lo - 1) * (a.rw + 1) : mt_idx * TM - (a.rw + 1);
 #pragma unroll
             for (int j = 0; j < MT; ++j)
               tma_load_2d(dst + j * (a.box_rows * ROW_BYTES), &maps.in, bar, s * SLAB, row0 + j * a.box_rows);
@@ -968,6 +974,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
           cy = (cx - cn * a.hw) / a.wo;
           cx = 0;
         }
+        if (FLATWIN && a.img_tile) { cn = mt_idx; cy = 0; cx = 0; }
       }
     };
     auto load_res = [&](int tile, uint32_t slot, uint32_t phase) {
@@ -984,7 +991,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
         } else {
           int pc0 = 0;  // first channel of the piece
           for (int q = 0; q < a.pieces; ++q) {
-            tma_load_2d(rdst + a.piece_off[q], &maps.res[q ? 1 : 0], rbar, n0 + pc0, cx);
+            if (FLATWIN && a.img_tile) tma_load_4d(rdst + a.piece_off[q], &maps.res[q ? 1 : 0], rbar, n0 + pc0, 0, 0, cn);
+            else tma_load_2d(rdst + a.piece_off[q], &maps.res[q ? 1 : 0], rbar, n0 + pc0, cx);
             pc0 += a.piece_ch[q];
           }
         }
@@ -1016,7 +1024,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) conv_win_kernel(const __grid_c
         } else {
           int pc0 = 0;
           for (int q = 0; q < a.pieces && n0 + pc0 < a.cout; ++q) {
-            if (MODE == 2 && a.pad_store) tma_store_4d(&maps.out[q ? 1 : 0], src + a.piece_off[q], n0 + pc0, 0, cy, cn);
+            if ((MODE == 2 && a.pad_store) || (FLATWIN && a.img_tile)) tma_store_4d(&maps.out[q ? 1 : 0], src + a.piece_off[q], n0 + pc0, 0, cy, cn);
             else tma_store_2d(&maps.out[q ? 1 : 0], src + a.piece_off[q], n0 + pc0, cx);
             pc0 += a.piece_ch[q];
           }
@@ -1125,6 +1133,7 @@ struct WinPlan {
   long long tiles = 0;
   uint32_t stage_buf = 0;
   int nres = 0, nstage = 1;
+  bool img = false;  // mode 4: one image per tile (WinArgs::img_tile)
 };
 
 }  // namespace
@@ -1324,11 +1333,15 @@ plan:
           // flat padded raster: MT boxes of `bh` rows cover the tile and the RW + 1 positions either side of it
           p.tw = L.w; p.rw = wp; p.tstep = tm; p.tiles_per_strip = 0;
           p.bh = ((tm + 2 * wp + 2 + mt - 1) / mt + 7) / 8 * 8;
+          // 8-pixel-wide maps of 128 pixels (ReID layer 3): one image per tile, its rows picked by the descriptor's group stride
+          static const bool no_img_tile = getenv("AICAM_WIN_NO_IMG_TILE") != nullptr;
+          p.img = epi && mt == 1 && L.w == 8 && L.h * L.w == 128 && !no_img_tile;
+          if (p.img) p.bh = ((L.h - 1) * wp + L.w + 2 * wp + 2 + 7) / 8 * 8;
           if (p.bh > 256) continue;
           p.box_bytes = static_cast<uint32_t>(mt) * p.bh * row_bytes;
           (void)ilo;
           p.patch_bytes = (p.box_bytes + 1023) / 1024 * 1024;
-          p.tiles = (padded_pixels + tm - 1) / tm;
+          p.tiles = p.img ? L.batch : (padded_pixels + tm - 1) / tm;
           if (epi) {
             // the residual tile is loaded into the staging buffer and finished in place: no residual ring
             size_t buf = 0;
@@ -1488,6 +1501,7 @@ plan:
   }
   a.ws = (ws_ok && best.mt == 2) ? 1 : 0;
   a.pad_store = (epi && epi_pad2) ? 1 : 0;
+  a.img_tile = (mode == 4 && epi && best.img) ? 1 : 0;
   static const bool thread_arrive = getenv("AICAM_WIN_THREAD_ARRIVE") != nullptr;
   a.warp_arrive = thread_arrive ? 0 : 1;
   a.epi_alt = (!no_alt && epi && best.mt == 2 && n_tile <= 32 && best.nstage == 2 && (!res_mode || best.nres == 2) && !a.res_inplace) ? 1 : 0;
@@ -1542,7 +1556,7 @@ plan:
     for (int q = 0; q < std::min(a.pieces, 2) && cr == CUDA_SUCCESS; ++q) {  // (pieces beyond the second reuse map 1)
       const int pb = piece_ch[q] * 2;
       const CUtensorMapSwizzle psw = pb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (pb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-      if (a.pad_store) {
+      if (a.pad_store || a.img_tile) {
         // interiors of the zero-bordered output images: (channels, wo, ho, batch), rows (wo + border) pixels apart
         const int hwo = L.ho * L.wo;
         const cuuint64_t pd[4] = {static_cast<cuuint64_t>(pc.cout), static_cast<cuuint64_t>(L.wo), static_cast<cuuint64_t>(L.ho),
@@ -1555,6 +1569,13 @@ plan:
         __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(L.out) + L.out_coff + static_cast<long long>(olo) * (L.wo + oext + 1) * L.out_cstride;
         cr = get_encode_tiled()(&maps.out[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, obase, pd, ps, pbx, pe, CU_TENSOR_MAP_INTERLEAVE_NONE, psw,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr == CUDA_SUCCESS && res_mode) {  // (image tiles: the residual shares the output's zero-bordered layout)
+          const cuuint64_t rs[3] = {static_cast<cuuint64_t>(L.res_cstride) * 2, static_cast<cuuint64_t>(L.wo + oext) * L.res_cstride * 2,
+                                    static_cast<cuuint64_t>(L.res_img_stride) * 2};
+          const __nv_bfloat16* rbase = L.res + L.res_coff + static_cast<long long>(olo) * (L.wo + oext + 1) * L.res_cstride;
+          cr = get_encode_tiled()(&maps.res[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(rbase), pd, rs, pbx, pe,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, psw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
         continue;
       }
       if (!window) {

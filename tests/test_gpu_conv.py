@@ -90,6 +90,9 @@ PADDED_CASES = [
     ("pad_l2_128", 5, 32, 16, 128, 128, 3, 1, 2, 2, 1, 1),
     ("pad_l3_256", 9, 16, 8, 256, 256, 3, 1, 2, 2, 1, 1),
     ("pad_l3_256_nores", 3, 16, 8, 256, 256, 3, 1, 2, 0, 1, 1),
+    # 16 x 8 maps take one image per tile (descriptor group stride = one raster row): narrower layers, act(conv) + res
+    ("pad_16x8_64", 7, 16, 8, 64, 64, 3, 1, 1, 1, 1, 1),
+    ("pad_16x8_128_to_96", 4, 16, 8, 128, 96, 3, 1, 2, 2, 1, 1),
     ("pad_l4_512", 13, 8, 4, 512, 512, 3, 1, 2, 2, 1, 1),
     ("pad_one_image", 1, 8, 4, 64, 64, 3, 1, 1, 1, 1, 1),
     ("pad_odd_13x7_c64_96", 4, 13, 7, 64, 96, 3, 1, 0, 0, 1, 1),
