@@ -1,3 +1,5 @@
+# The evidence series of a round state (run through gpurun): every -m gpu test file, smoke(), every bench.py config and the reference arm,
+# the ncu launch list of one step (-> scripts/summarize_ncu.py traffic) and the in-graph timeline.  Outputs land in gpurun_out/.
 bash scripts/gpu_tests.sh > gpurun_out/tests_summary.txt 2>&1
 cat gpurun_out/tests_summary.txt
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc $?"; tail -1 gpurun_out/smoke.log
